@@ -1,0 +1,164 @@
+"""Oracle self-consistency (CPU only): every restated op is cross-checked against an
+independent implementation, since the reference ships no golden vectors."""
+import itertools
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import crnn_oracle as O
+
+
+def brute_force_ctc(logits_tc, lab, blank=0):
+    """-log sum over all alignments that collapse to lab (T<=5, C small)."""
+    T, C = logits_tc.shape
+    lp = logits_tc - np.log(np.exp(logits_tc).sum(1, keepdims=True))
+    tot = 0.0
+    for path in itertools.product(range(C), repeat=T):
+        col, prev = [], -1
+        for a in path:
+            if a != prev and a != blank:
+                col.append(a)
+            prev = a
+        if col == list(lab):
+            tot += math.exp(sum(lp[t, a] for t, a in enumerate(path)))
+    return -math.log(tot) if tot > 0 else float("inf")
+
+
+@pytest.mark.parametrize("lab", [[1], [1, 2], [2, 2], [1, 2, 1]])
+def test_ctc_brute_force(lab):
+    rng = np.random.default_rng(0)
+    T, C = 5, 4
+    x = rng.standard_normal((T, 1, C))
+    costs, _ = O.ctc_loss_np(x, lab, [len(lab)], [T])
+    assert abs(costs[0] - brute_force_ctc(x[:, 0], lab)) < 1e-10
+
+
+def test_ctc_infeasible_returns_zero():
+    x = np.random.default_rng(1).standard_normal((2, 1, 4))
+    costs, g = O.ctc_loss_np(x, [2, 2], [2], [2])      # needs 3 frames
+    assert costs[0] == 0.0 and np.all(g == 0)
+
+
+def test_ctc_vs_torch_and_grad():
+    rng = np.random.default_rng(2)
+    T, N, C = 21, 6, 64
+    x = rng.standard_normal((T, N, C)) * 2
+    ll = np.array([4, 5, 6, 4, 6, 5]); il = np.array([21, 20, 13, 21, 17, 12])
+    lab = rng.integers(1, 63, size=ll.sum()); lab[1] = lab[0]      # a repeat
+    costs, grad = O.ctc_loss_np(x, lab, ll, il)
+    xt = torch.tensor(x, requires_grad=True)
+    ct = O.ctc_loss_torch(xt, lab, ll, il)
+    ct.sum().backward()
+    assert np.allclose(costs, ct.detach().numpy(), atol=1e-9)
+    assert np.allclose(grad, xt.grad.numpy(), atol=1e-9)
+    # frames >= input_len get zero gradient
+    assert np.all(grad[13:, 2] == 0)
+
+
+def test_lstm_vs_torch_nn_lstm():
+    rng = np.random.default_rng(3)
+    N, T, D, H = 3, 7, 512, 256
+    x = torch.tensor(rng.standard_normal((N, T, D)) * 0.5)
+    w = torch.tensor(rng.standard_normal((D + H, 4 * H)) * 0.05)
+    b = torch.tensor(rng.standard_normal((4 * H,)) * 0.1)
+    lens = np.array([7, 4, 1])
+    for reverse in (False, True):
+        y = O.lstm_direction(x, lens, w, b, reverse)
+        # torch gate order i,f,g,o ; TF i,j(g),f,o ; forget bias +1
+        perm = torch.cat([torch.arange(0, H), torch.arange(2 * H, 3 * H), torch.arange(H, 2 * H), torch.arange(3 * H, 4 * H)])
+        lstm = torch.nn.LSTM(D, H, batch_first=True).double()
+        with torch.no_grad():
+            lstm.weight_ih_l0.copy_(w[:D, perm].t()); lstm.weight_hh_l0.copy_(w[D:, perm].t())
+            bb = b.clone(); bb[2 * H:3 * H] += 1.0
+            lstm.bias_ih_l0.copy_(bb[perm]); lstm.bias_hh_l0.zero_()
+        for n in range(N):
+            L = int(lens[n])
+            xs = x[n:n + 1, :L]
+            if reverse:
+                xs = xs.flip(1)
+            ref, _ = lstm(xs)
+            if reverse:
+                ref = ref.flip(1)
+            assert torch.allclose(y[n, :L], ref[0], atol=1e-10)
+            assert torch.all(y[n, L:] == 0)
+
+
+def test_forward_shapes_and_padding_contract():
+    p = O.to_torch(O.randomize_params(O.init_params(3)))
+    data, lab, ll, tsl = O.synth_batch(2, 88, seed=5, widths=[85, 60])
+    assert tsl.tolist() == [85 // 4 - 1, 60 // 4 - 1]
+    assert np.all(data[1, 60:] == 0)
+    logits, acts = O.forward(p, data, tsl, return_all=True)
+    assert logits.shape == (88 // 4 - 1, 2, 64)
+    assert acts["conv1"].shape == (2, 64, 44, 16)
+    assert acts["conv3_2"].shape == (2, 256, 22, 4)
+    assert acts["conv4_2"].shape == (2, 512, 22, 2)
+    assert acts["reshaped_layer"].shape == (2, 21, 512)
+    # frames past len: LSTM output zero -> logits == bias
+    b = p["logits/biases"]
+    assert torch.allclose(logits[tsl[1]:, 1], b.expand(21 - tsl[1], 64))
+
+
+def test_bn_matches_functional():
+    rng = np.random.default_rng(4)
+    x = torch.tensor(rng.standard_normal((3, 8, 5, 4)))
+    w = torch.tensor(rng.standard_normal((3, 3, 8, 6)) * 0.2)
+    b = torch.tensor(rng.standard_normal(6)); beta = torch.tensor(rng.standard_normal(6)); gamma = torch.tensor(rng.standard_normal(6))
+    y, _ = O.conv_single(x, w, b, (beta, gamma), relu=False)
+    z = F.conv2d(x, w.permute(3, 2, 0, 1), b, padding=1)
+    ref = F.batch_norm(z, None, None, gamma, beta, training=True, eps=1e-3)
+    assert torch.allclose(y, ref, atol=1e-12)
+
+
+def test_greedy_rule_table():
+    C = 64
+    def onehot(seq):
+        x = np.zeros((len(seq), 1, C)); 
+        for t, a in enumerate(seq): x[t, 0, a] = 5.0
+        return x
+    dec = lambda seq, L=None: O.greedy_decode(onehot(seq), [L or len(seq)])[0]
+    assert dec([5, 5, 63, 5, 0, 7]) == [5, 5, 7]          # repeat merged, 63 splits, 0 stripped
+    assert dec([63, 63, 63]) == []
+    assert dec([0, 0, 3, 3, 0, 3]) == [3, 3]              # 0 acts as separator (raw prev), then stripped
+    assert dec([1, 2, 3, 4], 2) == [1, 2]                 # honours input_len
+    x = np.zeros((1, 1, C)); assert O.greedy_decode(x, [1])[0] == []   # tie -> lowest index 0 -> stripped
+
+
+def test_accuracy_calculation():
+    assert O.accuracy_calculation([[1, 2, 0], [3]], [[1, 2], [3, 0, 0]]) == 1.0
+    assert O.accuracy_calculation([[1, 2], [3]], [[1, 2], [4]]) == 0.5
+    assert O.accuracy_calculation([[1]], [[1], [2]]) == 0
+
+
+def test_adam_and_clip_hand_computed():
+    p = {"a": torch.tensor([1.0, 2.0], dtype=torch.float64)}
+    g = {"a": torch.tensor([30.0, 40.0], dtype=torch.float64)}          # norm 50 -> scale 0.2
+    cg, gn = O.clip_by_global_norm(g, 10.0)
+    assert abs(gn - 50) < 1e-12 and torch.allclose(cg["a"], torch.tensor([6.0, 8.0], dtype=torch.float64))
+    m = {"a": torch.zeros(2, dtype=torch.float64)}; v = {"a": torch.zeros(2, dtype=torch.float64)}
+    p2, m, v = O.adam_step(dict(p), cg, m, v, 1, lr=1e-4)
+    lr_t = 1e-4 * math.sqrt(1 - 0.999) / (1 - 0.9)
+    exp0 = 1.0 - lr_t * 0.6 / (math.sqrt(0.001 * 36) + 1e-8)
+    assert abs(float(p2["a"][0]) - exp0) < 1e-15
+
+
+def test_finite_difference_full_graph():
+    """d loss / d param via autograd == central differences (fp64), tiny batch."""
+    pn = O.randomize_params(O.init_params(3, logits_scale=20.0))
+    batch = O.synth_batch(2, 24, seed=9, min_len=1, max_len=2)
+    out = O.train_step(pn, batch, wd=1e-2)
+    for name, idx in [("conv5/biases", (3,)), ("logits/weights", (7, 5)), ("conv4_1/conv4_1/gamma", (10,)),
+                      (O.LSTM_BW + "/weights", (600, 300)), ("conv2/weights", (1, 1, 3, 4))]:
+        eps = 1e-5
+        vals = []
+        for sgn in (+1, -1):
+            q = {k: v.copy() for k, v in pn.items()}
+            q[name][idx] += sgn * eps
+            loss, *_ = O.build_loss(O.to_torch(q), *[batch[0], batch[1], batch[2], batch[3]], wd=1e-2)
+            vals.append(float(loss))
+        fd = (vals[0] - vals[1]) / (2 * eps)
+        an = float(out["grads"][name][idx])
+        assert abs(fd - an) <= 1e-6 * max(1.0, abs(an)), (name, fd, an)
