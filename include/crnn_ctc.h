@@ -1,0 +1,120 @@
+/*
+ * crnn_ctc.h -- C ABI of libcrnnctc.so: the B200 (sm_100a) CRNN+CTC hot path that stands
+ * behind the model/solver API of ilovin/lstm_ctc_ocr.
+ *
+ * The reference has no C ABI of its own (it is pure Python on TensorFlow 1.0.1 + the
+ * warp-ctc TF binding).  Each entry point below names the reference call site it replaces
+ * (paths relative to the reference checkout).  Conventions follow warp-ctc's ctc.h:
+ * status-code returns, no exceptions across the ABI, caller-owned device buffers and
+ * workspace (size queried first), every call asynchronous on the caller's stream, no
+ * hidden host synchronisation.  All pointers are DEVICE pointers unless marked host.
+ * One host thread per handle (thread-compatible, not thread-safe).
+ */
+#ifndef CRNN_CTC_H_
+#define CRNN_CTC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* crnn_stream_t;   /* == cudaStream_t */
+typedef struct crnn_model crnn_model;
+
+enum crnn_status {
+  CRNN_OK = 0,
+  CRNN_INVALID_VALUE = 1,     /* bad shape / length / null pointer */
+  CRNN_CUDA_ERROR = 2,        /* a CUDA runtime/driver call failed; see crnn_last_error() */
+  CRNN_NOT_BOUND = 3,         /* model used before crnn_model_bind() */
+  CRNN_UNSUPPORTED = 4,       /* shape outside what the sm_100a kernels implement */
+  CRNN_WORKSPACE_TOO_SMALL = 5
+};
+
+int         crnn_version(void);
+const char* crnn_status_string(int status);
+const char* crnn_last_error(void);           /* host string, valid until the next failing call */
+
+/* ------------------------------------------------------------------------------------------
+ * CTC operator boundary.
+ * Replaces warpctc_tensorflow.ctc(activations, flat_labels, label_lengths, input_lengths)
+ * at lib/networks/network.py:653-654 (warp-ctc compute_ctc_loss semantics: softmax inside,
+ * blank label 0 by default, cost = -log p(l|x), zero gradient for frames >= input_length,
+ * infeasible alignment -> cost 0 and zero gradient).
+ *   logits      [T,N,C] f32, unnormalised, time-major (lib/networks/network.py:126-128)
+ *   grad        [T,N,C] f32 or NULL; receives grad_scale * d costs[n] / d logits
+ *   flat_labels [sum(label_len)] i32, label_len [N] i32, input_len [N] i32
+ *   costs       [N] f32
+ * max_label_len is a host-side upper bound on label_len[] (chooses the states-per-lane
+ * variant; labels longer than it make that sample's cost NaN).  C must be 64.
+ * ---------------------------------------------------------------------------------------- */
+int crnn_ctc_workspace_size(int T, int N, int C, int max_label_len, size_t* bytes);
+int crnn_ctc_loss(const float* logits, float* grad, const int* flat_labels, const int* label_len,
+                  const int* input_len, int T, int N, int C, int blank, int max_label_len,
+                  float grad_scale, float* costs, void* workspace, size_t workspace_bytes,
+                  crnn_stream_t stream);
+
+/* Greedy decode.  Replaces tf.nn.ctc_*_decoder(merge_repeated=True) + sparse_tensor_to_dense
+ * at lib/networks/network.py:656-657 and the zero stripping of lib/lstm/utils/training.py:32:
+ * per frame argmax (lowest index on ties) for t < input_len; emit iff != tf_blank and != the
+ * previous raw argmax; drop `strip`.  out [N,T] i32 zero padded, out_len [N] i32. */
+int crnn_ctc_greedy(const float* logits, const int* input_len, int T, int N, int C, int tf_blank,
+                    int strip, int* out, int* out_len, crnn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Model boundary.  Replaces the graph built by lib/networks/LSTM_train.py:22-38 through
+ * lib/networks/network.py (conv_single :160-191, max_pool :343-350, reshape_squeeze_layer
+ * :361-368, bi_lstm :97-129) and executed by sess.run at lib/lstm/train.py:129-130.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct crnn_config {
+  int   img_height;     /* cfg.IMG_HEIGHT = 32        (lib/lstm/config.py:19) */
+  int   nclasses;       /* cfg.NCLASSES   = 64        (lib/lstm/config.py:23) */
+  int   num_hid;        /* cfg.TRAIN.NUM_HID = 512    (lib/lstm/config.py:48) */
+  float bn_eps;         /* 1e-3  tf.contrib.layers.batch_norm default */
+  float weight_decay;   /* cfg.TRAIN.WEIGHT_DECAY (lstm/lstm.yml:13 -> 1e-5) */
+  int   compute_dtype;  /* 1 = bf16 operands / f32 accumulate (tcgen05 kind::f16) */
+} crnn_config;
+
+int     crnn_model_create(const crnn_config* cfg, crnn_model** out);
+int     crnn_model_destroy(crnn_model* m);
+
+/* Trainable tensors, addressable by TF variable name and laid out exactly as the reference
+ * checkpoint has them (HWIO conv kernels, [768,1024] LSTM matrices with gate order i,j,f,o;
+ * SURVEY §8(a)).  All live in ONE flat f32 buffer owned by the caller. */
+int     crnn_num_tensors(const crnn_model* m);
+int64_t crnn_param_count(const crnn_model* m);
+int     crnn_param_info(const crnn_model* m, int index, const char** tf_name, int64_t* offset,
+                        int64_t shape[4], int* ndim);
+/* Bind caller-owned flat buffers (each crnn_param_count() f32).  grads/adam_* may be NULL
+ * for inference.  Marks the derived bf16 operand copies dirty. */
+int     crnn_model_bind(crnn_model* m, float* params, float* grads, float* adam_m, float* adam_v);
+int     crnn_model_params_changed(crnn_model* m);   /* caller wrote params in place */
+
+int     crnn_model_workspace_size(const crnn_model* m, int N, int W, int train, size_t* bytes);
+
+/* data [N,W,32] f32 (width-major rows, lib/lstm/utils/gen.py:62-64), time_step_len [N] i32
+ * (nw//4-1, gen.py:54) -> logits_out [T=W/4-1, N, 64] f32. */
+int     crnn_forward(crnn_model* m, const float* data, const int* time_step_len, int N, int W,
+                     float* logits_out, void* workspace, size_t workspace_bytes,
+                     crnn_stream_t stream);
+
+/* loss = mean_n(costs) + weight_decay * 0.5 * sum(w^2) over conv kernels + logits matrix
+ * (lib/networks/network.py:655,660-662).  loss_out: 1 f32 on device. */
+int     crnn_total_loss(crnn_model* m, const float* costs, int N, float* loss_out,
+                        crnn_stream_t stream);
+
+/* Debug/parity taps: copy a named intermediate of the last crnn_forward() as f32 into dst.
+ * names: "conv1" "conv2" "conv3_1" "conv3_2" "conv4_1" "conv4_2" "conv5" "lstm_out"
+ * (pooled / post-activation, NHWC, as the reference's layers dict holds them). */
+int     crnn_debug_tap(crnn_model* m, const char* name, float* dst, size_t dst_elems,
+                       void* workspace, crnn_stream_t stream);
+
+/* Stand-alone bf16 GEMM test entry (tests only): D[M,Nc] f32 = A[M,K] * B[Nc,K]^T, bf16 in. */
+int     crnn_test_gemm_bf16(const void* A, const void* B, float* D, int M, int Nc, int K,
+                            int block_n, crnn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* CRNN_CTC_H_ */

@@ -1,0 +1,68 @@
+"""ctypes binding of libcrnnctc.so (include/crnn_ctc.h).  No CPU fallback: a missing or
+unloadable library raises immediately."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcrnnctc.so")
+
+c_int, c_float, c_size_t, c_void_p, c_char_p, c_int64 = (ctypes.c_int, ctypes.c_float, ctypes.c_size_t,
+                                                         ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64)
+
+
+class CrnnConfig(ctypes.Structure):
+    _fields_ = [("img_height", c_int), ("nclasses", c_int), ("num_hid", c_int), ("bn_eps", c_float),
+                ("weight_decay", c_float), ("compute_dtype", c_int)]
+
+
+# name -> (restype, argtypes); mirrors include/crnn_ctc.h one to one
+SIGNATURES = {
+    "crnn_version": (c_int, []),
+    "crnn_status_string": (c_char_p, [c_int]),
+    "crnn_last_error": (c_char_p, []),
+    "crnn_ctc_workspace_size": (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
+    "crnn_ctc_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                              c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "crnn_ctc_greedy": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "crnn_model_create": (c_int, [ctypes.POINTER(CrnnConfig), ctypes.POINTER(c_void_p)]),
+    "crnn_model_destroy": (c_int, [c_void_p]),
+    "crnn_num_tensors": (c_int, [c_void_p]),
+    "crnn_param_count": (c_int64, [c_void_p]),
+    "crnn_param_info": (c_int, [c_void_p, c_int, ctypes.POINTER(c_char_p), ctypes.POINTER(c_int64),
+                                ctypes.POINTER(c_int64 * 4), ctypes.POINTER(c_int)]),
+    "crnn_model_bind": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "crnn_model_params_changed": (c_int, [c_void_p]),
+    "crnn_model_workspace_size": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
+    "crnn_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "crnn_total_loss": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "crnn_debug_tap": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "crnn_test_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+}
+
+_lib = None
+
+
+class CrnnError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CrnnError(f"{LIB_PATH} is missing: run `python build.py` (or __graft_entry__.build()). "
+                        "There is no CPU fallback for this path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        lib = load()
+        raise CrnnError(f"{lib.crnn_status_string(status).decode()}: {lib.crnn_last_error().decode()}")

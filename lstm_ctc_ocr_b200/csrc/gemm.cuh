@@ -1,0 +1,468 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a with fused epilogues.
+//
+//   D[128 x BLOCK_N tile, f32 in TMEM] = A[rows x K] (bf16, K-major, TMA) * B[Nc x K]^T (bf16, K-major, TMA)
+//
+// Roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = tcgen05.mma issuer (one lane,
+// also owns the TMEM allocation), warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4).
+// Pipelines: STAGES-deep smem ring (full/empty mbarriers, TMA <-> MMA) and a 2-deep TMEM accumulator
+// ring (tmem_full/tmem_empty, MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// A-operand modes
+//   A_PLAIN  rows are consecutive rows of a 2-D [rows, K] tensor map; conv5 (2x2 VALID over [N,H,2,512]) reads
+//            row m for the first half of K and row m+1 for the second half (kb_per_shift).
+//   A_CONV3  implicit GEMM for a 3x3 SAME convolution over an NHWC activation [N, H, Wd, C]: a tile is
+//            4 sub-boxes of 32 output positions (bh = 32/Wd rows of H x full Wd); K-block kb = tap (r,s) x
+//            64-channel block; the producer issues one 4-D TMA box per sub-box at coordinates shifted by
+//            (r-1, s-1) -- out-of-bounds elements are zero-filled by TMA, which *is* the SAME padding.
+//
+// Epilogues: see enum Epi.  Every epilogue thread owns one accumulator row (TMEM lane).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace gemm {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;                      // bf16 elements per K-block = one 128 B swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BLOCK_M * 128;     // 16 KB
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARP0 = 2;
+
+enum AMode { A_PLAIN = 0, A_CONV3 = 1 };
+enum Epi {
+  EPI_F32 = 0,          // D f32 row-major [M, Nc] (tests)
+  EPI_BIAS_BF16 = 1,    // + bias -> bf16 row-major [M, ldo]            (conv5, LSTM input projection)
+  EPI_RELU = 2,         // conv: + bias, ReLU -> bf16 NHWC              (conv3_1)
+  EPI_RELU_POOL22 = 3,  // conv: + bias, ReLU, 2x2/2 max-pool           (conv2 + pool2), needs Wd=16
+  EPI_RELU_POOL12 = 4,  // conv: + bias, ReLU, max over Wd pairs        (conv3_2 + pool), needs Wd=8
+  EPI_STATS = 5,        // conv: + bias -> bf16 pre-BN, per-channel sum / sum^2 (f64 atomics) (conv4_x)
+  EPI_LSTM = 6,         // recurrent step: gates = acc + xproj; LSTM cell; writes h, c, output
+  EPI_LOGITS = 7        // + bias -> f32 time-major [T, N, 64]
+};
+
+struct Params {
+  int num_m_tiles, num_n_tiles, num_k_blocks;
+  int kb_per_shift;      // A_PLAIN: K-block kb reads A columns (kb % kb_per_shift)*64 of row (m + kb / kb_per_shift);
+                         // == num_k_blocks for an ordinary GEMM; conv5 (2x2 VALID) uses 16 -> rows t and t+1
+  int M;                 // valid rows (plain modes)
+  int Nc;                // total output columns
+  // conv geometry (A_CONV3 and conv epilogues)
+  int cin_blocks;        // Cin / 64
+  int sb_per_img;        // ceil(H / bh)
+  int bh, Wd, H, Nimg;
+  // epilogue
+  const float* bias;     // [Nc]
+  void* out;             // primary output
+  int ldo;               // row stride of `out` in elements (plain modes)
+  double* stats;         // [2][Nc] (EPI_STATS)
+  // EPI_LSTM
+  const __nv_bfloat16* xproj;   // [Nimg*H, 2048] gate pre-activations (x part + bias), permuted columns
+  float* c_state;               // [2][Npad][256]
+  __nv_bfloat16* h_next;        // [2][Npad][256]
+  __nv_bfloat16* lstm_out;      // [Nimg*H, 512]
+  const int* seq_len;           // [Nimg]
+  int step, Npad, m_tiles_per_dir, T;
+};
+
+__device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
+  // Sum over the 32 lanes of a warp for each of 32 per-lane registers; lane l returns column l's total.
+  float r16[16], r8[8], r4[4], r2[2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float send = (lane & 16) ? v[i] : v[i + 16];
+    float keep = (lane & 16) ? v[i + 16] : v[i];
+    r16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float send = (lane & 8) ? r16[i] : r16[i + 8];
+    float keep = (lane & 8) ? r16[i + 8] : r16[i];
+    r8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float send = (lane & 4) ? r8[i] : r8[i + 4];
+    float keep = (lane & 4) ? r8[i + 4] : r8[i];
+    r4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float send = (lane & 2) ? r4[i] : r4[i + 2];
+    float keep = (lane & 2) ? r4[i + 2] : r4[i];
+    r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  float send = (lane & 1) ? r2[0] : r2[1];
+  float keep = (lane & 1) ? r2[1] : r2[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+template <int BLOCK_N, int STAGES>
+struct Smem {
+  static constexpr int B_STAGE_BYTES = BLOCK_N * 128;
+  static constexpr int BAR_OFFSET = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+  static constexpr int BYTES = BAR_OFFSET + 256 + 1024;   // barriers + alignment slack
+};
+
+template <int BLOCK_N, int AMODE, int EPI, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  static_assert(BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
+  constexpr int B_STAGE_BYTES = BLOCK_N * 128;
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;        // power of two >= 32
+  constexpr uint32_t IDESC = ptx::make_idesc_bf16(BLOCK_M, BLOCK_N);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Smem<BLOCK_N, STAGES>::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp_idx == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tmem_full[s], 1);
+      ptx::mbar_init(&tmem_empty[s], 4);   // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp_idx == 1) {
+    ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+        int b_row = n_blk * BLOCK_N;
+        if (EPI == EPI_LSTM) b_row += (m_blk >= p.m_tiles_per_dir) ? 1024 : 0;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+          uint8_t* a_dst = smem_a + stage * A_STAGE_BYTES;
+          if (AMODE == A_PLAIN) {
+            const int rs = kb / p.kb_per_shift, kc = kb - rs * p.kb_per_shift;
+            ptx::tma_load_2d(&tmA, &full_bar[stage], a_dst, kc * BLOCK_K, m_blk * BLOCK_M + rs);
+          } else {
+            const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
+            const int r = tap / 3, s = tap - 3 * r;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int g = m_blk * 4 + j;
+              const int n = g / p.sb_per_img;
+              const int h0 = (g - n * p.sb_per_img) * p.bh;
+              ptx::tma_load_4d(&tmA, &full_bar[stage], a_dst + j * 4096, cb * BLOCK_K, s - 1, h0 + r - 1, n);
+            }
+          }
+          ptx::tma_load_2d(&tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, b_row);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t a_desc = ptx::make_desc_k_sw128(ptx::smem_u32(smem_a + stage * A_STAGE_BYTES));
+          const uint64_t b_desc = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b + stage * B_STAGE_BYTES));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            ptx::mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0);
+          }
+          ptx::tc_commit(&empty_bar[stage]);         // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::tc_commit(&tmem_full[acc]);             // accumulator complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp_idx & 3;                      // TMEM lane quadrant accessible to this warp
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+      const int col0 = n_blk * BLOCK_N;
+
+      // ---- conv row geometry (one sub-box of 32 positions per warp)
+      int n_img = 0, h = 0, w = 0;
+      bool valid = true;
+      if (EPI == EPI_RELU || EPI == EPI_RELU_POOL22 || EPI == EPI_RELU_POOL12 || EPI == EPI_STATS) {
+        const int g = m_blk * 4 + q;
+        n_img = g / p.sb_per_img;
+        const int hb = g - n_img * p.sb_per_img;
+        const int hl = lane / p.Wd;
+        w = lane - hl * p.Wd;
+        h = hb * p.bh + hl;
+        valid = (n_img < p.Nimg) && (h < p.H);
+      }
+
+      if (EPI == EPI_F32) {
+        const int grow = m_blk * BLOCK_M + row;
+        float* out = reinterpret_cast<float*>(p.out) + (size_t)grow * p.Nc + col0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(tbase + c0, v);
+          ptx::tmem_ld_wait();
+          if (grow < p.M) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<uint4*>(out + c0 + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+        }
+      } else if (EPI == EPI_BIAS_BF16) {
+        const int grow = m_blk * BLOCK_M + row;
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)grow * p.ldo + col0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(tbase + c0, v);
+          ptx::tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c0 + i));
+            pk[i / 2] = ptx::pack_bf16x2(__uint_as_float(v[i]) + b.x, __uint_as_float(v[i + 1]) + b.y);
+            pk[i / 2 + 1] = ptx::pack_bf16x2(__uint_as_float(v[i + 2]) + b.z, __uint_as_float(v[i + 3]) + b.w);
+          }
+          if (grow < p.M) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              *reinterpret_cast<uint4*>(out + c0 + 2 * i) = make_uint4(pk[i], pk[i + 1], pk[i + 2], pk[i + 3]);
+          }
+        }
+      } else if (EPI == EPI_LOGITS) {
+        const int grow = m_blk * BLOCK_M + row;
+        const int n = grow / p.H, t = grow - n * p.H;
+        const bool ok = (grow < p.M) && (t < p.T);
+        float* out = reinterpret_cast<float*>(p.out) + ((size_t)t * p.Nimg + n) * p.Nc + col0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(tbase + c0, v);
+          ptx::tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c0 + i));
+              *reinterpret_cast<float4*>(out + c0 + i) =
+                  make_float4(__uint_as_float(v[i]) + b.x, __uint_as_float(v[i + 1]) + b.y,
+                              __uint_as_float(v[i + 2]) + b.z, __uint_as_float(v[i + 3]) + b.w);
+            }
+          }
+        }
+      } else if (EPI == EPI_RELU || EPI == EPI_RELU_POOL22 || EPI == EPI_RELU_POOL12) {
+        __nv_bfloat16* outb = reinterpret_cast<__nv_bfloat16*>(p.out);
+        size_t off;
+        if (EPI == EPI_RELU) off = (((size_t)n_img * p.H + h) * p.Wd + w) * p.Nc;
+        else if (EPI == EPI_RELU_POOL22) off = (((size_t)n_img * (p.H >> 1) + (h >> 1)) * (p.Wd >> 1) + (w >> 1)) * p.Nc;
+        else off = (((size_t)n_img * p.H + h) * (p.Wd >> 1) + (w >> 1)) * p.Nc;
+        __nv_bfloat16* out = outb + off + col0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(tbase + c0, v);
+          ptx::tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c0 + i));
+            pk[i / 2] = ptx::pack_bf16x2(fmaxf(__uint_as_float(v[i]) + b.x, 0.f), fmaxf(__uint_as_float(v[i + 1]) + b.y, 0.f));
+            pk[i / 2 + 1] = ptx::pack_bf16x2(fmaxf(__uint_as_float(v[i + 2]) + b.z, 0.f), fmaxf(__uint_as_float(v[i + 3]) + b.w, 0.f));
+          }
+          if (EPI == EPI_RELU) {
+            if (valid) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<uint4*>(out + c0 + 2 * i) = make_uint4(pk[i], pk[i + 1], pk[i + 2], pk[i + 3]);
+            }
+          } else if (EPI == EPI_RELU_POOL22) {
+            // lane = hl*16 + w : partners lane^1 (w pair) and lane^16 (h pair); rounding to bf16 is monotonic,
+            // so max after packing == packing after max
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              pk[i] = ptx::hmax2_bf16(pk[i], __shfl_xor_sync(0xffffffffu, pk[i], 1));
+              pk[i] = ptx::hmax2_bf16(pk[i], __shfl_xor_sync(0xffffffffu, pk[i], 16));
+            }
+            const int sub = (lane & 1) | ((lane >> 3) & 2);     // which quarter of the 32 columns this lane stores
+            uint4 o;
+            o.x = sub == 0 ? pk[0] : sub == 1 ? pk[4] : sub == 2 ? pk[8] : pk[12];
+            o.y = sub == 0 ? pk[1] : sub == 1 ? pk[5] : sub == 2 ? pk[9] : pk[13];
+            o.z = sub == 0 ? pk[2] : sub == 1 ? pk[6] : sub == 2 ? pk[10] : pk[14];
+            o.w = sub == 0 ? pk[3] : sub == 1 ? pk[7] : sub == 2 ? pk[11] : pk[15];
+            if (valid) *reinterpret_cast<uint4*>(out + c0 + 8 * sub) = o;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = ptx::hmax2_bf16(pk[i], __shfl_xor_sync(0xffffffffu, pk[i], 1));
+            const int sub = lane & 1;
+            uint4 o0, o1;
+            o0.x = sub ? pk[8] : pk[0];  o0.y = sub ? pk[9] : pk[1];  o0.z = sub ? pk[10] : pk[2]; o0.w = sub ? pk[11] : pk[3];
+            o1.x = sub ? pk[12] : pk[4]; o1.y = sub ? pk[13] : pk[5]; o1.z = sub ? pk[14] : pk[6]; o1.w = sub ? pk[15] : pk[7];
+            if (valid) {
+              *reinterpret_cast<uint4*>(out + c0 + 16 * sub) = o0;
+              *reinterpret_cast<uint4*>(out + c0 + 16 * sub + 8) = o1;
+            }
+          }
+        }
+      } else if (EPI == EPI_STATS) {
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (((size_t)n_img * p.H + h) * p.Wd + w) * p.Nc + col0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(tbase + c0, v);
+          ptx::tmem_ld_wait();
+          float f[32], f2[32];
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c0 + i));
+            f[i] = __uint_as_float(v[i]) + b.x;
+            f[i + 1] = __uint_as_float(v[i + 1]) + b.y;
+            f[i + 2] = __uint_as_float(v[i + 2]) + b.z;
+            f[i + 3] = __uint_as_float(v[i + 3]) + b.w;
+            pk[i / 2] = ptx::pack_bf16x2(f[i], f[i + 1]);
+            pk[i / 2 + 1] = ptx::pack_bf16x2(f[i + 2], f[i + 3]);
+          }
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              *reinterpret_cast<uint4*>(out + c0 + 2 * i) = make_uint4(pk[i], pk[i + 1], pk[i + 2], pk[i + 3]);
+          }
+          // statistics of the values the next layer will actually read (bf16-rounded), masked to valid rows
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float a = valid ? ptx::bf16_lo(pk[i]) : 0.f, b = valid ? ptx::bf16_hi(pk[i]) : 0.f;
+            f[2 * i] = a; f[2 * i + 1] = b;
+            f2[2 * i] = a * a; f2[2 * i + 1] = b * b;
+          }
+          const float s1 = warp_colsum32(f, lane);
+          const float s2 = warp_colsum32(f2, lane);
+          atomicAdd(p.stats + col0 + c0 + lane, (double)s1);
+          atomicAdd(p.stats + p.Nc + col0 + c0 + lane, (double)s2);
+        }
+      } else if (EPI == EPI_LSTM) {
+        // row = sample within the direction-stacked batch; tile columns = [i(64) j(64) f(64) o(64)] of 64 units
+        const int grow = m_blk * BLOCK_M + row;
+        const int dir = (m_blk >= p.m_tiles_per_dir) ? 1 : 0;
+        const int n = grow - dir * p.Npad;
+        const bool okn = n < p.Nimg;
+        const int len = okn ? min(max(__ldg(p.seq_len + n), 0), p.T) : 0;
+        const bool active = p.step < len;
+        const int t = active ? (dir ? (len - 1 - p.step) : p.step) : p.step;
+        const size_t rt = (size_t)n * p.H + t;
+        const __nv_bfloat16* xp = p.xproj + rt * 2048 + dir * 1024 + n_blk * 256;
+        float* cst = p.c_state + ((size_t)dir * p.Npad + n) * 256 + n_blk * 64;
+        __nv_bfloat16* hn = p.h_next + ((size_t)dir * p.Npad + n) * 256 + n_blk * 64;
+        __nv_bfloat16* lo = p.lstm_out + rt * 512 + dir * 256 + n_blk * 64;
+#pragma unroll 1
+        for (int u0 = 0; u0 < 64; u0 += 16) {
+          uint32_t gi[16], gj[16], gf[16], go[16];
+          ptx::tmem_ld_32x32b_x16(tbase + u0, gi);
+          ptx::tmem_ld_32x32b_x16(tbase + 64 + u0, gj);
+          ptx::tmem_ld_32x32b_x16(tbase + 128 + u0, gf);
+          ptx::tmem_ld_32x32b_x16(tbase + 192 + u0, go);
+          ptx::tmem_ld_wait();
+          uint32_t hp[8];
+          if (active) {
+            uint4 xi[2], xj[2], xf[2], xo[2];
+            float4 cp[4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              xi[i] = __ldg(reinterpret_cast<const uint4*>(xp + u0) + i);
+              xj[i] = __ldg(reinterpret_cast<const uint4*>(xp + 64 + u0) + i);
+              xf[i] = __ldg(reinterpret_cast<const uint4*>(xp + 128 + u0) + i);
+              xo[i] = __ldg(reinterpret_cast<const uint4*>(xp + 192 + u0) + i);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cp[i] = *(reinterpret_cast<const float4*>(cst + u0) + i);
+            const uint32_t* xiw = reinterpret_cast<const uint32_t*>(xi);
+            const uint32_t* xjw = reinterpret_cast<const uint32_t*>(xj);
+            const uint32_t* xfw = reinterpret_cast<const uint32_t*>(xf);
+            const uint32_t* xow = reinterpret_cast<const uint32_t*>(xo);
+            float* cpf = reinterpret_cast<float*>(cp);
+            float hv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float zi = __uint_as_float(gi[i]) + ((i & 1) ? ptx::bf16_hi(xiw[i >> 1]) : ptx::bf16_lo(xiw[i >> 1]));
+              const float zj = __uint_as_float(gj[i]) + ((i & 1) ? ptx::bf16_hi(xjw[i >> 1]) : ptx::bf16_lo(xjw[i >> 1]));
+              const float zf = __uint_as_float(gf[i]) + ((i & 1) ? ptx::bf16_hi(xfw[i >> 1]) : ptx::bf16_lo(xfw[i >> 1]));
+              const float zo = __uint_as_float(go[i]) + ((i & 1) ? ptx::bf16_hi(xow[i >> 1]) : ptx::bf16_lo(xow[i >> 1]));
+              // forget_bias (+1.0) is folded into the projected bias at weight-prep time
+              const float c = ptx::fast_sigmoid(zf) * cpf[i] + ptx::fast_sigmoid(zi) * ptx::fast_tanh(zj);
+              cpf[i] = c;
+              hv[i] = ptx::fast_sigmoid(zo) * ptx::fast_tanh(c);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) *(reinterpret_cast<float4*>(cst + u0) + i) = cp[i];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hp[i] = ptx::pack_bf16x2(hv[2 * i], hv[2 * i + 1]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hp[i] = 0u;    // zero output past sequence_length; state no longer used
+          }
+          if (okn) {
+            *reinterpret_cast<uint4*>(hn + u0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+            *reinterpret_cast<uint4*>(hn + u0 + 8) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+            *reinterpret_cast<uint4*>(lo + u0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+            *reinterpret_cast<uint4*>(lo + u0 + 8) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+          }
+        }
+      }
+
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace gemm

@@ -1,0 +1,496 @@
+// Host side of libcrnnctc.so: model handle, parameter table (TF variable names/layouts), workspace plan,
+// TMA tensor maps, forward orchestration.  Graph restated from lib/networks/LSTM_train.py:22-38.
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+int crnn_fail(int status, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return status;
+}
+extern "C" const char* crnn_last_error(void) { return g_err; }
+extern "C" int crnn_version(void) { return 100; }
+extern "C" const char* crnn_status_string(int s) {
+  switch (s) {
+    case CRNN_OK: return "CRNN_OK";
+    case CRNN_INVALID_VALUE: return "CRNN_INVALID_VALUE";
+    case CRNN_CUDA_ERROR: return "CRNN_CUDA_ERROR";
+    case CRNN_NOT_BOUND: return "CRNN_NOT_BOUND";
+    case CRNN_UNSUPPORTED: return "CRNN_UNSUPPORTED";
+    case CRNN_WORKSPACE_TOO_SMALL: return "CRNN_WORKSPACE_TOO_SMALL";
+  }
+  return "CRNN_UNKNOWN";
+}
+
+// ------------------------------------------------------------------------------------------------ TMA maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 map over [rows, cols] with arbitrary row stride (elements); box = [64 cols, box_rows], 128B swizzle.
+static int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride,
+                        uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return crnn_fail(CRNN_CUDA_ERROR, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return crnn_fail(CRNN_CUDA_ERROR, "cuTensorMapEncodeTiled(2d) failed: %d", (int)r);
+  return CRNN_OK;
+}
+// 4-D bf16 map over NHWC [N, H, Wd, C]; box = [64 ch, Wd, bh, 1]; OOB (halo) elements read as zero.
+static int make_tmap_nhwc(CUtensorMap* m, const void* base, int N, int H, int Wd, int C, int bh) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return crnn_fail(CRNN_CUDA_ERROR, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wd, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wd * C * 2, (cuuint64_t)H * Wd * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)Wd, (cuuint32_t)bh, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return crnn_fail(CRNN_CUDA_ERROR, "cuTensorMapEncodeTiled(4d) failed: %d", (int)r);
+  return CRNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ model
+struct TensorInfo {
+  std::string name;
+  int ndim;
+  int64_t shape[4];
+  int64_t offset;
+  int64_t count;
+};
+
+struct ConvSpec { const char* name; int kh, kw, ci, co; bool bn; };
+static const ConvSpec kConvs[7] = {   // lib/networks/LSTM_train.py:24-34
+    {"conv1", 3, 3, 1, 64, false},    {"conv2", 3, 3, 64, 128, false},  {"conv3_1", 3, 3, 128, 256, false},
+    {"conv3_2", 3, 3, 256, 256, false}, {"conv4_1", 3, 3, 256, 512, true}, {"conv4_2", 3, 3, 512, 512, true},
+    {"conv5", 2, 2, 512, 512, false}};
+
+struct Plan {
+  int N = 0, W = 0, H1 = 0, H2 = 0, T = 0, Npad = 0;
+  void* ws = nullptr;
+  __nv_bfloat16 *a1, *a2, *a3, *a3p, *a4a_pre, *a4a, *a4b_pre, *a4b, *a5, *xproj, *lstm_out, *h_state;
+  float* c_state;
+  double* stats;        // [2 layers][2][512]
+  float* bn;            // [2 layers][4][512]: scale, shift, mean, invstd
+  CUtensorMap tA_c2, tA_c31, tA_c32, tA_c41, tA_c42, tA_c5, tA_x, tA_h[2], tA_l;
+};
+
+struct crnn_model {
+  crnn_config cfg;
+  int num_sms = 148;
+  std::vector<TensorInfo> tensors;
+  int64_t total = 0;
+  float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+  bool dirty = true;
+  // bf16 K-major operand copies of the weights (B matrices [Cout][K])
+  __nv_bfloat16 *Bc2 = nullptr, *Bc31, *Bc32, *Bc41, *Bc42, *Bc5, *Bx, *Bh, *Bl;
+  float* xbias = nullptr;    // [2048] permuted LSTM bias with forget_bias folded in
+  double* sumsq = nullptr;
+  void* wblock = nullptr;
+  CUtensorMap tB_c2, tB_c31, tB_c32, tB_c41, tB_c42, tB_c5, tB_x, tB_h, tB_l;
+  Plan plan;
+
+  const TensorInfo* find(const std::string& n) const {
+    for (auto& t : tensors) if (t.name == n) return &t;
+    return nullptr;
+  }
+  float* P(const std::string& n) const { return params + find(n)->offset; }
+};
+
+static void add_tensor(crnn_model* m, const std::string& name, std::initializer_list<int64_t> shp) {
+  TensorInfo t;
+  t.name = name;
+  t.ndim = (int)shp.size();
+  t.count = 1;
+  int i = 0;
+  for (int k = 0; k < 4; ++k) t.shape[k] = 1;
+  for (auto s : shp) { t.shape[i++] = s; t.count *= s; }
+  t.offset = m->total;
+  m->total += t.count;
+  m->tensors.push_back(t);
+}
+
+extern "C" int crnn_model_create(const crnn_config* cfg, crnn_model** out) {
+  if (!cfg || !out) return crnn_fail(CRNN_INVALID_VALUE, "model_create: null");
+  if (cfg->img_height != 32 || cfg->nclasses != 64 || cfg->num_hid != 512)
+    return crnn_fail(CRNN_UNSUPPORTED, "model_create: only IMG_HEIGHT=32, NCLASSES=64, NUM_HID=512 (the reference's net)");
+  if (cfg->compute_dtype != 1) return crnn_fail(CRNN_UNSUPPORTED, "model_create: compute_dtype must be 1 (bf16)");
+  crnn_model* m = new crnn_model();
+  m->cfg = *cfg;
+  for (auto& c : kConvs) {
+    add_tensor(m, std::string(c.name) + "/weights", {c.kh, c.kw, c.ci, c.co});
+    add_tensor(m, std::string(c.name) + "/biases", {c.co});
+    if (c.bn) {
+      add_tensor(m, std::string(c.name) + "/" + c.name + "/beta", {c.co});
+      add_tensor(m, std::string(c.name) + "/" + c.name + "/gamma", {c.co});
+    }
+  }
+  for (const char* d : {"fw", "bw"}) {
+    std::string s = std::string("logits/bidirectional_rnn/") + d + "/lstm_cell";
+    add_tensor(m, s + "/weights", {768, 1024});
+    add_tensor(m, s + "/biases", {1024});
+  }
+  add_tensor(m, "logits/weights", {512, 64});
+  add_tensor(m, "logits/biases", {64});
+
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    delete m;
+    return crnn_fail(CRNN_CUDA_ERROR, "model_create: no CUDA device (this library has no CPU fallback)");
+  }
+  if (prop.major != 10) {
+    delete m;
+    return crnn_fail(CRNN_UNSUPPORTED, "model_create: needs sm_100 (found sm_%d%d)", prop.major, prop.minor);
+  }
+  m->num_sms = prop.multiProcessorCount;
+
+  // one allocation for all derived operand copies
+  const size_t nB[9] = {128 * 576, 256 * 1152, 256 * 2304, 512 * 2304, 512 * 4608, 512 * 2048, 2048 * 512, 2048 * 256, 64 * 512};
+  size_t tot = 0;
+  for (size_t v : nB) tot += (v * 2 + 1023) / 1024 * 1024;
+  tot += 2048 * 4 + 1024;
+  if (cudaMalloc(&m->wblock, tot) != cudaSuccess) { delete m; return crnn_fail(CRNN_CUDA_ERROR, "model_create: cudaMalloc"); }
+  uint8_t* p = reinterpret_cast<uint8_t*>(m->wblock);
+  __nv_bfloat16** dst[9] = {&m->Bc2, &m->Bc31, &m->Bc32, &m->Bc41, &m->Bc42, &m->Bc5, &m->Bx, &m->Bh, &m->Bl};
+  for (int i = 0; i < 9; ++i) { *dst[i] = reinterpret_cast<__nv_bfloat16*>(p); p += (nB[i] * 2 + 1023) / 1024 * 1024; }
+  m->xbias = reinterpret_cast<float*>(p); p += 2048 * 4;
+  m->sumsq = reinterpret_cast<double*>(p);
+  int st = CRNN_OK;
+  if (st == CRNN_OK) st = make_tmap_2d(&m->tB_c2, m->Bc2, 128, 576, 576, 128);
+  if (st == CRNN_OK) st = make_tmap_2d(&m->tB_c31, m->Bc31, 256, 1152, 1152, 256);
+  if (st == CRNN_OK) st = make_tmap_2d(&m->tB_c32, m->Bc32, 256, 2304, 2304, 256);
+  if (st == CRNN_OK) st = make_tmap_2d(&m->tB_c41, m->Bc41, 512, 2304, 2304, 256);
+  if (st == CRNN_OK) st = make_tmap_2d(&m->tB_c42, m->Bc42, 512, 4608, 4608, 256);
+  if (st == CRNN_OK) st = make_tmap_2d(&m->tB_c5, m->Bc5, 512, 2048, 2048, 256);
+  if (st == CRNN_OK) st = make_tmap_2d(&m->tB_x, m->Bx, 2048, 512, 512, 256);
+  if (st == CRNN_OK) st = make_tmap_2d(&m->tB_h, m->Bh, 2048, 256, 256, 256);
+  if (st == CRNN_OK) st = make_tmap_2d(&m->tB_l, m->Bl, 64, 512, 512, 64);
+  if (st != CRNN_OK) { cudaFree(m->wblock); delete m; return st; }
+  *out = m;
+  return CRNN_OK;
+}
+
+extern "C" int crnn_model_destroy(crnn_model* m) {
+  if (!m) return CRNN_OK;
+  if (m->wblock) cudaFree(m->wblock);
+  delete m;
+  return CRNN_OK;
+}
+extern "C" int crnn_num_tensors(const crnn_model* m) { return m ? (int)m->tensors.size() : 0; }
+extern "C" int64_t crnn_param_count(const crnn_model* m) { return m ? m->total : 0; }
+extern "C" int crnn_param_info(const crnn_model* m, int index, const char** tf_name, int64_t* offset, int64_t shape[4],
+                               int* ndim) {
+  if (!m || index < 0 || index >= (int)m->tensors.size()) return crnn_fail(CRNN_INVALID_VALUE, "param_info: bad index");
+  const TensorInfo& t = m->tensors[index];
+  if (tf_name) *tf_name = t.name.c_str();
+  if (offset) *offset = t.offset;
+  if (shape) for (int k = 0; k < 4; ++k) shape[k] = t.shape[k];
+  if (ndim) *ndim = t.ndim;
+  return CRNN_OK;
+}
+extern "C" int crnn_model_bind(crnn_model* m, float* params, float* grads, float* adam_m, float* adam_v) {
+  if (!m || !params) return crnn_fail(CRNN_INVALID_VALUE, "model_bind: null params");
+  m->params = params; m->grads = grads; m->adam_m = adam_m; m->adam_v = adam_v;
+  m->dirty = true;
+  return CRNN_OK;
+}
+extern "C" int crnn_model_params_changed(crnn_model* m) {
+  if (!m) return crnn_fail(CRNN_INVALID_VALUE, "null model");
+  m->dirty = true;
+  return CRNN_OK;
+}
+
+// f32 TF-layout parameters -> bf16 K-major GEMM operands (B[co][(kh,kw,ci)] == transpose of HWIO flattened)
+static int prepare_weights(crnn_model* m, cudaStream_t st) {
+  struct { const char* n; __nv_bfloat16* d; int R, C; } cv[6] = {
+      {"conv2/weights", m->Bc2, 576, 128},    {"conv3_1/weights", m->Bc31, 1152, 256}, {"conv3_2/weights", m->Bc32, 2304, 256},
+      {"conv4_1/weights", m->Bc41, 2304, 512}, {"conv4_2/weights", m->Bc42, 4608, 512}, {"conv5/weights", m->Bc5, 2048, 512}};
+  for (auto& c : cv) CRNN_TRY(launch_transpose_cast(m->P(c.n), c.R, c.C, c.C, c.d, c.R, 0, st));
+  const char* dirs[2] = {"logits/bidirectional_rnn/fw/lstm_cell", "logits/bidirectional_rnn/bw/lstm_cell"};
+  for (int d = 0; d < 2; ++d) {
+    const float* w = m->P(std::string(dirs[d]) + "/weights");                 // [768,1024], rows [x(512); h(256)]
+    CRNN_TRY(launch_transpose_cast(w, 512, 1024, 1024, m->Bx + (size_t)d * 1024 * 512, 512, 1, st));
+    CRNN_TRY(launch_transpose_cast(w + 512 * 1024, 256, 1024, 1024, m->Bh + (size_t)d * 1024 * 256, 256, 1, st));
+  }
+  CRNN_TRY(launch_lstm_bias_prep(m->P(std::string(dirs[0]) + "/biases"), m->P(std::string(dirs[1]) + "/biases"), m->xbias, st));
+  CRNN_TRY(launch_transpose_cast(m->P("logits/weights"), 512, 64, 64, m->Bl, 512, 0, st));
+  // L2 term depends only on the parameters: computed here, consumed by crnn_total_loss
+  SumsqSegs segs;
+  segs.n = 0;
+  for (auto& c : kConvs) {
+    const TensorInfo* t = m->find(std::string(c.name) + "/weights");
+    segs.off[segs.n] = t->offset; segs.cnt[segs.n] = t->count; segs.n++;
+  }
+  const TensorInfo* t = m->find("logits/weights");
+  segs.off[segs.n] = t->offset; segs.cnt[segs.n] = t->count; segs.n++;
+  CRNN_TRY(launch_sumsq(m->params, segs, m->sumsq, st));
+  m->dirty = false;
+  return CRNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ workspace
+static size_t align_up(size_t v, size_t a = 1024) { return (v + a - 1) / a * a; }
+
+static size_t layout_plan(Plan& pl, int N, int W, uint8_t* base) {
+  pl.N = N; pl.W = W; pl.H1 = W / 2; pl.H2 = W / 4; pl.T = W / 4 - 1;
+  pl.Npad = (N + 127) / 128 * 128;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { uint8_t* p = base ? base + off : nullptr; off += align_up(bytes); return p; };
+  const size_t n = N, h1 = pl.H1, h2 = pl.H2;
+  pl.a1 = (__nv_bfloat16*)take(n * h1 * 16 * 64 * 2);
+  pl.a2 = (__nv_bfloat16*)take(n * h2 * 8 * 128 * 2);
+  pl.a3 = (__nv_bfloat16*)take(n * h2 * 8 * 256 * 2);
+  pl.a3p = (__nv_bfloat16*)take(n * h2 * 4 * 256 * 2);
+  pl.a4a_pre = (__nv_bfloat16*)take(n * h2 * 4 * 512 * 2);
+  pl.a4a = (__nv_bfloat16*)take(n * h2 * 4 * 512 * 2);
+  pl.a4b_pre = (__nv_bfloat16*)take(n * h2 * 4 * 512 * 2);
+  pl.a4b = (__nv_bfloat16*)take(n * h2 * 2 * 512 * 2);
+  pl.a5 = (__nv_bfloat16*)take(n * h2 * 512 * 2);
+  pl.xproj = (__nv_bfloat16*)take(n * h2 * 2048 * 2);
+  pl.lstm_out = (__nv_bfloat16*)take(n * h2 * 512 * 2);
+  pl.h_state = (__nv_bfloat16*)take((size_t)2 * 2 * pl.Npad * 256 * 2);
+  pl.c_state = (float*)take((size_t)2 * pl.Npad * 256 * 4);
+  pl.stats = (double*)take(2 * 2 * 512 * 8);
+  pl.bn = (float*)take(2 * 4 * 512 * 4);
+  return off;
+}
+
+extern "C" int crnn_model_workspace_size(const crnn_model* m, int N, int W, int train, size_t* bytes) {
+  (void)train;
+  if (!m || !bytes) return crnn_fail(CRNN_INVALID_VALUE, "workspace_size: null");
+  if (N <= 0 || W < 8 || (W % 4) != 0) return crnn_fail(CRNN_INVALID_VALUE, "workspace_size: need N>0, W>=8, W%%4==0 (gen.py:58)");
+  Plan pl;
+  *bytes = layout_plan(pl, N, W, nullptr);
+  return CRNN_OK;
+}
+
+static int build_plan(crnn_model* m, int N, int W, void* ws, cudaStream_t st) {
+  Plan& pl = m->plan;
+  layout_plan(pl, N, W, reinterpret_cast<uint8_t*>(ws));
+  pl.ws = ws;
+  CRNN_TRY(make_tmap_nhwc(&pl.tA_c2, pl.a1, N, pl.H1, 16, 64, 2));
+  CRNN_TRY(make_tmap_nhwc(&pl.tA_c31, pl.a2, N, pl.H2, 8, 128, 4));
+  CRNN_TRY(make_tmap_nhwc(&pl.tA_c32, pl.a3, N, pl.H2, 8, 256, 4));
+  CRNN_TRY(make_tmap_nhwc(&pl.tA_c41, pl.a3p, N, pl.H2, 4, 256, 8));
+  CRNN_TRY(make_tmap_nhwc(&pl.tA_c42, pl.a4a, N, pl.H2, 4, 512, 8));
+  // conv5 (2x2 VALID over [N,H2,2,512]): output (n,t) = rows n*H2+t and n*H2+t+1 of the [N*H2, 1024] view
+  CRNN_TRY(make_tmap_2d(&pl.tA_c5, pl.a4b, (uint64_t)N * pl.H2, 1024, 1024, 128));
+  CRNN_TRY(make_tmap_2d(&pl.tA_x, pl.a5, (uint64_t)N * pl.H2, 512, 512, 128));
+  for (int b = 0; b < 2; ++b)
+    CRNN_TRY(make_tmap_2d(&pl.tA_h[b], pl.h_state + (size_t)b * 2 * pl.Npad * 256, (uint64_t)2 * pl.Npad, 256, 256, 128));
+  CRNN_TRY(make_tmap_2d(&pl.tA_l, pl.lstm_out, (uint64_t)N * pl.H2, 512, 512, 128));
+  // rows t = T (= H2-1) of lstm_out are never produced by a time step: keep them defined (zero)
+  CUDA_TRY(cudaMemsetAsync(pl.lstm_out, 0, (size_t)N * pl.H2 * 512 * 2, st));
+  return CRNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM launch
+template <int BN, int AM, int EPI, int ST>
+static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const gemm::Params& p, int num_sms, cudaStream_t st) {
+  auto kern = gemm::gemm_kernel<BN, AM, EPI, ST>;
+  constexpr int smem = gemm::Smem<BN, ST>::BYTES;
+  static bool attr = false;
+  if (!attr) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, gemm::NUM_THREADS, smem, st>>>(a, b, p);
+  CUDA_TRY(cudaGetLastError());
+  return CRNN_OK;
+}
+
+static gemm::Params conv_params(int N, int H, int Wd, int Cin, int Cout, int block_n, const float* bias, void* out) {
+  gemm::Params p;
+  memset(&p, 0, sizeof(p));
+  p.bh = 32 / Wd;
+  p.Wd = Wd; p.H = H; p.Nimg = N;
+  p.sb_per_img = (H + p.bh - 1) / p.bh;
+  p.num_m_tiles = (N * p.sb_per_img + 3) / 4;
+  p.num_n_tiles = Cout / block_n;
+  p.cin_blocks = Cin / 64;
+  p.num_k_blocks = 9 * p.cin_blocks;
+  p.Nc = Cout;
+  p.bias = bias;
+  p.out = out;
+  return p;
+}
+
+extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_step_len, int N, int W, float* logits_out,
+                            void* workspace, size_t workspace_bytes, crnn_stream_t stream) {
+  if (!m || !data || !time_step_len || !logits_out || !workspace) return crnn_fail(CRNN_INVALID_VALUE, "forward: null pointer");
+  if (!m->params) return crnn_fail(CRNN_NOT_BOUND, "forward: call crnn_model_bind first");
+  if (N <= 0 || W < 8 || (W % 4) != 0) return crnn_fail(CRNN_INVALID_VALUE, "forward: need N>0, W>=8, W%%4==0");
+  size_t need = 0;
+  CRNN_TRY(crnn_model_workspace_size(m, N, W, 0, &need));
+  if (workspace_bytes < need) return crnn_fail(CRNN_WORKSPACE_TOO_SMALL, "forward: workspace %zu < %zu", workspace_bytes, need);
+  if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return crnn_fail(CRNN_INVALID_VALUE, "forward: workspace must be 1024-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (m->dirty) CRNN_TRY(prepare_weights(m, st));
+  Plan& pl = m->plan;
+  if (pl.N != N || pl.W != W || pl.ws != workspace) CRNN_TRY(build_plan(m, N, W, workspace, st));
+  const int H1 = pl.H1, H2 = pl.H2, T = pl.T, sms = m->num_sms;
+
+  // conv1 + pool1 (SIMT, HBM/FMA-bound: K = 9)
+  CRNN_TRY(launch_conv1_pool(data, m->P("conv1/weights"), m->P("conv1/biases"), pl.a1, N, W, sms, st));
+  // conv2 + ReLU + pool2
+  {
+    gemm::Params p = conv_params(N, H1, 16, 64, 128, 128, m->P("conv2/biases"), pl.a2);
+    CRNN_TRY((launch_gemm<128, gemm::A_CONV3, gemm::EPI_RELU_POOL22, 6>(pl.tA_c2, m->tB_c2, p, sms, st)));
+  }
+  // conv3_1 + ReLU
+  {
+    gemm::Params p = conv_params(N, H2, 8, 128, 256, 256, m->P("conv3_1/biases"), pl.a3);
+    CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_RELU, 4>(pl.tA_c31, m->tB_c31, p, sms, st)));
+  }
+  // conv3_2 + ReLU + height pool
+  {
+    gemm::Params p = conv_params(N, H2, 8, 256, 256, 256, m->P("conv3_2/biases"), pl.a3p);
+    CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_RELU_POOL12, 4>(pl.tA_c32, m->tB_c32, p, sms, st)));
+  }
+  CUDA_TRY(cudaMemsetAsync(pl.stats, 0, 2 * 2 * 512 * sizeof(double), st));
+  const double bn_count = (double)N * H2 * 4;
+  // conv4_1 + bias -> batch statistics -> BN + ReLU
+  {
+    gemm::Params p = conv_params(N, H2, 4, 256, 512, 256, m->P("conv4_1/biases"), pl.a4a_pre);
+    p.stats = pl.stats;
+    CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_STATS, 4>(pl.tA_c41, m->tB_c41, p, sms, st)));
+    float* bn = pl.bn;
+    CRNN_TRY(launch_bn_finalize(pl.stats, bn_count, m->P("conv4_1/conv4_1/gamma"), m->P("conv4_1/conv4_1/beta"),
+                                m->cfg.bn_eps, bn, bn + 512, bn + 1024, bn + 1536, 512, st));
+    CRNN_TRY(launch_bn_apply_relu(pl.a4a_pre, pl.a4a, bn, bn + 512, (size_t)N * H2 * 4, 512, st));
+  }
+  // conv4_2 + bias -> batch statistics -> BN + ReLU + height pool (pool3)
+  {
+    gemm::Params p = conv_params(N, H2, 4, 512, 512, 256, m->P("conv4_2/biases"), pl.a4b_pre);
+    p.stats = pl.stats + 1024;
+    CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_STATS, 4>(pl.tA_c42, m->tB_c42, p, sms, st)));
+    float* bn = pl.bn + 2048;
+    CRNN_TRY(launch_bn_finalize(pl.stats + 1024, bn_count, m->P("conv4_2/conv4_2/gamma"), m->P("conv4_2/conv4_2/beta"),
+                                m->cfg.bn_eps, bn, bn + 512, bn + 1024, bn + 1536, 512, st));
+    CRNN_TRY(launch_bn_apply_relu_pool12(pl.a4b_pre, pl.a4b, bn, bn + 512, (size_t)N * H2 * 2, 512, st));
+  }
+  // conv5 (2x2 VALID, no activation) as a plain GEMM over the overlapping-row view
+  {
+    gemm::Params p;
+    memset(&p, 0, sizeof(p));
+    p.M = N * H2;
+    p.num_m_tiles = (p.M + 127) / 128; p.num_n_tiles = 2; p.num_k_blocks = 32; p.kb_per_shift = 16;
+    p.Nc = 512; p.bias = m->P("conv5/biases"); p.out = pl.a5; p.ldo = 512;
+    CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 4>(pl.tA_c5, m->tB_c5, p, sms, st)));
+  }
+  // LSTM input projection for all frames and both directions: [N*H2, 512] x [512, 2048]
+  {
+    gemm::Params p;
+    memset(&p, 0, sizeof(p));
+    p.M = N * H2;
+    p.num_m_tiles = (p.M + 127) / 128; p.num_n_tiles = 8; p.num_k_blocks = 8; p.kb_per_shift = 8;
+    p.Nc = 2048; p.bias = m->xbias; p.out = pl.xproj; p.ldo = 2048;
+    CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 4>(pl.tA_x, m->tB_x, p, sms, st)));
+  }
+  // recurrence: one launch per time step covers both directions (fw rows [0,Npad), bw rows [Npad,2Npad))
+  CUDA_TRY(cudaMemsetAsync(pl.h_state, 0, (size_t)2 * pl.Npad * 256 * 2, st));
+  CUDA_TRY(cudaMemsetAsync(pl.c_state, 0, (size_t)2 * pl.Npad * 256 * 4, st));
+  for (int s = 0; s < T; ++s) {
+    gemm::Params p;
+    memset(&p, 0, sizeof(p));
+    p.num_m_tiles = 2 * pl.Npad / 128; p.num_n_tiles = 4; p.num_k_blocks = 4; p.kb_per_shift = 4;
+    p.m_tiles_per_dir = pl.Npad / 128;
+    p.Nc = 1024; p.H = H2; p.T = T; p.Nimg = N; p.Npad = pl.Npad; p.step = s;
+    p.xproj = pl.xproj; p.c_state = pl.c_state; p.lstm_out = pl.lstm_out; p.seq_len = time_step_len;
+    p.h_next = pl.h_state + (size_t)((s + 1) & 1) * 2 * pl.Npad * 256;
+    CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_LSTM, 4>(pl.tA_h[s & 1], m->tB_h, p, sms, st)));
+  }
+  // 512 -> 64 projection, written time-major [T, N, 64] (network.py:126-128)
+  {
+    gemm::Params p;
+    memset(&p, 0, sizeof(p));
+    p.M = N * H2;
+    p.num_m_tiles = (p.M + 127) / 128; p.num_n_tiles = 1; p.num_k_blocks = 8; p.kb_per_shift = 8;
+    p.Nc = 64; p.bias = m->P("logits/biases"); p.out = logits_out; p.H = H2; p.T = T; p.Nimg = N;
+    CRNN_TRY((launch_gemm<64, gemm::A_PLAIN, gemm::EPI_LOGITS, 8>(pl.tA_l, m->tB_l, p, sms, st)));
+  }
+  return CRNN_OK;
+}
+
+extern "C" int crnn_total_loss(crnn_model* m, const float* costs, int N, float* loss_out, crnn_stream_t stream) {
+  if (!m || !costs || !loss_out || N <= 0) return crnn_fail(CRNN_INVALID_VALUE, "total_loss: bad args");
+  if (!m->params) return crnn_fail(CRNN_NOT_BOUND, "total_loss: call crnn_model_bind first");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (m->dirty) CRNN_TRY(prepare_weights(m, st));
+  return launch_total_loss(costs, N, m->sumsq, m->cfg.weight_decay, loss_out, st);
+}
+
+extern "C" int crnn_debug_tap(crnn_model* m, const char* name, float* dst, size_t dst_elems, void* workspace,
+                              crnn_stream_t stream) {
+  if (!m || !name || !dst) return crnn_fail(CRNN_INVALID_VALUE, "debug_tap: null");
+  Plan& pl = m->plan;
+  if (pl.ws == nullptr || pl.ws != workspace) return crnn_fail(CRNN_INVALID_VALUE, "debug_tap: no forward ran on this workspace");
+  const size_t n = pl.N, h1 = pl.H1, h2 = pl.H2;
+  const __nv_bfloat16* src = nullptr;
+  size_t cnt = 0;
+  std::string s(name);
+  if (s == "conv1") { src = pl.a1; cnt = n * h1 * 16 * 64; }
+  else if (s == "conv2") { src = pl.a2; cnt = n * h2 * 8 * 128; }
+  else if (s == "conv3_1") { src = pl.a3; cnt = n * h2 * 8 * 256; }
+  else if (s == "conv3_2") { src = pl.a3p; cnt = n * h2 * 4 * 256; }
+  else if (s == "conv4_1") { src = pl.a4a; cnt = n * h2 * 4 * 512; }
+  else if (s == "conv4_2") { src = pl.a4b; cnt = n * h2 * 2 * 512; }
+  else if (s == "conv5") { src = pl.a5; cnt = n * h2 * 512; }
+  else if (s == "lstm_out") { src = pl.lstm_out; cnt = n * h2 * 512; }
+  else if (s == "xproj") { src = pl.xproj; cnt = n * h2 * 2048; }
+  else return crnn_fail(CRNN_INVALID_VALUE, "debug_tap: unknown tap %s", name);
+  if (dst_elems < cnt) return crnn_fail(CRNN_INVALID_VALUE, "debug_tap: dst too small (%zu < %zu)", dst_elems, cnt);
+  return launch_bf16_to_f32(src, dst, cnt, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int crnn_test_gemm_bf16(const void* A, const void* B, float* D, int M, int Nc, int K, int block_n,
+                                   crnn_stream_t stream) {
+  if (!A || !B || !D || M <= 0 || Nc <= 0 || K <= 0 || (K % 64) != 0 || (Nc % block_n) != 0)
+    return crnn_fail(CRNN_INVALID_VALUE, "test_gemm: bad args");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CUtensorMap ta, tb;
+  CRNN_TRY(make_tmap_2d(&ta, A, M, K, K, 128));
+  CRNN_TRY(make_tmap_2d(&tb, B, Nc, K, K, block_n));
+  gemm::Params p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.Nc = Nc;
+  p.num_m_tiles = (M + 127) / 128; p.num_n_tiles = Nc / block_n; p.num_k_blocks = K / 64; p.kb_per_shift = p.num_k_blocks;
+  p.out = D;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (block_n == 64) return launch_gemm<64, gemm::A_PLAIN, gemm::EPI_F32, 8>(ta, tb, p, sms, st);
+  if (block_n == 128) return launch_gemm<128, gemm::A_PLAIN, gemm::EPI_F32, 6>(ta, tb, p, sms, st);
+  if (block_n == 256) return launch_gemm<256, gemm::A_PLAIN, gemm::EPI_F32, 4>(ta, tb, p, sms, st);
+  return crnn_fail(CRNN_INVALID_VALUE, "test_gemm: block_n must be 64/128/256");
+}

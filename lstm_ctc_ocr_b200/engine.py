@@ -1,0 +1,168 @@
+"""Device-side engine behind the reference-facing API.  PyTorch tensors are used purely as
+device-memory containers and for the current CUDA stream; every kernel on this path lives in
+libcrnnctc.so (hand-written sm_100a CUDA, see csrc/)."""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CrnnConfig, CrnnError, check
+
+NCLASSES = 64
+TF_BLANK = NCLASSES - 1
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+class CrnnModel:
+    """Owns the flat f32 parameter buffer (TF variable names/layouts) and the C model handle."""
+
+    def __init__(self, weight_decay=1e-5, bn_eps=1e-3, device=None):
+        if not torch.cuda.is_available():
+            raise CrnnError("lstm_ctc_ocr_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        torch.cuda.set_device(self.device)
+        cfg = CrnnConfig(32, NCLASSES, 512, bn_eps, weight_decay, 1)
+        h = _lib.c_void_p()
+        check(self.lib.crnn_model_create(cfg, h))
+        self.handle = h
+        self.weight_decay = weight_decay
+        self.total = int(self.lib.crnn_param_count(h))
+        self.table = OrderedDict()
+        for i in range(self.lib.crnn_num_tensors(h)):
+            name = _lib.c_char_p(); off = _lib.c_int64(); shp = (_lib.c_int64 * 4)(); nd = _lib.c_int()
+            check(self.lib.crnn_param_info(h, i, name, off, shp, nd))
+            self.table[name.value.decode()] = (int(off.value), tuple(int(shp[k]) for k in range(nd.value)))
+        self.params = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        self.grads = None
+        self.adam_m = None
+        self.adam_v = None
+        self._bind()
+        self._ws = None
+        self._ws_key = None
+
+    def _bind(self):
+        check(self.lib.crnn_model_bind(self.handle, _ptr(self.params), _ptr(self.grads), _ptr(self.adam_m), _ptr(self.adam_v)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                torch.cuda.synchronize(self.device)
+                self.lib.crnn_model_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ---- parameters, addressable by TF variable name --------------------------------------
+    def tensor(self, name):
+        off, shp = self.table[name]
+        n = int(np.prod(shp))
+        return self.params[off:off + n].view(*shp)
+
+    def load_params(self, params):
+        for name in self.table:
+            v = params[name]
+            v = torch.as_tensor(np.asarray(v, dtype=np.float32)) if not torch.is_tensor(v) else v.detach().float().cpu()
+            self.tensor(name).copy_(v.to(self.device))
+        check(self.lib.crnn_model_params_changed(self.handle))
+
+    def state_dict(self):
+        return OrderedDict((k, self.tensor(k).detach().cpu().numpy().copy()) for k in self.table)
+
+    # ---- forward ----------------------------------------------------------------------------
+    def _workspace(self, N, W):
+        key = (N, W)
+        if self._ws_key != key:
+            nbytes = _lib.c_size_t()
+            check(self.lib.crnn_model_workspace_size(self.handle, N, W, 0, nbytes))
+            self._ws = None
+            self._ws = torch.empty(nbytes.value + 1024, dtype=torch.uint8, device=self.device)
+            self._ws_key = key
+        base = self._ws.data_ptr()
+        aligned = (base + 1023) // 1024 * 1024
+        return aligned, self._ws.numel() - (aligned - base)
+
+    def forward(self, data, time_step_len, out=None):
+        """data [N,W,32] f32 cuda, time_step_len [N] i32 cuda -> logits [T,N,64] f32 (time-major)."""
+        assert data.is_cuda and data.dtype == torch.float32 and data.is_contiguous()
+        assert time_step_len.is_cuda and time_step_len.dtype == torch.int32
+        N, W, Hh = data.shape
+        if Hh != 32:
+            raise CrnnError("data must be [N, W, 32] (cfg.NUM_FEATURES = 32)")
+        T = W // 4 - 1
+        if out is None:
+            out = torch.empty((T, N, NCLASSES), dtype=torch.float32, device=self.device)
+        ws, nbytes = self._workspace(N, W)
+        check(self.lib.crnn_forward(self.handle, data.data_ptr(), time_step_len.data_ptr(), N, W, out.data_ptr(), ws,
+                                    nbytes, _stream()))
+        return out
+
+    def tap(self, name, N, W):
+        """Intermediate of the last forward as f32 NHWC (tests only)."""
+        H1, H2 = W // 2, W // 4
+        shapes = {"conv1": (N, H1, 16, 64), "conv2": (N, H2, 8, 128), "conv3_1": (N, H2, 8, 256),
+                  "conv3_2": (N, H2, 4, 256), "conv4_1": (N, H2, 4, 512), "conv4_2": (N, H2, 2, 512),
+                  "conv5": (N, H2, 512), "lstm_out": (N, H2, 512), "xproj": (N, H2, 2048)}
+        shp = shapes[name]
+        dst = torch.empty(shp, dtype=torch.float32, device=self.device)
+        ws, _ = self._workspace(N, W)
+        check(self.lib.crnn_debug_tap(self.handle, name.encode(), dst.data_ptr(), dst.numel(), ws, _stream()))
+        return dst
+
+    # ---- loss / decode ------------------------------------------------------------------------
+    def total_loss(self, costs):
+        loss = torch.empty(1, dtype=torch.float32, device=self.device)
+        check(self.lib.crnn_total_loss(self.handle, costs.data_ptr(), costs.numel(), loss.data_ptr(), _stream()))
+        return loss
+
+
+def ctc_loss(logits, flat_labels, label_len, input_len, blank=0, want_grad=False, grad_scale=1.0, max_label_len=None,
+             costs=None, grad=None):
+    """logits [T,N,64] f32 cuda; integer tensors i32 cuda.  Returns (costs [N], grad [T,N,64] | None)."""
+    lib = _lib.load()
+    assert logits.is_cuda and logits.dtype == torch.float32 and logits.is_contiguous()
+    T, N, C = logits.shape
+    if max_label_len is None:
+        max_label_len = int(label_len.max().item()) if label_len.numel() else 0      # host sync; pass it to avoid
+    if costs is None:
+        costs = torch.empty(N, dtype=torch.float32, device=logits.device)
+    if want_grad and grad is None:
+        grad = torch.empty_like(logits)
+    check(lib.crnn_ctc_loss(logits.data_ptr(), _ptr(grad) if want_grad else 0, flat_labels.data_ptr(),
+                            label_len.data_ptr(), input_len.data_ptr(), T, N, C, blank, int(max_label_len),
+                            float(grad_scale), costs.data_ptr(), 0, 0, _stream()))
+    return costs, (grad if want_grad else None)
+
+
+def ctc_greedy(logits, input_len, tf_blank=TF_BLANK, strip=0):
+    """Returns (out [N,T] i32 zero padded, out_len [N] i32) on device."""
+    lib = _lib.load()
+    T, N, C = logits.shape
+    out = torch.empty((N, T), dtype=torch.int32, device=logits.device)
+    out_len = torch.empty(N, dtype=torch.int32, device=logits.device)
+    check(lib.crnn_ctc_greedy(logits.data_ptr(), input_len.data_ptr(), T, N, C, tf_blank, strip, out.data_ptr(),
+                              out_len.data_ptr(), _stream()))
+    return out, out_len
+
+
+def dense_decoded(out, out_len):
+    """sparse_tensor_to_dense(default 0) shape [N, max_len] (network.py:657); one D2H sync."""
+    m = int(out_len.max().item()) if out_len.numel() else 0
+    return out[:, :m].contiguous()
+
+
+def test_gemm_bf16(A, B, block_n):
+    lib = _lib.load()
+    M, K = A.shape
+    Nc = B.shape[0]
+    D = torch.empty((M, Nc), dtype=torch.float32, device=A.device)
+    check(lib.crnn_test_gemm_bf16(A.data_ptr(), B.data_ptr(), D.data_ptr(), M, Nc, K, block_n, _stream()))
+    return D
