@@ -110,6 +110,14 @@ int     crnn_total_loss(crnn_model* m, const float* costs, int N, float* loss_ou
 int     crnn_debug_tap(crnn_model* m, const char* name, float* dst, size_t dst_elems,
                        void* workspace, crnn_stream_t stream);
 
+/* Per-stage timing of crnn_forward with CUDA events recorded on the caller's stream (bench.py's roofline line).
+ * crnn_profile_begin arms the next `max_forwards` forward calls; crnn_profile_read synchronises on the events and
+ * returns ms_out[forwards][crnn_profile_num_stages()]. */
+int         crnn_profile_begin(crnn_model* m, int max_forwards);
+int         crnn_profile_num_stages(void);
+const char* crnn_profile_stage_name(int stage);
+int         crnn_profile_read(crnn_model* m, float* ms_out, int* forwards);
+
 /* Stand-alone bf16 GEMM test entry (tests only): D[M,Nc] f32 = A[M,K] * B[Nc,K]^T, bf16 in. */
 int     crnn_test_gemm_bf16(const void* A, const void* B, float* D, int M, int Nc, int K,
                             int block_n, crnn_stream_t stream);

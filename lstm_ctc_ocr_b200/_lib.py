@@ -36,6 +36,10 @@ SIGNATURES = {
     "crnn_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "crnn_total_loss": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "crnn_debug_tap": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "crnn_profile_begin": (c_int, [c_void_p, c_int]),
+    "crnn_profile_num_stages": (c_int, []),
+    "crnn_profile_stage_name": (c_char_p, [c_int]),
+    "crnn_profile_read": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_int)]),
     "crnn_test_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }
 

@@ -92,6 +92,10 @@ static const ConvSpec kConvs[7] = {   // lib/networks/LSTM_train.py:24-34
     {"conv3_2", 3, 3, 256, 256, false}, {"conv4_1", 3, 3, 256, 512, true}, {"conv4_2", 3, 3, 512, 512, true},
     {"conv5", 2, 2, 512, 512, false}};
 
+static const char* kStageNames[] = {"conv1_pool1", "conv2_pool2", "conv3_1", "conv3_2_pool", "conv4_1_gemm", "bn4_1_apply",
+                                    "conv4_2_gemm", "bn4_2_apply_pool3", "conv5", "lstm_xproj", "lstm_recurrence", "logits"};
+static const int kNumStages = 12;
+
 struct Plan {
   int N = 0, W = 0, H1 = 0, H2 = 0, T = 0, Npad = 0;
   void* ws = nullptr;
@@ -116,6 +120,10 @@ struct crnn_model {
   void* wblock = nullptr;
   CUtensorMap tB_c2, tB_c31, tB_c32, tB_c41, tB_c42, tB_c5, tB_x, tB_h, tB_l;
   Plan plan;
+  // per-stage CUDA-event profiling (crnn_profile_*): events are recorded on the caller's stream between stages
+  std::vector<cudaEvent_t> prof_events;   // [slots][kNumStages + 1]
+  int prof_slots = 0, prof_used = 0;
+  bool prof_on = false;
 
   const TensorInfo* find(const std::string& n) const {
     for (auto& t : tensors) if (t.name == n) return &t;
@@ -201,6 +209,7 @@ extern "C" int crnn_model_create(const crnn_config* cfg, crnn_model** out) {
 extern "C" int crnn_model_destroy(crnn_model* m) {
   if (!m) return CRNN_OK;
   if (m->wblock) cudaFree(m->wblock);
+  for (auto e : m->prof_events) cudaEventDestroy(e);
   delete m;
   return CRNN_OK;
 }
@@ -359,24 +368,33 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
   Plan& pl = m->plan;
   if (pl.N != N || pl.W != W || pl.ws != workspace) CRNN_TRY(build_plan(m, N, W, workspace, st));
   const int H1 = pl.H1, H2 = pl.H2, T = pl.T, sms = m->num_sms;
+  cudaEvent_t* ev = nullptr;
+  if (m->prof_on && m->prof_used < m->prof_slots) ev = &m->prof_events[(size_t)(m->prof_used++) * (kNumStages + 1)];
+  int evi = 0;
+#define STAGE_MARK() do { if (ev) CUDA_TRY(cudaEventRecord(ev[evi++], st)); } while (0)
+  STAGE_MARK();
 
   // conv1 + pool1 (SIMT, HBM/FMA-bound: K = 9)
   CRNN_TRY(launch_conv1_pool(data, m->P("conv1/weights"), m->P("conv1/biases"), pl.a1, N, W, sms, st));
+  STAGE_MARK();
   // conv2 + ReLU + pool2
   {
     gemm::Params p = conv_params(N, H1, 16, 64, 128, 128, m->P("conv2/biases"), pl.a2);
     CRNN_TRY((launch_gemm<128, gemm::A_CONV3, gemm::EPI_RELU_POOL22, 6>(pl.tA_c2, m->tB_c2, p, sms, st)));
   }
+  STAGE_MARK();
   // conv3_1 + ReLU
   {
     gemm::Params p = conv_params(N, H2, 8, 128, 256, 256, m->P("conv3_1/biases"), pl.a3);
     CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_RELU, 4>(pl.tA_c31, m->tB_c31, p, sms, st)));
   }
+  STAGE_MARK();
   // conv3_2 + ReLU + height pool
   {
     gemm::Params p = conv_params(N, H2, 8, 256, 256, 256, m->P("conv3_2/biases"), pl.a3p);
     CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_RELU_POOL12, 4>(pl.tA_c32, m->tB_c32, p, sms, st)));
   }
+  STAGE_MARK();
   CUDA_TRY(cudaMemsetAsync(pl.stats, 0, 2 * 2 * 512 * sizeof(double), st));
   const double bn_count = (double)N * H2 * 4;
   // conv4_1 + bias -> batch statistics -> BN + ReLU
@@ -384,22 +402,26 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
     gemm::Params p = conv_params(N, H2, 4, 256, 512, 256, m->P("conv4_1/biases"), pl.a4a_pre);
     p.stats = pl.stats;
     CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_STATS, 4>(pl.tA_c41, m->tB_c41, p, sms, st)));
+    STAGE_MARK();
     float* bn = pl.bn;
     CRNN_TRY(launch_bn_finalize(pl.stats, bn_count, m->P("conv4_1/conv4_1/gamma"), m->P("conv4_1/conv4_1/beta"),
                                 m->cfg.bn_eps, bn, bn + 512, bn + 1024, bn + 1536, 512, st));
     CRNN_TRY(launch_bn_apply_relu(pl.a4a_pre, pl.a4a, bn, bn + 512, (size_t)N * H2 * 4, 512, st));
   }
+  STAGE_MARK();
   // conv4_2 + bias -> batch statistics -> BN + ReLU + height pool (pool3)
   {
     gemm::Params p = conv_params(N, H2, 4, 512, 512, 256, m->P("conv4_2/biases"), pl.a4b_pre);
     p.stats = pl.stats + 1024;
     CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_STATS, 4>(pl.tA_c42, m->tB_c42, p, sms, st)));
+    STAGE_MARK();
     float* bn = pl.bn + 2048;
     CRNN_TRY(launch_bn_finalize(pl.stats + 1024, bn_count, m->P("conv4_2/conv4_2/gamma"), m->P("conv4_2/conv4_2/beta"),
                                 m->cfg.bn_eps, bn, bn + 512, bn + 1024, bn + 1536, 512, st));
     CRNN_TRY(launch_bn_apply_relu_pool12(pl.a4b_pre, pl.a4b, bn, bn + 512, (size_t)N * H2 * 2, 512, st));
   }
-  // conv5 (2x2 VALID, no activation) as a plain GEMM over the overlapping-row view
+  STAGE_MARK();
+  // conv5 (2x2 VALID, no activation): plain GEMM, K-blocks 0..15 from row m, 16..31 from row m+1
   {
     gemm::Params p;
     memset(&p, 0, sizeof(p));
@@ -408,6 +430,7 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
     p.Nc = 512; p.bias = m->P("conv5/biases"); p.out = pl.a5; p.ldo = 512;
     CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 4>(pl.tA_c5, m->tB_c5, p, sms, st)));
   }
+  STAGE_MARK();
   // LSTM input projection for all frames and both directions: [N*H2, 512] x [512, 2048]
   {
     gemm::Params p;
@@ -417,6 +440,7 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
     p.Nc = 2048; p.bias = m->xbias; p.out = pl.xproj; p.ldo = 2048;
     CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 4>(pl.tA_x, m->tB_x, p, sms, st)));
   }
+  STAGE_MARK();
   // recurrence: one launch per time step covers both directions (fw rows [0,Npad), bw rows [Npad,2Npad))
   CUDA_TRY(cudaMemsetAsync(pl.h_state, 0, (size_t)2 * pl.Npad * 256 * 2, st));
   CUDA_TRY(cudaMemsetAsync(pl.c_state, 0, (size_t)2 * pl.Npad * 256 * 4, st));
@@ -430,6 +454,7 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
     p.h_next = pl.h_state + (size_t)((s + 1) & 1) * 2 * pl.Npad * 256;
     CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_LSTM, 4>(pl.tA_h[s & 1], m->tB_h, p, sms, st)));
   }
+  STAGE_MARK();
   // 512 -> 64 projection, written time-major [T, N, 64] (network.py:126-128)
   {
     gemm::Params p;
@@ -438,6 +463,35 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
     p.num_m_tiles = (p.M + 127) / 128; p.num_n_tiles = 1; p.num_k_blocks = 8; p.kb_per_shift = 8;
     p.Nc = 64; p.bias = m->P("logits/biases"); p.out = logits_out; p.H = H2; p.T = T; p.Nimg = N;
     CRNN_TRY((launch_gemm<64, gemm::A_PLAIN, gemm::EPI_LOGITS, 8>(pl.tA_l, m->tB_l, p, sms, st)));
+  }
+  STAGE_MARK();
+#undef STAGE_MARK
+  return CRNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ profiling
+extern "C" int crnn_profile_begin(crnn_model* m, int max_forwards) {
+  if (!m || max_forwards < 0) return crnn_fail(CRNN_INVALID_VALUE, "profile_begin: bad args");
+  const size_t need = (size_t)max_forwards * (kNumStages + 1);
+  while (m->prof_events.size() < need) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreate(&e));
+    m->prof_events.push_back(e);
+  }
+  m->prof_slots = max_forwards; m->prof_used = 0; m->prof_on = max_forwards > 0;
+  return CRNN_OK;
+}
+extern "C" int crnn_profile_num_stages(void) { return kNumStages; }
+extern "C" const char* crnn_profile_stage_name(int i) { return (i >= 0 && i < kNumStages) ? kStageNames[i] : ""; }
+// Host-synchronising: waits for the recorded events. ms_out [forwards][kNumStages]
+extern "C" int crnn_profile_read(crnn_model* m, float* ms_out, int* forwards) {
+  if (!m || !ms_out || !forwards) return crnn_fail(CRNN_INVALID_VALUE, "profile_read: null");
+  m->prof_on = false;
+  *forwards = m->prof_used;
+  for (int f = 0; f < m->prof_used; ++f) {
+    cudaEvent_t* ev = &m->prof_events[(size_t)f * (kNumStages + 1)];
+    CUDA_TRY(cudaEventSynchronize(ev[kNumStages]));
+    for (int s = 0; s < kNumStages; ++s) CUDA_TRY(cudaEventElapsedTime(ms_out + (size_t)f * kNumStages + s, ev[s], ev[s + 1]));
   }
   return CRNN_OK;
 }

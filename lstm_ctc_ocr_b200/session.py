@@ -1,0 +1,167 @@
+"""``Session.run(fetches, feed_dict)`` -- the call the reference's solver makes every iteration
+(lib/lstm/train.py:129-130,160; lib/lstm/test.py:77), evaluated by the sm_100a engine.
+
+Per run: feed_dict numpy arrays -> pinned host staging -> async H2D on the current stream ->
+crnn_forward -> crnn_ctc_loss / crnn_total_loss / crnn_ctc_greedy as the fetches require -> D2H of
+exactly the fetched values."""
+import numpy as np
+import torch
+
+from . import engine
+from ._lib import CrnnError
+from .lib.networks.network import Fetch, Placeholder
+
+_NP2T = {np.dtype("float32"): torch.float32, np.dtype("int32"): torch.int32}
+
+
+class _Pinned(object):
+    """Reusable pinned staging buffers keyed by name; grown on demand."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def stage(self, name, arr, device):
+        arr = np.ascontiguousarray(arr)
+        tdt = _NP2T[arr.dtype]
+        t = self.bufs.get(name)
+        if t is None or t.numel() < arr.size or t.dtype != tdt:
+            t = torch.empty(max(arr.size, 1), dtype=tdt).pin_memory()
+            self.bufs[name] = t
+        v = t[:arr.size].view(arr.shape)
+        v.copy_(torch.from_numpy(arr))
+        return v.to(device, non_blocking=True)
+
+
+class Session(object):
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise CrnnError("Session needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self._engines = {}
+        self._pinned = _Pinned()
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def close(self):
+        self._engines.clear()
+
+    # ---- variables ------------------------------------------------------------------------
+    def engine_for(self, net):
+        eng = self._engines.get(id(net))
+        if eng is None:
+            from .lib.lstm.config import cfg
+            eng = engine.CrnnModel(weight_decay=float(getattr(net, "_wd", cfg.TRAIN.WEIGHT_DECAY)), device=self.device)
+            self._engines[id(net)] = eng
+        return eng
+
+    def assign(self, net, state_dict, ignore_missing=False):
+        eng = self.engine_for(net)
+        full = eng.state_dict()
+        for k in full:
+            if k in state_dict:
+                full[k] = np.asarray(state_dict[k], dtype=np.float32).reshape(full[k].shape)
+            elif not ignore_missing:
+                raise KeyError(k)
+        eng.load_params(full)
+
+    def variables(self, net):
+        return self.engine_for(net).state_dict()
+
+    # ---- run ------------------------------------------------------------------------------
+    @staticmethod
+    def validate_feed(data, tsl, labels, labels_len):
+        """Host-side checks the C ABI cannot do without a device sync (invalid lengths)."""
+        if data.ndim != 3 or data.shape[2] != 32:
+            raise ValueError(f"data must be [N, W, 32], got {data.shape}")
+        N, W, _ = data.shape
+        if W % 4 != 0 or W < 8:
+            raise ValueError("padded width must be a multiple of POOL_SCALE=4 (gen.py:58) and >= 8")
+        T = W // 4 - 1
+        if tsl.shape != (N,):
+            raise ValueError("time_step_len must be [N]")
+        if tsl.min() < 0 or tsl.max() > T:
+            raise ValueError(f"time_step_len must lie in [0, {T}] (conv output has W/4-1 frames)")
+        if labels is not None:
+            if labels_len.shape != (N,) or labels_len.min() < 0:
+                raise ValueError("labels_len must be [N], non-negative")
+            if int(labels_len.sum()) != labels.size:
+                raise ValueError("sum(labels_len) != len(labels)")
+            if labels.size and (labels.min() < 1 or labels.max() > 62):
+                raise ValueError("label ids must lie in 1..62 (0 is the CTC blank, 63 the decoder blank)")
+
+    def run(self, fetches, feed_dict=None):
+        single = not isinstance(fetches, (list, tuple))
+        flist = [fetches] if single else list(fetches)
+        feed_dict = feed_dict or {}
+        net = None
+        for f in flist:
+            if isinstance(f, Fetch):
+                net = f.net
+        if net is None:
+            raise ValueError("nothing to run: fetches must come from a network (build_loss / get_output)")
+        feeds = {}
+        for k, v in feed_dict.items():
+            if not isinstance(k, Placeholder):
+                raise TypeError("feed_dict keys must be the network's placeholders")
+            feeds[k.name] = v
+        kinds = [f.kind for f in flist]
+        need_labels = any(k in ("loss", "ctc_costs", "train_op", "ctc_grad") for k in kinds)
+        data = np.asarray(feeds["data"], dtype=np.float32)
+        tsl = np.asarray(feeds["time_step_len"], dtype=np.int32)
+        labels = np.asarray(feeds["labels"], dtype=np.int32) if need_labels else None
+        llen = np.asarray(feeds["labels_len"], dtype=np.int32) if need_labels else None
+        self.validate_feed(data, tsl, labels, llen)
+        eng = self.engine_for(net)
+        dev = self.device
+        d_data = self._pinned.stage("data", data, dev)
+        d_tsl = self._pinned.stage("tsl", tsl, dev)
+        self.h2d_bytes = data.nbytes + tsl.nbytes
+        logits = eng.forward(d_data, d_tsl)
+        costs = grad = loss = None
+        if need_labels:
+            d_lab = self._pinned.stage("labels", labels, dev)
+            d_ll = self._pinned.stage("llen", llen, dev)
+            self.h2d_bytes += labels.nbytes + llen.nbytes
+            N = data.shape[0]
+            # warp-ctc computes the gradient inside its forward op; so does this kernel (one launch)
+            costs, grad = engine.ctc_loss(logits, d_lab, d_ll, d_tsl, want_grad=True, grad_scale=1.0 / N,
+                                          max_label_len=int(llen.max()) if llen.size else 0)
+            loss = eng.total_loss(costs)
+        out = []
+        self.d2h_bytes = 0
+        for f in flist:
+            k = f.kind
+            if k == "loss":
+                v = loss.cpu().numpy()[0]
+            elif k == "ctc_costs":
+                v = costs.cpu().numpy()
+            elif k == "ctc_grad":
+                v = grad.cpu().numpy()
+            elif k == "logits":
+                v = logits.cpu().numpy()
+            elif k == "dense_decoded":
+                o, ol = engine.ctc_greedy(logits, d_tsl)
+                v = engine.dense_decoded(o, ol).cpu().numpy()
+            elif k == "train_op":
+                step = getattr(f, "step_fn", None)
+                if step is None:
+                    raise CrnnError("train_op has no step function attached")
+                v = step(eng, logits, grad, d_data, d_tsl)
+            elif k.startswith("layer:"):
+                name = k.split(":", 1)[1]
+                tapname = {"pool1": "conv1", "pool2": "conv3_2", "pool3": "conv4_2", "reshaped_layer": "conv5"}.get(name, name)
+                v = eng.tap(tapname, data.shape[0], data.shape[1]).cpu().numpy()
+            else:
+                raise ValueError(f"unknown fetch {f}")
+            if isinstance(v, np.ndarray):
+                self.d2h_bytes += v.nbytes
+            elif isinstance(v, (np.floating, float)):
+                self.d2h_bytes += 4
+            out.append(v)
+        return out[0] if single else out
