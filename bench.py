@@ -83,9 +83,21 @@ def cpu_reference(N, W, steps, warmup, seed=3):
     """The reference's CPU path: the op-for-op fp32 restatement (oracle port) on all host cores."""
     import torch
     from oracle import crnn_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
     p32 = O.to_torch(O.init_params(seed, dtype=np.float32), torch.float32)
     data, lab, ll, tsl = O.synth_batch(N, W, seed=seed)
+    # "all the host threads it can use": oneDNN on these small convs is fastest well below the core count of a
+    # 128-core host, so try a ladder of thread counts once and keep the best (reported as `cores`)
+    ncpu = os.cpu_count() or 1
+    best = (None, 1e30)
+    for nt in sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)}):
+        torch.set_num_threads(nt)
+        O.fwd_ctc_fp32(p32, data[:max(1, N // 4)], lab[:int(ll[:max(1, N // 4)].sum())], ll[:max(1, N // 4)], tsl[:max(1, N // 4)])
+        t0 = time.perf_counter()
+        O.fwd_ctc_fp32(p32, data[:max(1, N // 4)], lab[:int(ll[:max(1, N // 4)].sum())], ll[:max(1, N // 4)], tsl[:max(1, N // 4)])
+        dt = time.perf_counter() - t0
+        if dt < best[1]:
+            best = (nt, dt)
+    torch.set_num_threads(best[0])
     times = []
     loss = None
     for i in range(warmup + steps):

@@ -176,10 +176,13 @@ __device__ __forceinline__ float lg2(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// One MUFU op each (the LSTM cell epilogue is MUFU-bound: 5 transcendentals per hidden unit per step).
+// tanh.approx.f32: max relative error ~2^-11, far below the bf16 rounding of h that follows.
 __device__ __forceinline__ float fast_tanh(float x) {
-  // tanh(x) = 2*sigmoid(2x) - 1 ; exact at 0, saturates cleanly
-  return 2.0f * __fdividef(1.0f, 1.0f + __expf(-2.0f * x)) - 1.0f;
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
+__device__ __forceinline__ float fast_sigmoid(float x) { return fmaf(0.5f, fast_tanh(0.5f * x), 0.5f); }
 
 }  // namespace ptx
