@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(64) ctc_loss_kernel(const float* __restrict__ 
   float* s_e = s_lse + T;               // [T][SP]
   float* s_alpha = s_e + (size_t)T * SP;
   float* s_beta = s_alpha + (size_t)T * SP;
-  float* s_acc = s_beta + (size_t)T * SP;   // [2][64]
+  float* s_acc = s_beta + (size_t)T * SP;   // [2 warps][4 rows][64]
   __shared__ int s_off;
   __shared__ int s_ext[SP];
   __shared__ int s_repeats;
@@ -104,29 +104,38 @@ __global__ void __launch_bounds__(64) ctc_loss_kernel(const float* __restrict__ 
 #pragma unroll
   for (int k = 0; k < KS; ++k) cls[k] = s_ext[lane * KS + k];
   for (int t0 = warp; t0 < Tn; t0 += 8) {
-    float2 x[4];
+    // 4 rows per iteration, reductions interleaved for ILP (rows t0, t0+2, t0+4, t0+6 belong to this warp)
+    float x0[4], x1[4], m[4], sum[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      int t = t0 + 2 * u;
-      x[u] = (t < Tn) ? __ldg(reinterpret_cast<const float2*>(logits + ((size_t)t * N + n) * CTC_C) + lane)
-                      : make_float2(0.f, 0.f);
+      const int t = t0 + 2 * u;
+      const float2 x = (t < Tn) ? __ldg(reinterpret_cast<const float2*>(logits + ((size_t)t * N + n) * CTC_C) + lane)
+                                : make_float2(0.f, 0.f);
+      x0[u] = x.x * LOG2E; x1[u] = x.y * LOG2E;
+      m[u] = fmaxf(x0[u], x1[u]);
     }
 #pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) m[u] = fmaxf(m[u], __shfl_xor_sync(0xffffffffu, m[u], o));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) sum[u] = ptx::ex2(x0[u] - m[u]) + ptx::ex2(x1[u] - m[u]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], o);
+#pragma unroll
     for (int u = 0; u < 4; ++u) {
-      int t = t0 + 2 * u;
-      if (t >= Tn) break;
-      float x0 = x[u].x * LOG2E, x1 = x[u].y * LOG2E;
-      float m = warp_max(fmaxf(x0, x1));
-      float sum = warp_sum(ptx::ex2(x0 - m) + ptx::ex2(x1 - m));
-      float lse = m + ptx::lg2(sum);
-      if (lane == 0) s_lse[t] = lse;
+      const int t = t0 + 2 * u;
+      const float lse = m[u] + ptx::lg2(sum[u]);
 #pragma unroll
       for (int k = 0; k < KS; ++k) {
-        int c = cls[k];
-        float v0 = __shfl_sync(0xffffffffu, x0, c >> 1);
-        float v1 = __shfl_sync(0xffffffffu, x1, c >> 1);
-        s_e[(size_t)t * SP + lane * KS + k] = ((c & 1) ? v1 : v0) - lse;
+        const int c = cls[k];
+        const float v0 = __shfl_sync(0xffffffffu, x0[u], c >> 1);
+        const float v1 = __shfl_sync(0xffffffffu, x1[u], c >> 1);
+        if (t < Tn) s_e[(size_t)t * SP + lane * KS + k] = ((c & 1) ? v1 : v0) - lse;
       }
+      if (lane == 0 && t < Tn) s_lse[t] = lse;
     }
   }
   __syncthreads();
@@ -213,34 +222,59 @@ __global__ void __launch_bounds__(64) ctc_loss_kernel(const float* __restrict__ 
   if (grad == nullptr) return;
 
   // ---------------- phase 2: gradient rows ----------------
-  float* acc = s_acc + warp * CTC_C;
-  for (int t = warp; t < T; t += 2) {
-    float2* gp = reinterpret_cast<float2*>(grad + ((size_t)t * N + n) * CTC_C) + lane;
-    if (t >= Tn || ll2 == NEG_INF) {
-      *gp = make_float2(0.f, 0.f);
-      continue;
-    }
-    float2 x = __ldg(reinterpret_cast<const float2*>(logits + ((size_t)t * N + n) * CTC_C) + lane);
-    acc[2 * lane] = 0.f;
-    acc[2 * lane + 1] = 0.f;
-    __syncwarp();
-    float blank_sum = 0.f;
+  float* acc = s_acc + warp * 4 * CTC_C;          // [4 rows][64] per warp
+  for (int t0 = warp; t0 < T; t0 += 8) {
+    float2 x[4];
+    bool live[4];
 #pragma unroll
-    for (int k = 0; k < KS; ++k) {
-      int s = lane * KS + k;
-      if (s < S) {
-        size_t i = (size_t)t * SP + s;
-        float w = ptx::ex2(s_alpha[i] + s_beta[i] - s_e[i] - ll2);   // alpha*beta / y / p(l|x)
-        if (s & 1) atomicAdd(&acc[cls[k]], w);
-        else blank_sum += w;
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + 2 * u;
+      live[u] = (t < Tn) && (ll2 != NEG_INF);
+      x[u] = live[u] ? __ldg(reinterpret_cast<const float2*>(logits + ((size_t)t * N + n) * CTC_C) + lane) : make_float2(0.f, 0.f);
+      acc[u * CTC_C + 2 * lane] = 0.f;
+      acc[u * CTC_C + 2 * lane + 1] = 0.f;
+    }
+    __syncwarp();
+    float blank_sum[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + 2 * u;
+      blank_sum[u] = 0.f;
+      if (live[u]) {
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+          const int st = lane * KS + k;
+          if (st < S) {
+            const size_t i = (size_t)t * SP + st;
+            const float w = ptx::ex2(s_alpha[i] + s_beta[i] - s_e[i] - ll2);   // alpha*beta / y / p(l|x)
+            if (st & 1) atomicAdd(&acc[u * CTC_C + cls[k]], w);
+            else blank_sum[u] += w;
+          }
+        }
       }
     }
-    blank_sum = warp_sum(blank_sum);
-    if (lane == 0) atomicAdd(&acc[blank], blank_sum);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) blank_sum[u] += __shfl_xor_sync(0xffffffffu, blank_sum[u], o);
+    if (lane == 0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) atomicAdd(&acc[u * CTC_C + blank], blank_sum[u]);
+    }
     __syncwarp();
-    float lse = s_lse[t];
-    float y0 = ptx::ex2(x.x * LOG2E - lse), y1 = ptx::ex2(x.y * LOG2E - lse);
-    *gp = make_float2(grad_scale * (y0 - acc[2 * lane]), grad_scale * (y1 - acc[2 * lane + 1]));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + 2 * u;
+      if (t >= T) continue;
+      float2* gp = reinterpret_cast<float2*>(grad + ((size_t)t * N + n) * CTC_C) + lane;
+      if (!live[u]) {
+        *gp = make_float2(0.f, 0.f);
+      } else {
+        const float lse = s_lse[t];
+        const float y0 = ptx::ex2(x[u].x * LOG2E - lse), y1 = ptx::ex2(x[u].y * LOG2E - lse);
+        *gp = make_float2(grad_scale * (y0 - acc[u * CTC_C + 2 * lane]), grad_scale * (y1 - acc[u * CTC_C + 2 * lane + 1]));
+      }
+    }
     __syncwarp();
   }
 }
@@ -285,7 +319,7 @@ __global__ void __launch_bounds__(128) ctc_greedy_kernel(const float* __restrict
   if (lane == 0) out_len[n] = count;
 }
 
-size_t ctc_smem_bytes(int T, int KS) { return sizeof(float) * ((size_t)T + 3 * (size_t)T * 32 * KS + 2 * CTC_C); }
+size_t ctc_smem_bytes(int T, int KS) { return sizeof(float) * ((size_t)T + 3 * (size_t)T * 32 * KS + 8 * CTC_C); }
 
 template <int KS>
 int launch_ctc(const float* logits, float* grad, const int* flat_labels, const int* label_len, const int* input_len,

@@ -39,7 +39,8 @@ enum Epi {
   EPI_RELU_POOL12 = 4,  // conv: + bias, ReLU, max over Wd pairs        (conv3_2 + pool), needs Wd=8
   EPI_STATS = 5,        // conv: + bias -> bf16 pre-BN, per-channel sum / sum^2 (f64 atomics) (conv4_x)
   EPI_LSTM = 6,         // recurrent step: gates = acc + xproj; LSTM cell; writes h, c, output
-  EPI_LOGITS = 7        // + bias -> f32 time-major [T, N, 64]
+  EPI_LOGITS = 7,       // + bias -> f32 time-major [T, N, 64]
+  EPI_XPROJ = 8         // + bias -> bf16 [N*H, 2048]; columns >= 1024 (backward direction) stored reversed-by-length
 };
 
 struct Params {
@@ -252,9 +253,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               *reinterpret_cast<uint4*>(out + c0 + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
           }
         }
-      } else if (EPI == EPI_BIAS_BF16) {
+      } else if (EPI == EPI_BIAS_BF16 || EPI == EPI_XPROJ) {
         const int grow = m_blk * BLOCK_M + row;
-        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)grow * p.ldo + col0;
+        int drow = grow;
+        if (EPI == EPI_XPROJ && col0 >= 1024 && grow < p.M) {
+          // tf.reverse_sequence(len) on the backward direction's input, done once at write time
+          const int n = grow / p.H, t = grow - n * p.H;
+          const int len = min(max(__ldg(p.seq_len + n), 0), p.T);
+          if (t < len) drow = n * p.H + (len - 1 - t);
+        }
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)drow * p.ldo + col0;
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
           uint32_t v[32];

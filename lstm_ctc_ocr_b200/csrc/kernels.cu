@@ -152,11 +152,12 @@ __global__ void __launch_bounds__(256) bn_apply_relu_pool12_kernel(const uint4* 
 
 // ------------------------------------------------------------------------------------------------
 // weight re-layout: dst[perm(c)][r] (bf16, K-major GEMM B operand) = src[r][c] (f32, TF layout)
-// perm_mode 0: identity; 1: LSTM gate permutation  j = g*256+u  ->  (u/64)*256 + g*64 + u%64
+// perm_mode 0: identity; upc > 0: LSTM gate permutation  j = g*256+u  ->  (u/upc)*4*upc + g*upc + u%upc
+// (a tile of 4*upc consecutive rows then holds [i|j|f|o] of upc hidden units)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int lstm_perm(int j) {
+__device__ __forceinline__ int lstm_perm(int j, int upc) {
   const int g = j >> 8, u = j & 255;
-  return (u >> 6) * 256 + g * 64 + (u & 63);
+  return (u / upc) * 4 * upc + g * upc + (u % upc);
 }
 __global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __restrict__ src, int R, int Cc, int ld_src,
                                                              __nv_bfloat16* __restrict__ dst, int ld_dst,
@@ -172,18 +173,18 @@ __global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __rest
   for (int i = ty; i < 32; i += 8) {
     const int c = c0 + i, r = r0 + tx;
     if (c < Cc && r < R) {
-      const int dc = perm_mode ? lstm_perm(c) : c;
+      const int dc = perm_mode ? lstm_perm(c, perm_mode) : c;
       dst[(size_t)dc * ld_dst + r] = __float2bfloat16_rn(tile[tx][i]);
     }
   }
 }
 __global__ void lstm_bias_prep_kernel(const float* __restrict__ b_fw, const float* __restrict__ b_bw,
-                                      float* __restrict__ xbias) {
+                                      float* __restrict__ xbias, int upc) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;   // 0..2047
   if (j >= 2048) return;
   const int dir = j >> 10, jj = j & 1023;
   const float v = (dir ? b_bw : b_fw)[jj] + (((jj >> 8) == 2) ? 1.0f : 0.0f);   // forget_bias = 1.0 on gate f
-  xbias[dir * 1024 + lstm_perm(jj)] = v;
+  xbias[dir * 1024 + lstm_perm(jj, upc)] = v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -276,8 +277,8 @@ int launch_transpose_cast(const float* src, int R, int Cc, int ld_src, __nv_bflo
   CUDA_TRY(cudaGetLastError());
   return CRNN_OK;
 }
-int launch_lstm_bias_prep(const float* b_fw, const float* b_bw, float* xbias, cudaStream_t st) {
-  lstm_bias_prep_kernel<<<8, 256, 0, st>>>(b_fw, b_bw, xbias);
+int launch_lstm_bias_prep(const float* b_fw, const float* b_bw, float* xbias, int upc, cudaStream_t st) {
+  lstm_bias_prep_kernel<<<8, 256, 0, st>>>(b_fw, b_bw, xbias, upc);
   CUDA_TRY(cudaGetLastError());
   return CRNN_OK;
 }

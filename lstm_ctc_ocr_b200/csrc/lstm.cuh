@@ -1,0 +1,219 @@
+// Persistent BiLSTM recurrence for sm_100a: one thread-block CLUSTER per (direction, 128-sample batch tile).
+//
+// Replaces the tf.while_loop of tf.contrib.rnn.LSTMCell(256) under bidirectional_dynamic_rnn
+// (lib/networks/network.py:104-107): per step  z = x_t W_x + b (precomputed, `xproj`) + h_{t-1} W_h ;
+// i,j,f,o = split(z); c = sigma(f+1) c + sigma(i) tanh(j); h = sigma(o) tanh(c); zero output past sequence_length.
+//
+// Cluster of CS CTAs; CTA `rank` owns UPC = 256/CS hidden units (4*UPC gate columns, ordered [i|j|f|o]):
+//   * its W_h slice [4*UPC x 256] bf16 stays resident in shared memory for all T steps (loaded once by TMA)
+//   * per step: TMA loads h_{t-1} [128 x 256] (written to global/L2 by the whole cluster in the previous step),
+//     one elected thread issues 16 tcgen05.mma (128 x 4*UPC x 16) into TMEM, 4 epilogue warps (thread = sample row)
+//     add the precomputed input projection (prefetched to registers before the MMA wait), run the cell with the
+//     f32 cell state held in REGISTERS for the whole sequence, write h (bf16) for the next step and the output row
+//   * one barrier.cluster per step orders the h exchange (generic-proxy global stores -> fence.proxy.async ->
+//     release/acquire cluster barrier -> TMA loads of the next step)
+// Clusters are independent (no grid-wide sync), so partial residency cannot deadlock.
+// The backward direction reads xproj rows that the projection GEMM already stored reversed-by-length, so both
+// directions index step s uniformly; outputs are written back at t = len-1-s.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace lstm {
+
+constexpr int NUM_THREADS = 192;
+constexpr int BLOCK_M = 128;
+
+struct Params {
+  const __nv_bfloat16* xproj;   // [Nimg*H, 2048]: [fw 1024 | bw 1024 (rows reversed by length)], permuted columns
+  __nv_bfloat16* h_state;       // [2 bufs][2 dirs][Npad][256]
+  __nv_bfloat16* lstm_out;      // [Nimg*H, 512]
+  const int* seq_len;           // [Nimg]
+  int Nimg, Npad, H, T, tiles_per_dir;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+template <int CS>
+struct Cfg {
+  static constexpr int UPC = 256 / CS;          // hidden units per CTA
+  static constexpr int NCOLS = 4 * UPC;         // gate columns per CTA
+  static constexpr int B_BYTES = 4 * NCOLS * 128;   // 4 K-blocks x [NCOLS rows x 128 B]
+  static constexpr int A_BYTES = 4 * BLOCK_M * 128; // 4 K-blocks x [128 rows x 128 B]
+  static constexpr int BAR_OFFSET = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFFSET + 128 + 1024;
+};
+
+template <int CS>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW, const Params p) {
+  static_assert(CS == 8, "register budget of the epilogue is sized for 32 units per CTA");
+  using C = Cfg<CS>;
+  constexpr int UPC = C::UPC, NCOLS = C::NCOLS;
+  constexpr uint32_t IDESC = ptx::make_idesc_bf16(BLOCK_M, NCOLS);
+  constexpr int HALF = UPC / 2;                 // units processed per epilogue pass (register budget)
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::A_BYTES;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + C::BAR_OFFSET);   // [4] one per K-block
+  uint64_t* b_full = a_full + 4;
+  uint64_t* acc_full = b_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int unit = blockIdx.x / CS;                   // (dir, batch tile)
+  const int dir = unit / p.tiles_per_dir;
+  const int tile = unit - dir * p.tiles_per_dir;
+
+  if (warp_idx == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmH);
+    ptx::prefetch_tmap(&tmW);
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(&a_full[i], 1);
+    ptx::mbar_init(b_full, 1);
+    ptx::mbar_init(acc_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp_idx == 1) {
+    ptx::tmem_alloc(tmem_ptr, NCOLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // resident recurrent weights: rows [dir*1024 + rank*NCOLS, +NCOLS) of Bh [2048, 256]
+  if (warp_idx == 0 && lane == 0) {
+    ptx::mbar_arrive_expect_tx(b_full, C::B_BYTES);
+    for (int kb = 0; kb < 4; ++kb)
+      ptx::tma_load_2d(&tmW, b_full, smem_b + kb * NCOLS * 128, kb * 64, dir * 1024 + rank * NCOLS);
+  }
+
+  // ---- per-thread epilogue state (warps 2..5): one sample row, UPC units, cell state in registers
+  const int q = warp_idx & 3;
+  const int row = q * 32 + lane;
+  const int n = tile * BLOCK_M + row;
+  const bool is_epi = warp_idx >= 2;
+  const bool okn = is_epi && (n < p.Nimg);
+  const int len = okn ? min(max(__ldg(p.seq_len + n), 0), p.T) : 0;
+  float cst[UPC];
+#pragma unroll
+  for (int i = 0; i < UPC; ++i) cst[i] = 0.f;
+
+  if (warp_idx == 1 && lane == 0) ptx::mbar_wait(b_full, 0);      // W_h slice resident before the first MMA / exit
+
+  for (int s = 0; s < p.T; ++s) {
+    if (warp_idx == 0) {
+      if (lane == 0 && s > 0) {
+        fence_proxy_async_all();
+        const int hrow = ((s & 1) * 2 + dir) * p.Npad + tile * BLOCK_M;
+        for (int kb = 0; kb < 4; ++kb) {
+          ptx::mbar_arrive_expect_tx(&a_full[kb], BLOCK_M * 128);
+          ptx::tma_load_2d(&tmH, &a_full[kb], smem_a + kb * BLOCK_M * 128, kb * 64, hrow);
+        }
+      }
+      __syncwarp();
+    } else if (warp_idx == 1) {
+      if (lane == 0 && s > 0) {
+        const uint32_t ph = (s - 1) & 1;
+        for (int kb = 0; kb < 4; ++kb) {
+          ptx::mbar_wait(&a_full[kb], ph);
+          ptx::tc_fence_after();
+          const uint64_t a_desc = ptx::make_desc_k_sw128(ptx::smem_u32(smem_a + kb * BLOCK_M * 128));
+          const uint64_t b_desc = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b + kb * NCOLS * 128));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0);
+        }
+        ptx::tc_commit(acc_full);
+      }
+      __syncwarp();
+    } else {
+      const bool active = s < len;
+      const int t = active ? (dir ? (len - 1 - s) : s) : s;
+      // prefetch this step's input projection (row n, step s; bw rows were stored reversed by the projection GEMM)
+      uint4 xp[UPC / 2];                                   // 4 gates x UPC bf16 = UPC/2 x 16 B
+      if (active) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.xproj + ((size_t)n * p.H + s) * 2048 + dir * 1024 + rank * NCOLS);
+#pragma unroll
+        for (int i = 0; i < UPC / 2; ++i) xp[i] = __ldg(src + i);
+      }
+      if (s > 0) {
+        ptx::mbar_wait(acc_full, (s - 1) & 1);
+        ptx::tc_fence_after();
+      }
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      __nv_bfloat16* hn = p.h_state + ((size_t)(((s + 1) & 1) * 2 + dir) * p.Npad + n) * 256 + rank * UPC;
+      __nv_bfloat16* lo = p.lstm_out + ((size_t)n * p.H + t) * 512 + dir * 256 + rank * UPC;
+      const uint32_t* xw = reinterpret_cast<const uint32_t*>(xp);    // gate g, unit u -> bf16 index g*UPC + u
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int u0 = hh * HALF;
+        uint32_t gi[HALF], gj[HALF], gf[HALF], go[HALF];
+        if (s > 0) {
+          ptx::tmem_ld_32x32b_x16(tbase + 0 * UPC + u0, gi);
+          ptx::tmem_ld_32x32b_x16(tbase + 1 * UPC + u0, gj);
+          ptx::tmem_ld_32x32b_x16(tbase + 2 * UPC + u0, gf);
+          ptx::tmem_ld_32x32b_x16(tbase + 3 * UPC + u0, go);
+          ptx::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < HALF; ++i) { gi[i] = 0u; gj[i] = 0u; gf[i] = 0u; go[i] = 0u; }
+        }
+        uint32_t hp[HALF / 2];
+        if (active) {
+          float hv[HALF];
+#pragma unroll
+          for (int i = 0; i < HALF; ++i) {
+            const int u = u0 + i;
+            const uint32_t wi = xw[(0 * UPC + u) >> 1], wj = xw[(1 * UPC + u) >> 1], wf = xw[(2 * UPC + u) >> 1], wo = xw[(3 * UPC + u) >> 1];
+            const float zi = __uint_as_float(gi[i]) + ((u & 1) ? ptx::bf16_hi(wi) : ptx::bf16_lo(wi));
+            const float zj = __uint_as_float(gj[i]) + ((u & 1) ? ptx::bf16_hi(wj) : ptx::bf16_lo(wj));
+            const float zf = __uint_as_float(gf[i]) + ((u & 1) ? ptx::bf16_hi(wf) : ptx::bf16_lo(wf));
+            const float zo = __uint_as_float(go[i]) + ((u & 1) ? ptx::bf16_hi(wo) : ptx::bf16_lo(wo));
+            const float c = ptx::fast_sigmoid(zf) * cst[u] + ptx::fast_sigmoid(zi) * ptx::fast_tanh(zj);   // +1.0 folded into bias
+            cst[u] = c;
+            hv[i] = ptx::fast_sigmoid(zo) * ptx::fast_tanh(c);
+          }
+#pragma unroll
+          for (int i = 0; i < HALF / 2; ++i) hp[i] = ptx::pack_bf16x2(hv[2 * i], hv[2 * i + 1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < HALF / 2; ++i) hp[i] = 0u;     // zero output past sequence_length
+        }
+        if (okn) {
+#pragma unroll
+          for (int i = 0; i < HALF / 2; i += 4) {
+            const uint4 v = make_uint4(hp[i], hp[i + 1], hp[i + 2], hp[i + 3]);
+            *reinterpret_cast<uint4*>(hn + u0 + 2 * i) = v;
+            *reinterpret_cast<uint4*>(lo + u0 + 2 * i) = v;
+          }
+        }
+      }
+      // make this thread's h stores visible to the async proxy (TMA loads of the next step) of the whole cluster
+      fence_proxy_async_all();
+      ptx::tc_fence_before();
+    }
+    cluster_arrive_release();
+    cluster_wait_acquire();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, NCOLS);
+  }
+}
+
+}  // namespace lstm

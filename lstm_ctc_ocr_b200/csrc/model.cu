@@ -5,7 +5,10 @@
 #include <string>
 #include <vector>
 
+#include <cstdlib>
+
 #include "gemm.cuh"
+#include "lstm.cuh"
 #include "kernels.cuh"
 
 // ------------------------------------------------------------------------------------------------ errors
@@ -103,7 +106,7 @@ struct Plan {
   float* c_state;
   double* stats;        // [2 layers][2][512]
   float* bn;            // [2 layers][4][512]: scale, shift, mean, invstd
-  CUtensorMap tA_c2, tA_c31, tA_c32, tA_c41, tA_c42, tA_c5, tA_x, tA_h[2], tA_l;
+  CUtensorMap tA_c2, tA_c31, tA_c32, tA_c41, tA_c42, tA_c5, tA_x, tA_h[2], tA_l, tA_hall;
 };
 
 struct crnn_model {
@@ -118,7 +121,8 @@ struct crnn_model {
   float* xbias = nullptr;    // [2048] permuted LSTM bias with forget_bias folded in
   double* sumsq = nullptr;
   void* wblock = nullptr;
-  CUtensorMap tB_c2, tB_c31, tB_c32, tB_c41, tB_c42, tB_c5, tB_x, tB_h, tB_l;
+  CUtensorMap tB_c2, tB_c31, tB_c32, tB_c41, tB_c42, tB_c5, tB_x, tB_h, tB_l, tB_h128;
+  int lstm_upc = 32;         // hidden units per gate tile: 32 = persistent cluster kernel (default), 64 = per-step launches
   Plan plan;
   // per-stage CUDA-event profiling (crnn_profile_*): events are recorded on the caller's stream between stages
   std::vector<cudaEvent_t> prof_events;   // [slots][kNumStages + 1]
@@ -179,6 +183,7 @@ extern "C" int crnn_model_create(const crnn_config* cfg, crnn_model** out) {
     return crnn_fail(CRNN_UNSUPPORTED, "model_create: needs sm_100 (found sm_%d%d)", prop.major, prop.minor);
   }
   m->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("CRNN_LSTM_IMPL")) m->lstm_upc = (std::string(e) == "step") ? 64 : 32;   // debug A/B switch
 
   // one allocation for all derived operand copies
   const size_t nB[9] = {128 * 576, 256 * 1152, 256 * 2304, 512 * 2304, 512 * 4608, 512 * 2048, 2048 * 512, 2048 * 256, 64 * 512};
@@ -200,6 +205,7 @@ extern "C" int crnn_model_create(const crnn_config* cfg, crnn_model** out) {
   if (st == CRNN_OK) st = make_tmap_2d(&m->tB_c5, m->Bc5, 512, 2048, 2048, 256);
   if (st == CRNN_OK) st = make_tmap_2d(&m->tB_x, m->Bx, 2048, 512, 512, 256);
   if (st == CRNN_OK) st = make_tmap_2d(&m->tB_h, m->Bh, 2048, 256, 256, 256);
+  if (st == CRNN_OK) st = make_tmap_2d(&m->tB_h128, m->Bh, 2048, 256, 256, 128);
   if (st == CRNN_OK) st = make_tmap_2d(&m->tB_l, m->Bl, 64, 512, 512, 64);
   if (st != CRNN_OK) { cudaFree(m->wblock); delete m; return st; }
   *out = m;
@@ -246,10 +252,10 @@ static int prepare_weights(crnn_model* m, cudaStream_t st) {
   const char* dirs[2] = {"logits/bidirectional_rnn/fw/lstm_cell", "logits/bidirectional_rnn/bw/lstm_cell"};
   for (int d = 0; d < 2; ++d) {
     const float* w = m->P(std::string(dirs[d]) + "/weights");                 // [768,1024], rows [x(512); h(256)]
-    CRNN_TRY(launch_transpose_cast(w, 512, 1024, 1024, m->Bx + (size_t)d * 1024 * 512, 512, 1, st));
-    CRNN_TRY(launch_transpose_cast(w + 512 * 1024, 256, 1024, 1024, m->Bh + (size_t)d * 1024 * 256, 256, 1, st));
+    CRNN_TRY(launch_transpose_cast(w, 512, 1024, 1024, m->Bx + (size_t)d * 1024 * 512, 512, m->lstm_upc, st));
+    CRNN_TRY(launch_transpose_cast(w + 512 * 1024, 256, 1024, 1024, m->Bh + (size_t)d * 1024 * 256, 256, m->lstm_upc, st));
   }
-  CRNN_TRY(launch_lstm_bias_prep(m->P(std::string(dirs[0]) + "/biases"), m->P(std::string(dirs[1]) + "/biases"), m->xbias, st));
+  CRNN_TRY(launch_lstm_bias_prep(m->P(std::string(dirs[0]) + "/biases"), m->P(std::string(dirs[1]) + "/biases"), m->xbias, m->lstm_upc, st));
   CRNN_TRY(launch_transpose_cast(m->P("logits/weights"), 512, 64, 64, m->Bl, 512, 0, st));
   // L2 term depends only on the parameters: computed here, consumed by crnn_total_loss
   SumsqSegs segs;
@@ -315,6 +321,7 @@ static int build_plan(crnn_model* m, int N, int W, void* ws, cudaStream_t st) {
   CRNN_TRY(make_tmap_2d(&pl.tA_x, pl.a5, (uint64_t)N * pl.H2, 512, 512, 128));
   for (int b = 0; b < 2; ++b)
     CRNN_TRY(make_tmap_2d(&pl.tA_h[b], pl.h_state + (size_t)b * 2 * pl.Npad * 256, (uint64_t)2 * pl.Npad, 256, 256, 128));
+  CRNN_TRY(make_tmap_2d(&pl.tA_hall, pl.h_state, (uint64_t)4 * pl.Npad, 256, 256, 128));
   CRNN_TRY(make_tmap_2d(&pl.tA_l, pl.lstm_out, (uint64_t)N * pl.H2, 512, 512, 128));
   // rows t = T (= H2-1) of lstm_out are never produced by a time step: keep them defined (zero)
   CUDA_TRY(cudaMemsetAsync(pl.lstm_out, 0, (size_t)N * pl.H2 * 512 * 2, st));
@@ -438,21 +445,48 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
     p.M = N * H2;
     p.num_m_tiles = (p.M + 127) / 128; p.num_n_tiles = 8; p.num_k_blocks = 8; p.kb_per_shift = 8;
     p.Nc = 2048; p.bias = m->xbias; p.out = pl.xproj; p.ldo = 2048;
-    CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 4>(pl.tA_x, m->tB_x, p, sms, st)));
+    p.H = H2; p.T = T; p.seq_len = time_step_len;
+    if (m->lstm_upc == 32) CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_XPROJ, 4>(pl.tA_x, m->tB_x, p, sms, st)));
+    else CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 4>(pl.tA_x, m->tB_x, p, sms, st)));
   }
   STAGE_MARK();
-  // recurrence: one launch per time step covers both directions (fw rows [0,Npad), bw rows [Npad,2Npad))
-  CUDA_TRY(cudaMemsetAsync(pl.h_state, 0, (size_t)2 * pl.Npad * 256 * 2, st));
-  CUDA_TRY(cudaMemsetAsync(pl.c_state, 0, (size_t)2 * pl.Npad * 256 * 4, st));
-  for (int s = 0; s < T; ++s) {
-    gemm::Params p;
-    memset(&p, 0, sizeof(p));
-    p.num_m_tiles = 2 * pl.Npad / 128; p.num_n_tiles = 4; p.num_k_blocks = 4; p.kb_per_shift = 4;
-    p.m_tiles_per_dir = pl.Npad / 128;
-    p.Nc = 1024; p.H = H2; p.T = T; p.Nimg = N; p.Npad = pl.Npad; p.step = s;
-    p.xproj = pl.xproj; p.c_state = pl.c_state; p.lstm_out = pl.lstm_out; p.seq_len = time_step_len;
-    p.h_next = pl.h_state + (size_t)((s + 1) & 1) * 2 * pl.Npad * 256;
-    CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_LSTM, 4>(pl.tA_h[s & 1], m->tB_h, p, sms, st)));
+  if (m->lstm_upc == 32) {
+    // recurrence: ONE persistent launch; a cluster of 8 CTAs per (direction, 128-sample tile) -- csrc/lstm.cuh
+    constexpr int CS = 8;
+    lstm::Params lp;
+    lp.xproj = pl.xproj; lp.h_state = pl.h_state; lp.lstm_out = pl.lstm_out; lp.seq_len = time_step_len;
+    lp.Nimg = N; lp.Npad = pl.Npad; lp.H = H2; lp.T = T; lp.tiles_per_dir = pl.Npad / 128;
+    auto kern = lstm::lstm_persistent_kernel<CS>;
+    static bool attr = false;
+    if (!attr) {
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::Cfg<CS>::SMEM_BYTES));
+      attr = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(CS * 2 * lp.tiles_per_dir);
+    cfg.blockDim = dim3(lstm::NUM_THREADS);
+    cfg.dynamicSmemBytes = lstm::Cfg<CS>::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, pl.tA_hall, m->tB_h128, lp));
+  } else {
+    // per-step launches (debug fallback, CRNN_LSTM_IMPL=step): both directions stacked along M
+    CUDA_TRY(cudaMemsetAsync(pl.h_state, 0, (size_t)2 * pl.Npad * 256 * 2, st));
+    CUDA_TRY(cudaMemsetAsync(pl.c_state, 0, (size_t)2 * pl.Npad * 256 * 4, st));
+    for (int s = 0; s < T; ++s) {
+      gemm::Params p;
+      memset(&p, 0, sizeof(p));
+      p.num_m_tiles = 2 * pl.Npad / 128; p.num_n_tiles = 4; p.num_k_blocks = 4; p.kb_per_shift = 4;
+      p.m_tiles_per_dir = pl.Npad / 128;
+      p.Nc = 1024; p.H = H2; p.T = T; p.Nimg = N; p.Npad = pl.Npad; p.step = s;
+      p.xproj = pl.xproj; p.c_state = pl.c_state; p.lstm_out = pl.lstm_out; p.seq_len = time_step_len;
+      p.h_next = pl.h_state + (size_t)((s + 1) & 1) * 2 * pl.Npad * 256;
+      CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_LSTM, 4>(pl.tA_h[s & 1], m->tB_h, p, sms, st)));
+    }
   }
   STAGE_MARK();
   // 512 -> 64 projection, written time-major [T, N, 64] (network.py:126-128)

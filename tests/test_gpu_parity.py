@@ -270,3 +270,26 @@ def test_full_size_c3_properties():
     out, out_len = engine.ctc_greedy(logits2, t(tsl))
     assert int((out_len > t(tsl)).sum()) == 0
     assert int(out.max()) <= 62 and int(out.min()) >= 0
+
+
+def test_persistent_cluster_lstm_matches_per_step_kernel():
+    """csrc/lstm.cuh (one persistent cluster launch) vs the per-step GEMM+cell launches (CRNN_LSTM_IMPL=step)."""
+    from lstm_ctc_ocr_b200 import engine, synthetic
+    N, W = 200, 100
+    params = synthetic.init_params(3, logits_scale=10.0)
+    widths = np.random.default_rng(2).integers(8, 101, size=N)
+    data, _, _, tsl = synthetic.synth_batch(N, W, seed=12, widths=widths)
+    t = lambda a: torch.tensor(a, device=DEV)
+    outs = []
+    for impl in ("persistent", "step"):
+        os.environ["CRNN_LSTM_IMPL"] = impl
+        try:
+            m = engine.CrnnModel(device=DEV)
+        finally:
+            os.environ.pop("CRNN_LSTM_IMPL", None)
+        m.load_params(params)
+        logits = m.forward(t(data), t(tsl)).clone()
+        outs.append((logits.cpu().numpy(), m.tap("lstm_out", N, W).cpu().numpy()))
+        del m
+    assert np.abs(outs[0][1] - outs[1][1]).max() <= 1e-2        # bf16 h, identical math up to MMA tile order
+    assert rel(outs[0][0], outs[1][0]) < 5e-3

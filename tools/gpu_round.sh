@@ -2,7 +2,8 @@
 # One gpurun call: parity tests, bench, ncu launch list, ncu full capture of the top kernels.
 mkdir -p gpurun_out
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
-echo "== pytest -m gpu"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 | tee gpurun_out/pytest_gpu.log
+echo "== diag (fast fail)"; timeout 180 python tools/diag.py > gpurun_out/diag.log 2>&1 || { echo "DIAG FAILED rc=$?"; tail -30 gpurun_out/diag.log; exit 1; }; tail -28 gpurun_out/diag.log
+echo "== pytest -m gpu"; timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -15 | tee gpurun_out/pytest_gpu.log
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 echo "== bench"; timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_ref.json
