@@ -3,7 +3,7 @@
 // Replaces warpctc_tensorflow.ctc at lib/networks/network.py:653-654 and the decode at
 // lib/networks/network.py:656-657 (+ zero stripping, lib/lstm/utils/training.py:32).
 //
-// ctc_loss_kernel: one CTA (2 warps) per utterance.
+// ctc_loss_kernel: one CTA (4 warps) per utterance; warps 0/1 run the two recursions, all 4 share the frame-parallel phases.
 //   phase 0  both warps, rows interleaved: log2-softmax normaliser per frame and the S <= 32*KS
 //            emission scores e[t][s] = log2 y_t(l'_s), kept in shared memory (HBM read #1, coalesced 256 B rows)
 //   phase 1  warp 0 runs the alpha recursion forward while warp 1 runs the beta recursion backward --
@@ -17,6 +17,10 @@
 namespace {
 
 constexpr int CTC_C = 64;
+constexpr int CTC_WARPS = 4;                 // phases 0/2 are parallel over frames: 4 warps x 16 rows covers T <= 64 in one batch
+constexpr int CTC_THREADS = 32 * CTC_WARPS;
+constexpr int CTC_RB = 16;                   // rows per warp per batch: all 16 loads are issued before any use (MLP)
+constexpr int CTC_RG = 4;                    // rows reduced in lockstep (ILP) within a batch
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 #define NEG_INF (-INFINITY)
@@ -39,7 +43,7 @@ __device__ __forceinline__ float lse3(float a, float b, float c) {
 }
 
 template <int KS>
-__global__ void __launch_bounds__(64) ctc_loss_kernel(const float* __restrict__ logits, float* __restrict__ grad,
+__global__ void __launch_bounds__(CTC_THREADS, 8) ctc_loss_kernel(const float* __restrict__ logits, float* __restrict__ grad,
                                                       const int* __restrict__ flat_labels,
                                                       const int* __restrict__ label_len,
                                                       const int* __restrict__ input_len, int T, int N, int blank,
@@ -50,7 +54,7 @@ __global__ void __launch_bounds__(64) ctc_loss_kernel(const float* __restrict__ 
   float* s_e = s_lse + T;               // [T][SP]
   float* s_alpha = s_e + (size_t)T * SP;
   float* s_beta = s_alpha + (size_t)T * SP;
-  float* s_acc = s_beta + (size_t)T * SP;   // [2 warps][4 rows][64]
+  float* s_acc = s_beta + (size_t)T * SP;   // [4 warps][4 rows][64]
   __shared__ int s_off;
   __shared__ int s_ext[SP];
   __shared__ int s_repeats;
@@ -74,7 +78,7 @@ __global__ void __launch_bounds__(64) ctc_loss_kernel(const float* __restrict__ 
   const bool too_long = (S > SP) || (L < 0);
   if (!too_long) {
     int rep = 0;
-    for (int s = threadIdx.x; s < SP; s += 64) {
+    for (int s = threadIdx.x; s < SP; s += CTC_THREADS) {
       int v = blank;
       if (s < S && (s & 1)) {
         v = flat_labels[s_off + (s >> 1)];
@@ -93,7 +97,7 @@ __global__ void __launch_bounds__(64) ctc_loss_kernel(const float* __restrict__ 
   if (!feasible) {
     if (threadIdx.x == 0) costs[n] = too_long ? __int_as_float(0x7fc00000) : 0.0f;
     if (grad != nullptr) {
-      for (int t = warp; t < T; t += 2)
+      for (int t = warp; t < T; t += CTC_WARPS)
         *reinterpret_cast<float2*>(grad + ((size_t)t * N + n) * CTC_C + 2 * lane) = make_float2(0.f, 0.f);
     }
     return;
@@ -103,39 +107,46 @@ __global__ void __launch_bounds__(64) ctc_loss_kernel(const float* __restrict__ 
   int cls[KS];
 #pragma unroll
   for (int k = 0; k < KS; ++k) cls[k] = s_ext[lane * KS + k];
-  for (int t0 = warp; t0 < Tn; t0 += 8) {
-    // 4 rows per iteration, reductions interleaved for ILP (rows t0, t0+2, t0+4, t0+6 belong to this warp)
-    float x0[4], x1[4], m[4], sum[4];
+  for (int t0 = warp; t0 < Tn; t0 += CTC_WARPS * CTC_RB) {
+    float2 xr[CTC_RB];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int t = t0 + 2 * u;
-      const float2 x = (t < Tn) ? __ldg(reinterpret_cast<const float2*>(logits + ((size_t)t * N + n) * CTC_C) + lane)
-                                : make_float2(0.f, 0.f);
-      x0[u] = x.x * LOG2E; x1[u] = x.y * LOG2E;
-      m[u] = fmaxf(x0[u], x1[u]);
+    for (int u = 0; u < CTC_RB; ++u) {
+      const int t = t0 + CTC_WARPS * u;
+      xr[u] = (t < Tn) ? __ldg(reinterpret_cast<const float2*>(logits + ((size_t)t * N + n) * CTC_C) + lane)
+                       : make_float2(0.f, 0.f);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
+    for (int g = 0; g < CTC_RB; g += CTC_RG) {
+      if (t0 + CTC_WARPS * g >= Tn) break;               // warp-uniform
+      float x0[CTC_RG], x1[CTC_RG], m[CTC_RG], sum[CTC_RG];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) m[u] = fmaxf(m[u], __shfl_xor_sync(0xffffffffu, m[u], o));
-#pragma unroll
-    for (int u = 0; u < 4; ++u) sum[u] = ptx::ex2(x0[u] - m[u]) + ptx::ex2(x1[u] - m[u]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-      for (int u = 0; u < 4; ++u) sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], o);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int t = t0 + 2 * u;
-      const float lse = m[u] + ptx::lg2(sum[u]);
-#pragma unroll
-      for (int k = 0; k < KS; ++k) {
-        const int c = cls[k];
-        const float v0 = __shfl_sync(0xffffffffu, x0[u], c >> 1);
-        const float v1 = __shfl_sync(0xffffffffu, x1[u], c >> 1);
-        if (t < Tn) s_e[(size_t)t * SP + lane * KS + k] = ((c & 1) ? v1 : v0) - lse;
+      for (int u = 0; u < CTC_RG; ++u) {
+        x0[u] = xr[g + u].x * LOG2E; x1[u] = xr[g + u].y * LOG2E;
+        m[u] = fmaxf(x0[u], x1[u]);
       }
-      if (lane == 0 && t < Tn) s_lse[t] = lse;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int u = 0; u < CTC_RG; ++u) m[u] = fmaxf(m[u], __shfl_xor_sync(0xffffffffu, m[u], o));
+#pragma unroll
+      for (int u = 0; u < CTC_RG; ++u) sum[u] = ptx::ex2(x0[u] - m[u]) + ptx::ex2(x1[u] - m[u]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int u = 0; u < CTC_RG; ++u) sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], o);
+#pragma unroll
+      for (int u = 0; u < CTC_RG; ++u) {
+        const int t = t0 + CTC_WARPS * (g + u);
+        const float lse = m[u] + ptx::lg2(sum[u]);
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+          const int c = cls[k];
+          const float v0 = __shfl_sync(0xffffffffu, x0[u], c >> 1);
+          const float v1 = __shfl_sync(0xffffffffu, x1[u], c >> 1);
+          if (t < Tn) s_e[(size_t)t * SP + lane * KS + k] = ((c & 1) ? v1 : v0) - lse;
+        }
+        if (lane == 0 && t < Tn) s_lse[t] = lse;
+      }
     }
   }
   __syncthreads();
@@ -151,7 +162,9 @@ __global__ void __launch_bounds__(64) ctc_loss_kernel(const float* __restrict__ 
       skip_out[k] = (s + 2 < S) && (s_ext[s + 2] != blank) && (s_ext[s + 2] != s_ext[s]);
     }
     float a[KS];
-    if (warp == 0) {
+    if (warp >= 2) {
+      // idle during the two recursions (frame-parallel phases only)
+    } else if (warp == 0) {
 #pragma unroll
       for (int k = 0; k < KS; ++k) {
         int s = lane * KS + k;
@@ -222,60 +235,69 @@ __global__ void __launch_bounds__(64) ctc_loss_kernel(const float* __restrict__ 
   if (grad == nullptr) return;
 
   // ---------------- phase 2: gradient rows ----------------
-  float* acc = s_acc + warp * 4 * CTC_C;          // [4 rows][64] per warp
-  for (int t0 = warp; t0 < T; t0 += 8) {
-    float2 x[4];
-    bool live[4];
+  float* acc = s_acc + warp * CTC_RG * CTC_C;         // [CTC_RG rows][64] per warp
+  for (int t0 = warp; t0 < T; t0 += CTC_WARPS * CTC_RB) {
+    float2 xr[CTC_RB];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int t = t0 + 2 * u;
-      live[u] = (t < Tn) && (ll2 != NEG_INF);
-      x[u] = live[u] ? __ldg(reinterpret_cast<const float2*>(logits + ((size_t)t * N + n) * CTC_C) + lane) : make_float2(0.f, 0.f);
-      acc[u * CTC_C + 2 * lane] = 0.f;
-      acc[u * CTC_C + 2 * lane + 1] = 0.f;
+    for (int u = 0; u < CTC_RB; ++u) {
+      const int t = t0 + CTC_WARPS * u;
+      xr[u] = ((t < Tn) && (ll2 != NEG_INF)) ? __ldg(reinterpret_cast<const float2*>(logits + ((size_t)t * N + n) * CTC_C) + lane)
+                                             : make_float2(0.f, 0.f);
     }
-    __syncwarp();
-    float blank_sum[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int t = t0 + 2 * u;
-      blank_sum[u] = 0.f;
-      if (live[u]) {
+    for (int g = 0; g < CTC_RB; g += CTC_RG) {
+      if (t0 + CTC_WARPS * g >= T) break;                 // warp-uniform
+      bool live[CTC_RG];
 #pragma unroll
-        for (int k = 0; k < KS; ++k) {
-          const int st = lane * KS + k;
-          if (st < S) {
-            const size_t i = (size_t)t * SP + st;
-            const float w = ptx::ex2(s_alpha[i] + s_beta[i] - s_e[i] - ll2);   // alpha*beta / y / p(l|x)
-            if (st & 1) atomicAdd(&acc[u * CTC_C + cls[k]], w);
-            else blank_sum[u] += w;
+      for (int u = 0; u < CTC_RG; ++u) {
+        const int t = t0 + CTC_WARPS * (g + u);
+        live[u] = (t < Tn) && (ll2 != NEG_INF);
+        acc[u * CTC_C + 2 * lane] = 0.f;
+        acc[u * CTC_C + 2 * lane + 1] = 0.f;
+      }
+      __syncwarp();
+      float blank_sum[CTC_RG];
+#pragma unroll
+      for (int u = 0; u < CTC_RG; ++u) {
+        const int t = t0 + CTC_WARPS * (g + u);
+        blank_sum[u] = 0.f;
+        if (live[u]) {
+#pragma unroll
+          for (int k = 0; k < KS; ++k) {
+            const int st = lane * KS + k;
+            if (st < S) {
+              const size_t i = (size_t)t * SP + st;
+              const float w = ptx::ex2(s_alpha[i] + s_beta[i] - s_e[i] - ll2);   // alpha*beta / y / p(l|x)
+              if (st & 1) atomicAdd(&acc[u * CTC_C + cls[k]], w);
+              else blank_sum[u] += w;
+            }
           }
         }
       }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
+      for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) blank_sum[u] += __shfl_xor_sync(0xffffffffu, blank_sum[u], o);
-    if (lane == 0) {
+        for (int u = 0; u < CTC_RG; ++u) blank_sum[u] += __shfl_xor_sync(0xffffffffu, blank_sum[u], o);
+      if (lane == 0) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) atomicAdd(&acc[u * CTC_C + blank], blank_sum[u]);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int t = t0 + 2 * u;
-      if (t >= T) continue;
-      float2* gp = reinterpret_cast<float2*>(grad + ((size_t)t * N + n) * CTC_C) + lane;
-      if (!live[u]) {
-        *gp = make_float2(0.f, 0.f);
-      } else {
-        const float lse = s_lse[t];
-        const float y0 = ptx::ex2(x[u].x * LOG2E - lse), y1 = ptx::ex2(x[u].y * LOG2E - lse);
-        *gp = make_float2(grad_scale * (y0 - acc[u * CTC_C + 2 * lane]), grad_scale * (y1 - acc[u * CTC_C + 2 * lane + 1]));
+        for (int u = 0; u < CTC_RG; ++u) atomicAdd(&acc[u * CTC_C + blank], blank_sum[u]);
       }
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < CTC_RG; ++u) {
+        const int t = t0 + CTC_WARPS * (g + u);
+        if (t >= T) continue;
+        float2* gp = reinterpret_cast<float2*>(grad + ((size_t)t * N + n) * CTC_C) + lane;
+        if (!live[u]) {
+          *gp = make_float2(0.f, 0.f);
+        } else {
+          const float lse = s_lse[t];
+          const float y0 = ptx::ex2(xr[g + u].x * LOG2E - lse), y1 = ptx::ex2(xr[g + u].y * LOG2E - lse);
+          *gp = make_float2(grad_scale * (y0 - acc[u * CTC_C + 2 * lane]), grad_scale * (y1 - acc[u * CTC_C + 2 * lane + 1]));
+        }
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
@@ -319,7 +341,7 @@ __global__ void __launch_bounds__(128) ctc_greedy_kernel(const float* __restrict
   if (lane == 0) out_len[n] = count;
 }
 
-size_t ctc_smem_bytes(int T, int KS) { return sizeof(float) * ((size_t)T + 3 * (size_t)T * 32 * KS + 8 * CTC_C); }
+size_t ctc_smem_bytes(int T, int KS) { return sizeof(float) * ((size_t)T + 3 * (size_t)T * 32 * KS + CTC_WARPS * 4 * CTC_C); }
 
 template <int KS>
 int launch_ctc(const float* logits, float* grad, const int* flat_labels, const int* label_len, const int* input_len,
@@ -327,7 +349,7 @@ int launch_ctc(const float* logits, float* grad, const int* flat_labels, const i
   size_t smem = ctc_smem_bytes(T, KS);
   if (smem > 200 * 1024) return CRNN_UNSUPPORTED;
   CUDA_TRY(cudaFuncSetAttribute(ctc_loss_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ctc_loss_kernel<KS><<<N, 64, smem, st>>>(logits, grad, flat_labels, label_len, input_len, T, N, blank, grad_scale,
+  ctc_loss_kernel<KS><<<N, CTC_THREADS, smem, st>>>(logits, grad, flat_labels, label_len, input_len, T, N, blank, grad_scale,
                                            costs);
   CUDA_TRY(cudaGetLastError());
   return CRNN_OK;

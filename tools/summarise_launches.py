@@ -8,7 +8,8 @@ import sys
 def short(n):
     m = re.search(r"gemm_kernel<(\d+), ?(\d+), ?(\d+), ?(\d+)>", n)
     if m:
-        epi = ["F32", "BIAS_BF16", "RELU", "RELU_POOL22", "RELU_POOL12", "STATS", "LSTM", "LOGITS"][int(m.group(3))]
+        names = ["F32", "BIAS_BF16", "RELU", "RELU_POOL22", "RELU_POOL12", "STATS", "LSTM", "LOGITS", "XPROJ", "GRADIN", "WGRAD"]
+        epi = names[int(m.group(3))] if int(m.group(3)) < len(names) else m.group(3)
         return f'gemm<{m.group(1)},{"CONV3" if m.group(2) == "1" else "PLAIN"},{epi}>'
     return re.sub(r"\(.*", "", n).replace("void ", "").replace("(anonymous namespace)::", "")[:60]
 
