@@ -40,13 +40,17 @@ enum Epi {
   EPI_STATS = 5,        // conv: + bias -> bf16 pre-BN, per-channel sum / sum^2 (f64 atomics) (conv4_x)
   EPI_LSTM = 6,         // recurrent step: gates = acc + xproj; LSTM cell; writes h, c, output
   EPI_LOGITS = 7,       // + bias -> f32 time-major [T, N, 64]
-  EPI_XPROJ = 8         // + bias -> bf16 [N*H, 2048]; columns >= 1024 (backward direction) stored reversed-by-length
+  EPI_XPROJ = 8,        // + bias -> bf16 [N*H, 2048]; columns >= 1024 (backward direction) stored reversed-by-length
+  EPI_CONV_STORE = 9,   // conv: plain bf16 NHWC store (data-gradient convolutions)
+  EPI_RELU_POOL22_T = 10,  // training variants of the pooled epilogues: also emit the arg-max window index (uint8)
+  EPI_RELU_POOL12_T = 11
 };
 
 struct Params {
   int num_m_tiles, num_n_tiles, num_k_blocks;
   int kb_per_shift;      // A_PLAIN: K-block kb reads A columns (kb % kb_per_shift)*64 of row (m + kb / kb_per_shift);
                          // == num_k_blocks for an ordinary GEMM; conv5 (2x2 VALID) uses 16 -> rows t and t+1
+  int row_shift_mul;     // +1 (conv5 forward: rows m, m+1) or -1 (conv5 data gradient: rows m, m-1)
   int M;                 // valid rows (plain modes)
   int Nc;                // total output columns
   // conv geometry (A_CONV3 and conv epilogues)
@@ -58,6 +62,7 @@ struct Params {
   void* out;             // primary output
   int ldo;               // row stride of `out` in elements (plain modes)
   double* stats;         // [2][Nc] (EPI_STATS)
+  uint8_t* argmax;       // pooled-epilogue training variants: window index of the max, same shape as `out`
   // EPI_LSTM
   const __nv_bfloat16* xproj;   // [Nimg*H, 2048] gate pre-activations (x part + bias), permuted columns
   float* c_state;               // [2][Npad][256]
@@ -165,7 +170,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint8_t* a_dst = smem_a + stage * A_STAGE_BYTES;
           if (AMODE == A_PLAIN) {
             const int rs = kb / p.kb_per_shift, kc = kb - rs * p.kb_per_shift;
-            ptx::tma_load_2d(&tmA, &full_bar[stage], a_dst, kc * BLOCK_K, m_blk * BLOCK_M + rs);
+            ptx::tma_load_2d(&tmA, &full_bar[stage], a_dst, kc * BLOCK_K, m_blk * BLOCK_M + rs * p.row_shift_mul);
           } else {
             const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
             const int r = tap / 3, s = tap - 3 * r;
@@ -229,7 +234,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // ---- conv row geometry (one sub-box of 32 positions per warp)
       int n_img = 0, h = 0, w = 0;
       bool valid = true;
-      if (EPI == EPI_RELU || EPI == EPI_RELU_POOL22 || EPI == EPI_RELU_POOL12 || EPI == EPI_STATS) {
+      if (EPI == EPI_RELU || EPI == EPI_RELU_POOL22 || EPI == EPI_RELU_POOL12 || EPI == EPI_STATS || EPI == EPI_CONV_STORE ||
+          EPI == EPI_RELU_POOL22_T || EPI == EPI_RELU_POOL12_T) {
         const int g = m_blk * 4 + q;
         n_img = g / p.sb_per_img;
         const int hb = g - n_img * p.sb_per_img;
@@ -271,7 +277,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c0 + i));
+            const float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
             pk[i / 2] = ptx::pack_bf16x2(__uint_as_float(v[i]) + b.x, __uint_as_float(v[i + 1]) + b.y);
             pk[i / 2 + 1] = ptx::pack_bf16x2(__uint_as_float(v[i + 2]) + b.z, __uint_as_float(v[i + 3]) + b.w);
           }
@@ -351,6 +357,84 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (valid) {
               *reinterpret_cast<uint4*>(out + c0 + 16 * sub) = o0;
               *reinterpret_cast<uint4*>(out + c0 + 16 * sub + 8) = o1;
+            }
+          }
+        }
+      } else if (EPI == EPI_CONV_STORE) {
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (((size_t)n_img * p.H + h) * p.Wd + w) * p.Nc + col0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(tbase + c0, v);
+          ptx::tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8)
+              *reinterpret_cast<uint4*>(out + c0 + i) =
+                  make_uint4(ptx::pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
+                             ptx::pack_bf16x2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])),
+                             ptx::pack_bf16x2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])),
+                             ptx::pack_bf16x2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
+          }
+        }
+      } else if (EPI == EPI_RELU_POOL22_T || EPI == EPI_RELU_POOL12_T) {
+        // Training variants: max over the pooling window carried as an integer key
+        //   key = (bf16 bits of relu(x) << 2) | (3 - window_index)
+        // post-ReLU bf16 bit patterns are monotone as unsigned integers, so max(key) picks the largest value and, among
+        // equal values, the FIRST window position (row-major (dy,dx), the tie-break of TF/torch max-pool gradients).
+        constexpr bool P22 = (EPI == EPI_RELU_POOL22_T);
+        size_t off;
+        if (P22) off = (((size_t)n_img * (p.H >> 1) + (h >> 1)) * (p.Wd >> 1) + (w >> 1)) * p.Nc;
+        else off = (((size_t)n_img * p.H + h) * (p.Wd >> 1) + (w >> 1)) * p.Nc;
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + off + col0;
+        uint8_t* amx = p.argmax + off + col0;
+        const uint32_t kidx = P22 ? (uint32_t)((((lane >> 4) & 1) << 1) | (lane & 1)) : (uint32_t)(lane & 1);
+        const uint32_t kinv = (P22 ? 3u : 1u) - kidx;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(tbase + c0, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c0 + i));
+            const uint32_t p0 = ptx::pack_bf16x2(fmaxf(__uint_as_float(v[i]) + b.x, 0.f), fmaxf(__uint_as_float(v[i + 1]) + b.y, 0.f));
+            const uint32_t p1 = ptx::pack_bf16x2(fmaxf(__uint_as_float(v[i + 2]) + b.z, 0.f), fmaxf(__uint_as_float(v[i + 3]) + b.w, 0.f));
+            v[i] = ((p0 & 0xFFFFu) << 2) | kinv;
+            v[i + 1] = ((p0 >> 16) << 2) | kinv;
+            v[i + 2] = ((p1 & 0xFFFFu) << 2) | kinv;
+            v[i + 3] = ((p1 >> 16) << 2) | kinv;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v[i] = max(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
+            if (P22) v[i] = max(v[i], __shfl_xor_sync(0xffffffffu, v[i], 16));
+          }
+          // each lane of the window stores its share of the 32 columns: 8 (2x2 window) or 16 (1x2 window)
+          constexpr int NS = P22 ? 4 : 2, PER = 32 / NS;
+          const int sub = P22 ? ((lane & 1) | ((lane >> 3) & 2)) : (lane & 1);
+          uint32_t sel[PER];
+#pragma unroll
+          for (int i = 0; i < PER; ++i) {
+            uint32_t x = v[i];
+#pragma unroll
+            for (int j = 1; j < NS; ++j) x = (sub == j) ? v[j * PER + i] : x;
+            sel[i] = x;
+          }
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < PER; i += 8) {
+              uint4 o;
+              o.x = ((sel[i] >> 2) & 0xFFFFu) | ((sel[i + 1] >> 2) << 16);
+              o.y = ((sel[i + 2] >> 2) & 0xFFFFu) | ((sel[i + 3] >> 2) << 16);
+              o.z = ((sel[i + 4] >> 2) & 0xFFFFu) | ((sel[i + 5] >> 2) << 16);
+              o.w = ((sel[i + 6] >> 2) & 0xFFFFu) | ((sel[i + 7] >> 2) << 16);
+              *reinterpret_cast<uint4*>(out + c0 + sub * PER + i) = o;
+              const uint32_t km = P22 ? 3u : 1u;
+              uint2 a;
+              a.x = (km - (sel[i] & km)) | ((km - (sel[i + 1] & km)) << 8) | ((km - (sel[i + 2] & km)) << 16) | ((km - (sel[i + 3] & km)) << 24);
+              a.y = (km - (sel[i + 4] & km)) | ((km - (sel[i + 5] & km)) << 8) | ((km - (sel[i + 6] & km)) << 16) | ((km - (sel[i + 7] & km)) << 24);
+              *reinterpret_cast<uint2*>(amx + c0 + sub * PER + i) = a;
             }
           }
         }

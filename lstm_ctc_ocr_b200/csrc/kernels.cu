@@ -14,7 +14,7 @@ constexpr int C1_ROWS = 8;                         // pooled rows per tile
 __global__ void __launch_bounds__(256) conv1_pool_kernel(const float* __restrict__ data,
                                                          const float* __restrict__ wgt,   // HWIO [3,3,1,64]
                                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
-                                                         int N, int W) {
+                                                         uint8_t* __restrict__ argmax, int N, int W) {
   __shared__ float s_in[2 * C1_ROWS + 2][36];
   const int H1 = W >> 1;
   const int tiles_per_img = (H1 + C1_ROWS - 1) / C1_ROWS;
@@ -55,8 +55,9 @@ __global__ void __launch_bounds__(256) conv1_pool_kernel(const float* __restrict
 #pragma unroll
         for (int j = 0; j < 4; ++j) patch[i][j] = s_in[2 * hol + i][2 * wo + j];
       float best[8];
+      uint32_t bidx[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
+      for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bidx[j] = 0; }
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
@@ -73,7 +74,9 @@ __global__ void __launch_bounds__(256) conv1_pool_kernel(const float* __restrict
               for (int j = 0; j < 8; ++j) acc[j] = fmaf(x, wr[r * 3 + s][j], acc[j]);
             }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], acc[j]);
+          for (int j = 0; j < 8; ++j) {
+            if (acc[j] > best[j]) { best[j] = acc[j]; bidx[j] = dy * 2 + dx; }     // strict '>' keeps the first max
+          }
         }
       if (ho < H1) {
         uint4 o;
@@ -81,7 +84,14 @@ __global__ void __launch_bounds__(256) conv1_pool_kernel(const float* __restrict
         o.y = ptx::pack_bf16x2(fmaxf(best[2] + br[2], 0.f), fmaxf(best[3] + br[3], 0.f));
         o.z = ptx::pack_bf16x2(fmaxf(best[4] + br[4], 0.f), fmaxf(best[5] + br[5], 0.f));
         o.w = ptx::pack_bf16x2(fmaxf(best[6] + br[6], 0.f), fmaxf(best[7] + br[7], 0.f));
-        *reinterpret_cast<uint4*>(out + (((size_t)n * H1 + ho) * 16 + wo) * 64 + cg * 8) = o;
+        const size_t oo = (((size_t)n * H1 + ho) * 16 + wo) * 64 + cg * 8;
+        *reinterpret_cast<uint4*>(out + oo) = o;
+        if (argmax != nullptr) {
+          uint2 a;
+          a.x = bidx[0] | (bidx[1] << 8) | (bidx[2] << 16) | (bidx[3] << 24);
+          a.y = bidx[4] | (bidx[5] << 8) | (bidx[6] << 16) | (bidx[7] << 24);
+          *reinterpret_cast<uint2*>(argmax + oo) = a;
+        }
       }
     }
   }
@@ -240,11 +250,11 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* 
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ launchers
-int launch_conv1_pool(const float* data, const float* w, const float* b, __nv_bfloat16* out, int N, int W, int num_sms,
-                      cudaStream_t st) {
+int launch_conv1_pool(const float* data, const float* w, const float* b, __nv_bfloat16* out, uint8_t* argmax, int N, int W,
+                      int num_sms, cudaStream_t st) {
   const int tiles = N * (((W >> 1) + C1_ROWS - 1) / C1_ROWS);
   const int grid = tiles < num_sms * 2 ? tiles : num_sms * 2;
-  conv1_pool_kernel<<<grid, 256, 0, st>>>(data, w, b, out, N, W);
+  conv1_pool_kernel<<<grid, 256, 0, st>>>(data, w, b, out, argmax, N, W);
   CUDA_TRY(cudaGetLastError());
   return CRNN_OK;
 }

@@ -8,8 +8,8 @@ struct SumsqSegs {
   long long cnt[8];
 };
 
-int launch_conv1_pool(const float* data, const float* w, const float* b, __nv_bfloat16* out, int N, int W, int num_sms,
-                      cudaStream_t st);
+int launch_conv1_pool(const float* data, const float* w, const float* b, __nv_bfloat16* out, uint8_t* argmax, int N, int W,
+                      int num_sms, cudaStream_t st);
 int launch_bn_finalize(const double* stats, double count, const float* gamma, const float* beta, float eps, float* scale,
                        float* shift, float* save_mean, float* save_invstd, int C, cudaStream_t st);
 int launch_bn_apply_relu(const __nv_bfloat16* in, __nv_bfloat16* out, const float* scale, const float* shift, size_t rows,

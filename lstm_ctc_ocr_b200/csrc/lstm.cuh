@@ -31,6 +31,9 @@ struct Params {
   __nv_bfloat16* lstm_out;      // [Nimg*H, 512]
   const int* seq_len;           // [Nimg]
   int Nimg, Npad, H, T, tiles_per_dir;
+  // training only (nullptr for inference): activations the backward recurrence needs
+  __nv_bfloat16* gates;         // [2 dirs][Nimg][T steps][4 gates i,j,f,o][256] post-activation
+  float* csave;                 // [2 dirs][Nimg][T steps][256] cell state after the step
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -181,9 +184,28 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_con
             const float zj = __uint_as_float(gj[i]) + ((u & 1) ? ptx::bf16_hi(wj) : ptx::bf16_lo(wj));
             const float zf = __uint_as_float(gf[i]) + ((u & 1) ? ptx::bf16_hi(wf) : ptx::bf16_lo(wf));
             const float zo = __uint_as_float(go[i]) + ((u & 1) ? ptx::bf16_hi(wo) : ptx::bf16_lo(wo));
-            const float c = ptx::fast_sigmoid(zf) * cst[u] + ptx::fast_sigmoid(zi) * ptx::fast_tanh(zj);   // +1.0 folded into bias
+            const float ai = ptx::fast_sigmoid(zi), aj = ptx::fast_tanh(zj), af = ptx::fast_sigmoid(zf), ao = ptx::fast_sigmoid(zo);
+            const float c = af * cst[u] + ai * aj;                 // forget_bias (+1.0) is folded into the projected bias
             cst[u] = c;
-            hv[i] = ptx::fast_sigmoid(zo) * ptx::fast_tanh(c);
+            hv[i] = ao * ptx::fast_tanh(c);
+            if (p.gates != nullptr) {                              // reuse the (now dead) accumulator registers as staging
+              gi[i] = __float_as_uint(ai); gj[i] = __float_as_uint(aj); gf[i] = __float_as_uint(af); go[i] = __float_as_uint(ao);
+            }
+          }
+          if (p.gates != nullptr) {
+            const size_t srow = ((size_t)dir * p.Nimg + n) * p.T + s;
+            __nv_bfloat16* gs = p.gates + srow * 1024 + rank * UPC + u0;
+            float* cs = p.csave + srow * 256 + rank * UPC + u0;
+#pragma unroll
+            for (int i = 0; i < HALF; i += 8) {
+              *reinterpret_cast<uint4*>(gs + 0 * 256 + i) = make_uint4(ptx::pack_bf16x2(__uint_as_float(gi[i]), __uint_as_float(gi[i + 1])), ptx::pack_bf16x2(__uint_as_float(gi[i + 2]), __uint_as_float(gi[i + 3])), ptx::pack_bf16x2(__uint_as_float(gi[i + 4]), __uint_as_float(gi[i + 5])), ptx::pack_bf16x2(__uint_as_float(gi[i + 6]), __uint_as_float(gi[i + 7])));
+              *reinterpret_cast<uint4*>(gs + 1 * 256 + i) = make_uint4(ptx::pack_bf16x2(__uint_as_float(gj[i]), __uint_as_float(gj[i + 1])), ptx::pack_bf16x2(__uint_as_float(gj[i + 2]), __uint_as_float(gj[i + 3])), ptx::pack_bf16x2(__uint_as_float(gj[i + 4]), __uint_as_float(gj[i + 5])), ptx::pack_bf16x2(__uint_as_float(gj[i + 6]), __uint_as_float(gj[i + 7])));
+              *reinterpret_cast<uint4*>(gs + 2 * 256 + i) = make_uint4(ptx::pack_bf16x2(__uint_as_float(gf[i]), __uint_as_float(gf[i + 1])), ptx::pack_bf16x2(__uint_as_float(gf[i + 2]), __uint_as_float(gf[i + 3])), ptx::pack_bf16x2(__uint_as_float(gf[i + 4]), __uint_as_float(gf[i + 5])), ptx::pack_bf16x2(__uint_as_float(gf[i + 6]), __uint_as_float(gf[i + 7])));
+              *reinterpret_cast<uint4*>(gs + 3 * 256 + i) = make_uint4(ptx::pack_bf16x2(__uint_as_float(go[i]), __uint_as_float(go[i + 1])), ptx::pack_bf16x2(__uint_as_float(go[i + 2]), __uint_as_float(go[i + 3])), ptx::pack_bf16x2(__uint_as_float(go[i + 4]), __uint_as_float(go[i + 5])), ptx::pack_bf16x2(__uint_as_float(go[i + 6]), __uint_as_float(go[i + 7])));
+            }
+#pragma unroll
+            for (int i = 0; i < HALF; i += 4)
+              *reinterpret_cast<float4*>(cs + i) = make_float4(cst[u0 + i], cst[u0 + i + 1], cst[u0 + i + 2], cst[u0 + i + 3]);
           }
 #pragma unroll
           for (int i = 0; i < HALF / 2; ++i) hp[i] = ptx::pack_bf16x2(hv[2 * i], hv[2 * i + 1]);

@@ -7,9 +7,10 @@
 
 #include <cstdlib>
 
-#include "gemm.cuh"
+#include "gemm_launch.h"
 #include "lstm.cuh"
 #include "kernels.cuh"
+#include "model_internal.h"
 
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local char g_err[1024] = "";
@@ -51,7 +52,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 // 2-D bf16 map over [rows, cols] with arbitrary row stride (elements); box = [64 cols, box_rows], 128B swizzle.
-static int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride,
+int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride,
                         uint32_t box_rows) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return crnn_fail(CRNN_CUDA_ERROR, "cuTensorMapEncodeTiled unavailable");
@@ -65,8 +66,22 @@ static int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_
   if (r != CUDA_SUCCESS) return crnn_fail(CRNN_CUDA_ERROR, "cuTensorMapEncodeTiled(2d) failed: %d", (int)r);
   return CRNN_OK;
 }
+int make_tmap_2d_box(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride, uint32_t box_cols,
+                     uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return crnn_fail(CRNN_CUDA_ERROR, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return crnn_fail(CRNN_CUDA_ERROR, "cuTensorMapEncodeTiled(2d box) failed: %d", (int)r);
+  return CRNN_OK;
+}
 // 4-D bf16 map over NHWC [N, H, Wd, C]; box = [64 ch, Wd, bh, 1]; OOB (halo) elements read as zero.
-static int make_tmap_nhwc(CUtensorMap* m, const void* base, int N, int H, int Wd, int C, int bh) {
+int make_tmap_nhwc(CUtensorMap* m, const void* base, int N, int H, int Wd, int C, int bh) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return crnn_fail(CRNN_CUDA_ERROR, "cuTensorMapEncodeTiled unavailable");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wd, (cuuint64_t)H, (cuuint64_t)N};
@@ -79,62 +94,6 @@ static int make_tmap_nhwc(CUtensorMap* m, const void* base, int N, int H, int Wd
   if (r != CUDA_SUCCESS) return crnn_fail(CRNN_CUDA_ERROR, "cuTensorMapEncodeTiled(4d) failed: %d", (int)r);
   return CRNN_OK;
 }
-
-// ------------------------------------------------------------------------------------------------ model
-struct TensorInfo {
-  std::string name;
-  int ndim;
-  int64_t shape[4];
-  int64_t offset;
-  int64_t count;
-};
-
-struct ConvSpec { const char* name; int kh, kw, ci, co; bool bn; };
-static const ConvSpec kConvs[7] = {   // lib/networks/LSTM_train.py:24-34
-    {"conv1", 3, 3, 1, 64, false},    {"conv2", 3, 3, 64, 128, false},  {"conv3_1", 3, 3, 128, 256, false},
-    {"conv3_2", 3, 3, 256, 256, false}, {"conv4_1", 3, 3, 256, 512, true}, {"conv4_2", 3, 3, 512, 512, true},
-    {"conv5", 2, 2, 512, 512, false}};
-
-static const char* kStageNames[] = {"conv1_pool1", "conv2_pool2", "conv3_1", "conv3_2_pool", "conv4_1_gemm", "bn4_1_apply",
-                                    "conv4_2_gemm", "bn4_2_apply_pool3", "conv5", "lstm_xproj", "lstm_recurrence", "logits"};
-static const int kNumStages = 12;
-
-struct Plan {
-  int N = 0, W = 0, H1 = 0, H2 = 0, T = 0, Npad = 0;
-  void* ws = nullptr;
-  __nv_bfloat16 *a1, *a2, *a3, *a3p, *a4a_pre, *a4a, *a4b_pre, *a4b, *a5, *xproj, *lstm_out, *h_state;
-  float* c_state;
-  double* stats;        // [2 layers][2][512]
-  float* bn;            // [2 layers][4][512]: scale, shift, mean, invstd
-  CUtensorMap tA_c2, tA_c31, tA_c32, tA_c41, tA_c42, tA_c5, tA_x, tA_h[2], tA_l, tA_hall;
-};
-
-struct crnn_model {
-  crnn_config cfg;
-  int num_sms = 148;
-  std::vector<TensorInfo> tensors;
-  int64_t total = 0;
-  float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
-  bool dirty = true;
-  // bf16 K-major operand copies of the weights (B matrices [Cout][K])
-  __nv_bfloat16 *Bc2 = nullptr, *Bc31, *Bc32, *Bc41, *Bc42, *Bc5, *Bx, *Bh, *Bl;
-  float* xbias = nullptr;    // [2048] permuted LSTM bias with forget_bias folded in
-  double* sumsq = nullptr;
-  void* wblock = nullptr;
-  CUtensorMap tB_c2, tB_c31, tB_c32, tB_c41, tB_c42, tB_c5, tB_x, tB_h, tB_l, tB_h128;
-  int lstm_upc = 32;         // hidden units per gate tile: 32 = persistent cluster kernel (default), 64 = per-step launches
-  Plan plan;
-  // per-stage CUDA-event profiling (crnn_profile_*): events are recorded on the caller's stream between stages
-  std::vector<cudaEvent_t> prof_events;   // [slots][kNumStages + 1]
-  int prof_slots = 0, prof_used = 0;
-  bool prof_on = false;
-
-  const TensorInfo* find(const std::string& n) const {
-    for (auto& t : tensors) if (t.name == n) return &t;
-    return nullptr;
-  }
-  float* P(const std::string& n) const { return params + find(n)->offset; }
-};
 
 static void add_tensor(crnn_model* m, const std::string& name, std::initializer_list<int64_t> shp) {
   TensorInfo t;
@@ -244,7 +203,7 @@ extern "C" int crnn_model_params_changed(crnn_model* m) {
 }
 
 // f32 TF-layout parameters -> bf16 K-major GEMM operands (B[co][(kh,kw,ci)] == transpose of HWIO flattened)
-static int prepare_weights(crnn_model* m, cudaStream_t st) {
+int prepare_weights(crnn_model* m, cudaStream_t st) {
   struct { const char* n; __nv_bfloat16* d; int R, C; } cv[6] = {
       {"conv2/weights", m->Bc2, 576, 128},    {"conv3_1/weights", m->Bc31, 1152, 256}, {"conv3_2/weights", m->Bc32, 2304, 256},
       {"conv4_1/weights", m->Bc41, 2304, 512}, {"conv4_2/weights", m->Bc42, 4608, 512}, {"conv5/weights", m->Bc5, 2048, 512}};
@@ -272,9 +231,9 @@ static int prepare_weights(crnn_model* m, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------ workspace
-static size_t align_up(size_t v, size_t a = 1024) { return (v + a - 1) / a * a; }
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static size_t layout_plan(Plan& pl, int N, int W, uint8_t* base) {
+size_t layout_plan(Plan& pl, int N, int W, uint8_t* base, bool train) {
   pl.N = N; pl.W = W; pl.H1 = W / 2; pl.H2 = W / 4; pl.T = W / 4 - 1;
   pl.Npad = (N + 127) / 128 * 128;
   size_t off = 0;
@@ -295,21 +254,44 @@ static size_t layout_plan(Plan& pl, int N, int W, uint8_t* base) {
   pl.c_state = (float*)take((size_t)2 * pl.Npad * 256 * 4);
   pl.stats = (double*)take(2 * 2 * 512 * 8);
   pl.bn = (float*)take(2 * 4 * 512 * 4);
+  pl.train = train;
+  if (train) {
+    const size_t T = pl.T;
+    pl.am1 = (uint8_t*)take(n * h1 * 16 * 64);
+    pl.am2 = (uint8_t*)take(n * h2 * 8 * 128);
+    pl.am3 = (uint8_t*)take(n * h2 * 4 * 256);
+    pl.gates = (__nv_bfloat16*)take((size_t)2 * n * T * 1024 * 2);
+    pl.csave = (float*)take((size_t)2 * n * T * 256 * 4);
+    pl.dl_rows = (__nv_bfloat16*)take(n * h2 * 64 * 2);
+    pl.d_lstm_out = (__nv_bfloat16*)take(n * h2 * 512 * 2);
+    pl.dz_all = (__nv_bfloat16*)take(n * h2 * 2048 * 2);
+    pl.dz_state = (__nv_bfloat16*)take((size_t)2 * 2 * pl.Npad * 1024 * 2);
+    pl.d_a5 = (__nv_bfloat16*)take(n * h2 * 512 * 2);
+    pl.d_a4b = (__nv_bfloat16*)take(n * h2 * 2 * 512 * 2);
+    pl.d_pre4b = (__nv_bfloat16*)take(n * h2 * 4 * 512 * 2);
+    pl.d_pre4a = (__nv_bfloat16*)take(n * h2 * 4 * 512 * 2);
+    pl.d_a3p = (__nv_bfloat16*)take(n * h2 * 4 * 256 * 2);
+    pl.d_pre32 = (__nv_bfloat16*)take(n * h2 * 8 * 256 * 2);
+    pl.d_pre31 = (__nv_bfloat16*)take(n * h2 * 8 * 256 * 2);
+    pl.d_a2 = (__nv_bfloat16*)take(n * h2 * 8 * 128 * 2);
+    pl.d_pre2 = (__nv_bfloat16*)take(n * h1 * 16 * 128 * 2);
+    pl.d_a1 = (__nv_bfloat16*)take(n * h1 * 16 * 64 * 2);
+    pl.bn_bwd_sums = (double*)take(2 * 2 * 512 * 8);
+  }
   return off;
 }
 
 extern "C" int crnn_model_workspace_size(const crnn_model* m, int N, int W, int train, size_t* bytes) {
-  (void)train;
   if (!m || !bytes) return crnn_fail(CRNN_INVALID_VALUE, "workspace_size: null");
   if (N <= 0 || W < 8 || (W % 4) != 0) return crnn_fail(CRNN_INVALID_VALUE, "workspace_size: need N>0, W>=8, W%%4==0 (gen.py:58)");
   Plan pl;
-  *bytes = layout_plan(pl, N, W, nullptr);
+  *bytes = layout_plan(pl, N, W, nullptr, train != 0);
   return CRNN_OK;
 }
 
 static int build_plan(crnn_model* m, int N, int W, void* ws, cudaStream_t st) {
   Plan& pl = m->plan;
-  layout_plan(pl, N, W, reinterpret_cast<uint8_t*>(ws));
+  layout_plan(pl, N, W, reinterpret_cast<uint8_t*>(ws), m->training);
   pl.ws = ws;
   CRNN_TRY(make_tmap_nhwc(&pl.tA_c2, pl.a1, N, pl.H1, 16, 64, 2));
   CRNN_TRY(make_tmap_nhwc(&pl.tA_c31, pl.a2, N, pl.H2, 8, 128, 4));
@@ -325,23 +307,38 @@ static int build_plan(crnn_model* m, int N, int W, void* ws, cudaStream_t st) {
   CRNN_TRY(make_tmap_2d(&pl.tA_l, pl.lstm_out, (uint64_t)N * pl.H2, 512, 512, 128));
   // rows t = T (= H2-1) of lstm_out are never produced by a time step: keep them defined (zero)
   CUDA_TRY(cudaMemsetAsync(pl.lstm_out, 0, (size_t)N * pl.H2 * 512 * 2, st));
+  if (pl.train) {
+    const uint64_t R = (uint64_t)N * pl.H2;
+    // K-major A operands (box = [64 K-elements, 128 rows])
+    CRNN_TRY(make_tmap_2d(&pl.tG_dl, pl.dl_rows, R, 64, 64, 128));
+    CRNN_TRY(make_tmap_2d(&pl.tG_dz, pl.dz_all, R, 2048, 2048, 128));
+    CRNN_TRY(make_tmap_2d(&pl.tG_da5, pl.d_a5, R, 512, 512, 128));
+    CRNN_TRY(make_tmap_2d(&pl.tG_dzstate, pl.dz_state, (uint64_t)4 * pl.Npad, 1024, 1024, 128));
+    CRNN_TRY(make_tmap_nhwc(&pl.tG_p4b, pl.d_pre4b, N, pl.H2, 4, 512, 8));
+    CRNN_TRY(make_tmap_nhwc(&pl.tG_p4a, pl.d_pre4a, N, pl.H2, 4, 512, 8));
+    CRNN_TRY(make_tmap_nhwc(&pl.tG_p32, pl.d_pre32, N, pl.H2, 8, 256, 4));
+    CRNN_TRY(make_tmap_nhwc(&pl.tG_p31, pl.d_pre31, N, pl.H2, 8, 256, 4));
+    CRNN_TRY(make_tmap_nhwc(&pl.tG_p2, pl.d_pre2, N, pl.H1, 16, 128, 2));
+    // MN-major (TN) operands: box = [64 channels, 64 rows]
+    CRNN_TRY(make_tmap_2d_box(&pl.tT_lstm_all, pl.lstm_out, R, 512, 512, 64, 64));
+    CRNN_TRY(make_tmap_2d_box(&pl.tT_lstm_fw, pl.lstm_out, R, 256, 512, 64, 64));
+    CRNN_TRY(make_tmap_2d_box(&pl.tT_lstm_bw, pl.lstm_out + 256, R, 256, 512, 64, 64));
+    CRNN_TRY(make_tmap_2d_box(&pl.tT_dl, pl.dl_rows, R, 64, 64, 64, 64));
+    CRNN_TRY(make_tmap_2d_box(&pl.tT_a5, pl.a5, R, 512, 512, 64, 64));
+    CRNN_TRY(make_tmap_2d_box(&pl.tT_dz, pl.dz_all, R, 2048, 2048, 64, 64));
+    CRNN_TRY(make_tmap_2d_box(&pl.tT_dz_fw, pl.dz_all, R, 1024, 2048, 64, 64));
+    CRNN_TRY(make_tmap_2d_box(&pl.tT_dz_bw, pl.dz_all + 1024, R, 1024, 2048, 64, 64));
+    CRNN_TRY(make_tmap_2d_box(&pl.tT_a4b, pl.a4b, R, 1024, 1024, 64, 64));
+    CRNN_TRY(make_tmap_2d_box(&pl.tT_da5, pl.d_a5, R, 512, 512, 64, 64));
+    // dz rows of padding frames (t = T) are never written by the backward recurrence: keep them zero
+    CUDA_TRY(cudaMemsetAsync(pl.dz_all, 0, (size_t)R * 2048 * 2, st));
+  }
   return CRNN_OK;
 }
 
-// ------------------------------------------------------------------------------------------------ GEMM launch
-template <int BN, int AM, int EPI, int ST>
-static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const gemm::Params& p, int num_sms, cudaStream_t st) {
-  auto kern = gemm::gemm_kernel<BN, AM, EPI, ST>;
-  constexpr int smem = gemm::Smem<BN, ST>::BYTES;
-  static bool attr = false;
-  if (!attr) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, gemm::NUM_THREADS, smem, st>>>(a, b, p);
-  CUDA_TRY(cudaGetLastError());
+int ensure_plan(crnn_model* m, int N, int W, void* ws, cudaStream_t st) {
+  Plan& pl = m->plan;
+  if (pl.N != N || pl.W != W || pl.ws != ws || pl.train != m->training) return build_plan(m, N, W, ws, st);
   return CRNN_OK;
 }
 
@@ -367,13 +364,13 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
   if (!m->params) return crnn_fail(CRNN_NOT_BOUND, "forward: call crnn_model_bind first");
   if (N <= 0 || W < 8 || (W % 4) != 0) return crnn_fail(CRNN_INVALID_VALUE, "forward: need N>0, W>=8, W%%4==0");
   size_t need = 0;
-  CRNN_TRY(crnn_model_workspace_size(m, N, W, 0, &need));
+  CRNN_TRY(crnn_model_workspace_size(m, N, W, m->training ? 1 : 0, &need));
   if (workspace_bytes < need) return crnn_fail(CRNN_WORKSPACE_TOO_SMALL, "forward: workspace %zu < %zu", workspace_bytes, need);
   if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return crnn_fail(CRNN_INVALID_VALUE, "forward: workspace must be 1024-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (m->dirty) CRNN_TRY(prepare_weights(m, st));
   Plan& pl = m->plan;
-  if (pl.N != N || pl.W != W || pl.ws != workspace) CRNN_TRY(build_plan(m, N, W, workspace, st));
+  CRNN_TRY(ensure_plan(m, N, W, workspace, st));
   const int H1 = pl.H1, H2 = pl.H2, T = pl.T, sms = m->num_sms;
   cudaEvent_t* ev = nullptr;
   if (m->prof_on && m->prof_used < m->prof_slots) ev = &m->prof_events[(size_t)(m->prof_used++) * (kNumStages + 1)];
@@ -382,12 +379,17 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
   STAGE_MARK();
 
   // conv1 + pool1 (SIMT, HBM/FMA-bound: K = 9)
-  CRNN_TRY(launch_conv1_pool(data, m->P("conv1/weights"), m->P("conv1/biases"), pl.a1, N, W, sms, st));
+  CRNN_TRY(launch_conv1_pool(data, m->P("conv1/weights"), m->P("conv1/biases"), pl.a1, pl.train ? pl.am1 : nullptr, N, W, sms, st));
   STAGE_MARK();
   // conv2 + ReLU + pool2
   {
     gemm::Params p = conv_params(N, H1, 16, 64, 128, 128, m->P("conv2/biases"), pl.a2);
-    CRNN_TRY((launch_gemm<128, gemm::A_CONV3, gemm::EPI_RELU_POOL22, 6>(pl.tA_c2, m->tB_c2, p, sms, st)));
+    if (pl.train) {
+      p.argmax = pl.am2;
+      CRNN_TRY((launch_gemm<128, gemm::A_CONV3, gemm::EPI_RELU_POOL22_T, 6>(pl.tA_c2, m->tB_c2, p, sms, st)));
+    } else {
+      CRNN_TRY((launch_gemm<128, gemm::A_CONV3, gemm::EPI_RELU_POOL22, 6>(pl.tA_c2, m->tB_c2, p, sms, st)));
+    }
   }
   STAGE_MARK();
   // conv3_1 + ReLU
@@ -399,7 +401,12 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
   // conv3_2 + ReLU + height pool
   {
     gemm::Params p = conv_params(N, H2, 8, 256, 256, 256, m->P("conv3_2/biases"), pl.a3p);
-    CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_RELU_POOL12, 4>(pl.tA_c32, m->tB_c32, p, sms, st)));
+    if (pl.train) {
+      p.argmax = pl.am3;
+      CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_RELU_POOL12_T, 4>(pl.tA_c32, m->tB_c32, p, sms, st)));
+    } else {
+      CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_RELU_POOL12, 4>(pl.tA_c32, m->tB_c32, p, sms, st)));
+    }
   }
   STAGE_MARK();
   CUDA_TRY(cudaMemsetAsync(pl.stats, 0, 2 * 2 * 512 * sizeof(double), st));
@@ -433,7 +440,7 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
     gemm::Params p;
     memset(&p, 0, sizeof(p));
     p.M = N * H2;
-    p.num_m_tiles = (p.M + 127) / 128; p.num_n_tiles = 2; p.num_k_blocks = 32; p.kb_per_shift = 16;
+    p.num_m_tiles = (p.M + 127) / 128; p.num_n_tiles = 2; p.num_k_blocks = 32; p.kb_per_shift = 16; p.row_shift_mul = 1;
     p.Nc = 512; p.bias = m->P("conv5/biases"); p.out = pl.a5; p.ldo = 512;
     CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 4>(pl.tA_c5, m->tB_c5, p, sms, st)));
   }
@@ -456,6 +463,7 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
     lstm::Params lp;
     lp.xproj = pl.xproj; lp.h_state = pl.h_state; lp.lstm_out = pl.lstm_out; lp.seq_len = time_step_len;
     lp.Nimg = N; lp.Npad = pl.Npad; lp.H = H2; lp.T = T; lp.tiles_per_dir = pl.Npad / 128;
+    lp.gates = pl.train ? pl.gates : nullptr; lp.csave = pl.train ? pl.csave : nullptr;
     auto kern = lstm::lstm_persistent_kernel<CS>;
     static bool attr = false;
     if (!attr) {

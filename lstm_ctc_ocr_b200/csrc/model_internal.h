@@ -1,0 +1,92 @@
+// Internal declarations shared by model.cu (forward) and backward.cu (gradients / optimizer).
+#pragma once
+#include <string>
+#include <vector>
+
+#include <cuda.h>
+
+#include "common.cuh"
+
+int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride, uint32_t box_rows);
+int make_tmap_nhwc(CUtensorMap* m, const void* base, int N, int H, int Wd, int C, int bh);
+size_t align_up(size_t v, size_t a = 1024);
+int make_tmap_2d_box(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride, uint32_t box_cols,
+                     uint32_t box_rows);
+
+struct TensorInfo {
+  std::string name;
+  int ndim;
+  int64_t shape[4];
+  int64_t offset;
+  int64_t count;
+};
+
+struct ConvSpec { const char* name; int kh, kw, ci, co; bool bn; };
+static const ConvSpec kConvs[7] = {   // lib/networks/LSTM_train.py:24-34
+    {"conv1", 3, 3, 1, 64, false},    {"conv2", 3, 3, 64, 128, false},  {"conv3_1", 3, 3, 128, 256, false},
+    {"conv3_2", 3, 3, 256, 256, false}, {"conv4_1", 3, 3, 256, 512, true}, {"conv4_2", 3, 3, 512, 512, true},
+    {"conv5", 2, 2, 512, 512, false}};
+
+static const char* kStageNames[] = {"conv1_pool1", "conv2_pool2", "conv3_1", "conv3_2_pool", "conv4_1_gemm", "bn4_1_apply",
+                                    "conv4_2_gemm", "bn4_2_apply_pool3", "conv5", "lstm_xproj", "lstm_recurrence", "logits"};
+static const int kNumStages = 12;
+
+struct Plan {
+  int N = 0, W = 0, H1 = 0, H2 = 0, T = 0, Npad = 0;
+  void* ws = nullptr;
+  __nv_bfloat16 *a1, *a2, *a3, *a3p, *a4a_pre, *a4a, *a4b_pre, *a4b, *a5, *xproj, *lstm_out, *h_state;
+  float* c_state;
+  double* stats;        // [2 layers][2][512]
+  float* bn;            // [2 layers][4][512]: scale, shift, mean, invstd
+  CUtensorMap tA_c2, tA_c31, tA_c32, tA_c41, tA_c42, tA_c5, tA_x, tA_h[2], tA_l, tA_hall;
+  // ---- training only -------------------------------------------------------------------------------------------
+  bool train = false;
+  uint8_t *am1, *am2, *am3;                       // arg-max window indices of pool1 / pool2 / the 1x2 pool after conv3_2
+  __nv_bfloat16* gates;                           // [2][N][T][4][256] post-activation gates
+  float* csave;                                   // [2][N][T][256]
+  __nv_bfloat16 *dl_rows, *d_lstm_out, *dz_all, *dz_state, *d_a5, *d_a4b, *d_pre4b, *d_pre4a, *d_a3p, *d_pre32, *d_pre31, *d_a2,
+      *d_pre2, *d_a1;
+  double* bn_bwd_sums;                            // [2 layers][2][512]
+  // K-major A maps of gradient buffers (data-gradient GEMMs)
+  CUtensorMap tG_dl, tG_dz, tG_da5, tG_p4b, tG_p4a, tG_p32, tG_p31, tG_p2, tG_dzstate;
+  // MN-major (TN) maps: 2-D [rows, C] with 64x64 boxes, and the NHWC maps above reused for TN_CONV
+  CUtensorMap tT_lstm_fw, tT_lstm_bw, tT_lstm_all, tT_dl, tT_a5, tT_dz, tT_dz_fw, tT_dz_bw, tT_a4b, tT_da5;
+};
+
+struct crnn_model {
+  crnn_config cfg;
+  int num_sms = 148;
+  std::vector<TensorInfo> tensors;
+  int64_t total = 0;
+  float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+  bool dirty = true;
+  // bf16 K-major operand copies of the weights (B matrices [Cout][K])
+  __nv_bfloat16 *Bc2 = nullptr, *Bc31, *Bc32, *Bc41, *Bc42, *Bc5, *Bx, *Bh, *Bl;
+  float* xbias = nullptr;    // [2048] permuted LSTM bias with forget_bias folded in
+  double* sumsq = nullptr;
+  void* wblock = nullptr;
+  CUtensorMap tB_c2, tB_c31, tB_c32, tB_c41, tB_c42, tB_c5, tB_x, tB_h, tB_l, tB_h128;
+  // training: bf16 operands of the data-gradient GEMMs (allocated by crnn_model_set_training)
+  bool training = false;
+  bool dirty_bwd = true;
+  void* wblock_bwd = nullptr;
+  __nv_bfloat16 *Bd_c42 = nullptr, *Bd_c41, *Bd_c32, *Bd_c31, *Bd_c2, *Bd_c5, *Bld, *Bxb, *Bhb;
+  CUtensorMap tD_c42, tD_c41, tD_c32, tD_c31, tD_c2, tD_c5, tD_l, tD_x, tD_h;
+  double* grad_sumsq = nullptr;
+  int lstm_upc = 32;         // hidden units per gate tile: 32 = persistent cluster kernel (default), 64 = per-step launches
+  Plan plan;
+  // per-stage CUDA-event profiling (crnn_profile_*): events are recorded on the caller's stream between stages
+  std::vector<cudaEvent_t> prof_events;   // [slots][kNumStages + 1]
+  int prof_slots = 0, prof_used = 0;
+  bool prof_on = false;
+
+  const TensorInfo* find(const std::string& n) const {
+    for (auto& t : tensors) if (t.name == n) return &t;
+    return nullptr;
+  }
+  float* P(const std::string& n) const { return params + find(n)->offset; }
+};
+
+size_t layout_plan(Plan& pl, int N, int W, uint8_t* base, bool train);
+int prepare_weights(crnn_model* m, cudaStream_t st);
+int ensure_plan(crnn_model* m, int N, int W, void* ws, cudaStream_t st);
