@@ -104,6 +104,23 @@ int     crnn_forward(crnn_model* m, const float* data, const int* time_step_len,
 int     crnn_total_loss(crnn_model* m, const float* costs, int N, float* loss_out,
                         crnn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training.  Replaces tf.gradients + tf.clip_by_global_norm(., 10.0) + AdamOptimizer.apply_gradients
+ * (lib/lstm/train.py:73-83).  Protocol per step:
+ *   crnn_model_set_training(m, 1) once; crnn_forward (saves what the backward needs in the workspace);
+ *   crnn_ctc_loss with grad != NULL and grad_scale = 1/N  -> dlogits;  crnn_backward -> flat `grads` buffer;
+ *   [data parallel: all-reduce(SUM) `grads` across ranks];  crnn_clip_adam_step.
+ * ---------------------------------------------------------------------------------------- */
+int     crnn_model_set_training(crnn_model* m, int flag);
+int     crnn_backward(crnn_model* m, const float* data, const int* time_step_len, const float* dlogits,
+                      int N, int W, void* workspace, size_t workspace_bytes, crnn_stream_t stream);
+/* grads += weight_decay*wd_mul*w on the L2-regularised tensors (network.py:660-662); g *= grad_mul;
+ * g *= clip/max(||g||, clip); TF Adam: lr_t = lr*sqrt(1-b2^step)/(1-b1^step), theta -= lr_t*m/(sqrt(v)+1e-8).
+ * Single GPU: grad_mul = wd_mul = 1.  Data parallel after a SUM all-reduce: grad_mul = 1/world, wd_mul = world. */
+int     crnn_clip_adam_step(crnn_model* m, float lr, float clip, int step, float grad_mul, float wd_mul,
+                            crnn_stream_t stream);
+int     crnn_last_grad_norm(crnn_model* m, float grad_mul, float* out_host, crnn_stream_t stream);   /* syncs */
+
 /* Debug/parity taps: copy a named intermediate of the last crnn_forward() as f32 into dst.
  * names: "conv1" "conv2" "conv3_1" "conv3_2" "conv4_1" "conv4_2" "conv5" "lstm_out"
  * (pooled / post-activation, NHWC, as the reference's layers dict holds them). */
@@ -121,6 +138,10 @@ int         crnn_profile_read(crnn_model* m, float* ms_out, int* forwards);
 /* Stand-alone bf16 GEMM test entry (tests only): D[M,Nc] f32 = A[M,K] * B[Nc,K]^T, bf16 in. */
 int     crnn_test_gemm_bf16(const void* A, const void* B, float* D, int M, int Nc, int K,
                             int block_n, crnn_stream_t stream);
+
+/* MN-major ("TN") GEMM test entry (tests only): D[M,N] f32 (caller-zeroed) += A[K,M]^T * B[K,N], bf16 in. */
+int     crnn_test_gemm_tn_bf16(const void* A, const void* B, float* D, int M, int N, int K, int block_n,
+                               int k_splits, crnn_stream_t stream);
 
 #ifdef __cplusplus
 }

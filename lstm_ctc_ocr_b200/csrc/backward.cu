@@ -1,0 +1,300 @@
+// Backward pass + optimizer orchestration: what tf.gradients / clip_by_global_norm / AdamOptimizer.apply_gradients do in
+// the reference's train_op (lib/lstm/train.py:73-83), as hand-written sm_100a kernels.
+//   data gradients   : K-major tcgen05 GEMMs (csrc/gemm.cuh) with transformed weights
+//   weight gradients : MN-major "TN" tcgen05 GEMMs with split-K f32 reduction (csrc/gemm_tn.cuh)
+//   BPTT             : persistent cluster kernel (csrc/lstm_bwd.cuh)
+//   BN / pool / ReLU / bias / conv1 / clip+Adam : HBM-bound kernels (csrc/backward_kernels.cu)
+#include <cmath>
+#include <cstring>
+
+#include "backward_kernels.cuh"
+#include "gemm_launch.h"
+#include "kernels.cuh"
+#include "lstm_bwd.cuh"
+#include "model_internal.h"
+
+extern "C" int crnn_model_set_training(crnn_model* m, int flag) {
+  if (!m) return crnn_fail(CRNN_INVALID_VALUE, "set_training: null model");
+  if (flag && !m->wblock_bwd) {
+    const size_t nB[9] = {512 * 4608, 256 * 4608, 256 * 2304, 128 * 2304, 64 * 1152, 1024 * 1024, 512 * 64, 512 * 2048, 512 * 1024};
+    size_t tot = 1024;
+    for (size_t v : nB) tot += align_up(v * 2);
+    CUDA_TRY(cudaMalloc(&m->wblock_bwd, tot));
+    uint8_t* p = reinterpret_cast<uint8_t*>(m->wblock_bwd);
+    __nv_bfloat16** dst[9] = {&m->Bd_c42, &m->Bd_c41, &m->Bd_c32, &m->Bd_c31, &m->Bd_c2, &m->Bd_c5, &m->Bld, &m->Bxb, &m->Bhb};
+    for (int i = 0; i < 9; ++i) { *dst[i] = reinterpret_cast<__nv_bfloat16*>(p); p += align_up(nB[i] * 2); }
+    m->grad_sumsq = reinterpret_cast<double*>(p);
+    CRNN_TRY(make_tmap_2d(&m->tD_c42, m->Bd_c42, 512, 4608, 4608, 256));
+    CRNN_TRY(make_tmap_2d(&m->tD_c41, m->Bd_c41, 256, 4608, 4608, 256));
+    CRNN_TRY(make_tmap_2d(&m->tD_c32, m->Bd_c32, 256, 2304, 2304, 256));
+    CRNN_TRY(make_tmap_2d(&m->tD_c31, m->Bd_c31, 128, 2304, 2304, 128));
+    CRNN_TRY(make_tmap_2d(&m->tD_c2, m->Bd_c2, 64, 1152, 1152, 64));
+    CRNN_TRY(make_tmap_2d(&m->tD_c5, m->Bd_c5, 1024, 1024, 1024, 256));
+    CRNN_TRY(make_tmap_2d(&m->tD_l, m->Bld, 512, 64, 64, 256));
+    CRNN_TRY(make_tmap_2d(&m->tD_x, m->Bxb, 512, 2048, 2048, 256));
+    CRNN_TRY(make_tmap_2d(&m->tD_h, m->Bhb, 512, 1024, 1024, 32));
+    m->dirty_bwd = true;
+  }
+  m->training = flag != 0;
+  return CRNN_OK;
+}
+
+static int prepare_weights_bwd(crnn_model* m, cudaStream_t st) {
+  CRNN_TRY(launch_dgrad_weight(m->P("conv4_2/weights"), m->Bd_c42, 512, 512, st));
+  CRNN_TRY(launch_dgrad_weight(m->P("conv4_1/weights"), m->Bd_c41, 256, 512, st));
+  CRNN_TRY(launch_dgrad_weight(m->P("conv3_2/weights"), m->Bd_c32, 256, 256, st));
+  CRNN_TRY(launch_dgrad_weight(m->P("conv3_1/weights"), m->Bd_c31, 128, 256, st));
+  CRNN_TRY(launch_dgrad_weight(m->P("conv2/weights"), m->Bd_c2, 64, 128, st));
+  CRNN_TRY(launch_conv5_dgrad_weight(m->P("conv5/weights"), m->Bd_c5, st));
+  CRNN_TRY(launch_cast_bf16(m->P("logits/weights"), m->Bld, 512 * 64, st));
+  CRNN_TRY(launch_lstm_bwd_weight(m->P("logits/bidirectional_rnn/fw/lstm_cell/weights"), m->P("logits/bidirectional_rnn/bw/lstm_cell/weights"),
+                                  m->Bxb, m->Bhb, 32, st));
+  m->dirty_bwd = false;
+  return CRNN_OK;
+}
+
+static gemm_tn::Params tn_plain(int M, int Ncols, long long rows, float* out, long long ldo) {
+  gemm_tn::Params p;
+  memset(&p, 0, sizeof(p));
+  p.num_taps = 1;
+  p.num_m_tiles = (M + 127) / 128;
+  p.M = M; p.N = Ncols;
+  p.k_blocks_total = (int)((rows + 63) / 64);
+  p.out = out; p.ldo = ldo;
+  return p;
+}
+static gemm_tn::Params tn_conv(int N, int H, int Wd, int Cin, int Cout, float* out) {
+  gemm_tn::Params p;
+  memset(&p, 0, sizeof(p));
+  p.num_taps = 9;
+  p.num_m_tiles = (Cin + 127) / 128;
+  p.M = Cin; p.N = Cout;
+  p.bh = 32 / Wd; p.Wd = Wd; p.H = H; p.Nimg = N; p.Cin = Cin;
+  p.sb_per_img = (H + p.bh - 1) / p.bh;
+  p.k_blocks_total = (N * p.sb_per_img + 1) / 2;
+  p.out = out; p.ldo = Cout; p.tap_stride = (long long)Cin * Cout;
+  return p;
+}
+
+extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_step_len, const float* dlogits, int N, int W,
+                             void* workspace, size_t workspace_bytes, crnn_stream_t stream) {
+  if (!m || !data || !time_step_len || !dlogits || !workspace) return crnn_fail(CRNN_INVALID_VALUE, "backward: null pointer");
+  if (!m->params || !m->grads) return crnn_fail(CRNN_NOT_BOUND, "backward: bind params and grads first");
+  if (!m->training) return crnn_fail(CRNN_INVALID_VALUE, "backward: call crnn_model_set_training(m, 1) before the forward pass");
+  Plan& pl = m->plan;
+  if (pl.N != N || pl.W != W || pl.ws != workspace || !pl.train)
+    return crnn_fail(CRNN_INVALID_VALUE, "backward: no training-mode forward ran on this workspace for (N=%d, W=%d)", N, W);
+  size_t need = 0;
+  CRNN_TRY(crnn_model_workspace_size(m, N, W, 1, &need));
+  if (workspace_bytes < need) return crnn_fail(CRNN_WORKSPACE_TOO_SMALL, "backward: workspace %zu < %zu", workspace_bytes, need);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (m->dirty_bwd) CRNN_TRY(prepare_weights_bwd(m, st));
+  const int H1 = pl.H1, H2 = pl.H2, T = pl.T, sms = m->num_sms;
+  const long long R = (long long)N * H2;
+  auto G = [&](const std::string& n) { return m->grads + m->find(n)->offset; };
+  CUDA_TRY(cudaMemsetAsync(m->grads, 0, (size_t)m->total * sizeof(float), st));
+
+  // ------------------------------------------------------------------ 512 -> 64 projection (network.py:118-128)
+  CRNN_TRY(launch_dlogits_rows(dlogits, pl.dl_rows, G("logits/biases"), T, N, H2, st));
+  {
+    gemm_tn::Params p = tn_plain(512, 64, R, G("logits/weights"), 64);
+    p.num_n_tiles = 1;
+    CRNN_TRY((launch_gemm_tn<64, gemm_tn::TN_PLAIN, 6>(pl.tT_lstm_all, pl.tT_dl, p, sms, st)));
+  }
+  {
+    gemm::Params p;
+    memset(&p, 0, sizeof(p));
+    p.M = (int)R; p.num_m_tiles = (p.M + 127) / 128; p.num_n_tiles = 2; p.num_k_blocks = 1; p.kb_per_shift = 1;
+    p.Nc = 512; p.out = pl.d_lstm_out; p.ldo = 512;
+    CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 4>(pl.tG_dl, m->tD_l, p, sms, st)));
+  }
+  // ------------------------------------------------------------------ BPTT through both directions
+  {
+    lstm_bwd::Params lp;
+    lp.gates = pl.gates; lp.csave = pl.csave; lp.d_out = pl.d_lstm_out; lp.dz_state = pl.dz_state; lp.dz_all = pl.dz_all;
+    lp.seq_len = time_step_len; lp.Nimg = N; lp.Npad = pl.Npad; lp.H = H2; lp.T = T; lp.tiles_per_dir = pl.Npad / 128;
+    static bool attr = false;
+    if (!attr) {
+      CUDA_TRY(cudaFuncSetAttribute(lstm_bwd::lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_bwd::SMEM_BYTES));
+      attr = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(lstm_bwd::CS * 2 * lp.tiles_per_dir);
+    cfg.blockDim = dim3(lstm_bwd::NUM_THREADS);
+    cfg.dynamicSmemBytes = lstm_bwd::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = lstm_bwd::CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, lstm_bwd::lstm_bwd_kernel, pl.tG_dzstate, m->tD_h, lp));
+  }
+  {
+    const std::string fw = "logits/bidirectional_rnn/fw/lstm_cell", bw = "logits/bidirectional_rnn/bw/lstm_cell";
+    const long long dW = m->find(bw + "/weights")->offset - m->find(fw + "/weights")->offset;
+    const long long db = m->find(bw + "/biases")->offset - m->find(fw + "/biases")->offset;
+    CRNN_TRY(launch_colsum_bf16(pl.dz_all, R, 2048, G(fw + "/biases"), 32, db, st));
+    {  // dW_x (rows 0..511 of both [768,1024] matrices) = a5^T dz
+      gemm_tn::Params p = tn_plain(512, 2048, R, G(fw + "/weights"), 1024);
+      p.num_n_tiles = 8; p.lstm_cols = 1; p.dir_stride = dW;
+      CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_PLAIN, 4>(pl.tT_a5, pl.tT_dz, p, sms, st)));
+    }
+    {  // dW_h forward direction: previous step = frame t-1
+      gemm_tn::Params p = tn_plain(256, 1024, R, G(fw + "/weights"), 1024);
+      p.num_n_tiles = 4; p.lstm_cols = 1; p.out_row_offset = 512; p.a_row_shift = -1;
+      CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_PLAIN, 4>(pl.tT_lstm_fw, pl.tT_dz_fw, p, sms, st)));
+    }
+    {  // dW_h backward direction: previous step = frame t+1
+      gemm_tn::Params p = tn_plain(256, 1024, R, G(bw + "/weights"), 1024);
+      p.num_n_tiles = 4; p.lstm_cols = 1; p.out_row_offset = 512; p.a_row_shift = +1;
+      CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_PLAIN, 4>(pl.tT_lstm_bw, pl.tT_dz_bw, p, sms, st)));
+    }
+    {  // dx = dz W_x^T  ->  gradient w.r.t. the conv5 feature rows
+      gemm::Params p;
+      memset(&p, 0, sizeof(p));
+      p.M = (int)R; p.num_m_tiles = (p.M + 127) / 128; p.num_n_tiles = 2; p.num_k_blocks = 32; p.kb_per_shift = 32;
+      p.Nc = 512; p.out = pl.d_a5; p.ldo = 512;
+      CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 4>(pl.tG_dz, m->tD_x, p, sms, st)));
+    }
+  }
+  // ------------------------------------------------------------------ conv5 (2x2 VALID)
+  CRNN_TRY(launch_colsum_bf16(pl.d_a5, R, 512, G("conv5/biases"), 0, 0, st));
+  for (int r = 0; r < 2; ++r) {
+    gemm_tn::Params p = tn_plain(1024, 512, R, G("conv5/weights") + (size_t)r * 1024 * 512, 512);
+    p.num_n_tiles = 2; p.a_row_shift = r;
+    CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_PLAIN, 4>(pl.tT_a4b, pl.tT_da5, p, sms, st)));
+  }
+  {
+    gemm::Params p;
+    memset(&p, 0, sizeof(p));
+    p.M = (int)R; p.num_m_tiles = (p.M + 127) / 128; p.num_n_tiles = 4; p.num_k_blocks = 16; p.kb_per_shift = 8; p.row_shift_mul = -1;
+    p.Nc = 1024; p.out = pl.d_a4b; p.ldo = 1024;
+    CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 4>(pl.tG_da5, m->tD_c5, p, sms, st)));
+  }
+  // ------------------------------------------------------------------ conv4_2: pool3 + ReLU + batch-stat BN backward
+  CUDA_TRY(cudaMemsetAsync(pl.bn_bwd_sums, 0, 2 * 2 * 512 * sizeof(double), st));
+  const size_t P4 = (size_t)N * H2 * 4;
+  CRNN_TRY(launch_bn_bwd_reduce(true, pl.d_a4b, pl.a4b_pre, pl.d_pre4b, pl.bn + 2048, pl.bn_bwd_sums + 1024, P4 / 2, 512, st));
+  CRNN_TRY(launch_bn_bwd_apply(pl.d_pre4b, pl.a4b_pre, pl.bn + 2048, m->P("conv4_2/conv4_2/gamma"), pl.bn_bwd_sums + 1024, (double)P4, P4,
+                               512, G("conv4_2/conv4_2/gamma"), G("conv4_2/conv4_2/beta"), st));
+  CRNN_TRY(launch_colsum_bf16(pl.d_pre4b, (long long)P4, 512, G("conv4_2/biases"), 0, 0, st));
+  {
+    gemm_tn::Params p = tn_conv(N, H2, 4, 512, 512, G("conv4_2/weights"));
+    p.num_n_tiles = 2;
+    CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tA_c42, pl.tG_p4b, p, sms, st)));
+  }
+  {
+    gemm::Params p = conv_params(N, H2, 4, 512, 512, 256, nullptr, pl.d_pre4a);
+    CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_CONV_STORE, 4>(pl.tG_p4b, m->tD_c42, p, sms, st)));
+  }
+  // ------------------------------------------------------------------ conv4_1: ReLU + BN backward
+  CRNN_TRY(launch_bn_bwd_reduce(false, pl.d_pre4a, pl.a4a_pre, pl.d_pre4a, pl.bn, pl.bn_bwd_sums, P4, 512, st));
+  CRNN_TRY(launch_bn_bwd_apply(pl.d_pre4a, pl.a4a_pre, pl.bn, m->P("conv4_1/conv4_1/gamma"), pl.bn_bwd_sums, (double)P4, P4, 512,
+                               G("conv4_1/conv4_1/gamma"), G("conv4_1/conv4_1/beta"), st));
+  CRNN_TRY(launch_colsum_bf16(pl.d_pre4a, (long long)P4, 512, G("conv4_1/biases"), 0, 0, st));
+  {
+    gemm_tn::Params p = tn_conv(N, H2, 4, 256, 512, G("conv4_1/weights"));
+    p.num_n_tiles = 2;
+    CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tA_c41, pl.tG_p4a, p, sms, st)));
+  }
+  {
+    gemm::Params p = conv_params(N, H2, 4, 512, 256, 256, nullptr, pl.d_a3p);
+    CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_CONV_STORE, 4>(pl.tG_p4a, m->tD_c41, p, sms, st)));
+  }
+  // ------------------------------------------------------------------ conv3_2: 1x2 pool + ReLU backward
+  CRNN_TRY(launch_unpool_relu_bwd(2, pl.d_a3p, pl.a3p, pl.am3, pl.d_pre32, (size_t)N * H2 * 4, H2, 4, 256, st));
+  CRNN_TRY(launch_colsum_bf16(pl.d_pre32, (long long)N * H2 * 8, 256, G("conv3_2/biases"), 0, 0, st));
+  {
+    gemm_tn::Params p = tn_conv(N, H2, 8, 256, 256, G("conv3_2/weights"));
+    p.num_n_tiles = 1;
+    CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tA_c32, pl.tG_p32, p, sms, st)));
+  }
+  {
+    gemm::Params p = conv_params(N, H2, 8, 256, 256, 256, nullptr, pl.d_pre31);
+    CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_CONV_STORE, 4>(pl.tG_p32, m->tD_c32, p, sms, st)));
+  }
+  // ------------------------------------------------------------------ conv3_1: ReLU backward
+  CRNN_TRY(launch_relu_bwd(pl.d_pre31, pl.a3, (size_t)N * H2 * 8 * 256, st));
+  CRNN_TRY(launch_colsum_bf16(pl.d_pre31, (long long)N * H2 * 8, 256, G("conv3_1/biases"), 0, 0, st));
+  {
+    gemm_tn::Params p = tn_conv(N, H2, 8, 128, 256, G("conv3_1/weights"));
+    p.num_n_tiles = 1;
+    CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tA_c31, pl.tG_p31, p, sms, st)));
+  }
+  {
+    gemm::Params p = conv_params(N, H2, 8, 256, 128, 128, nullptr, pl.d_a2);
+    CRNN_TRY((launch_gemm<128, gemm::A_CONV3, gemm::EPI_CONV_STORE, 6>(pl.tG_p31, m->tD_c31, p, sms, st)));
+  }
+  // ------------------------------------------------------------------ conv2: 2x2 pool + ReLU backward
+  CRNN_TRY(launch_unpool_relu_bwd(4, pl.d_a2, pl.a2, pl.am2, pl.d_pre2, (size_t)N * H2 * 8, H2, 8, 128, st));
+  CRNN_TRY(launch_colsum_bf16(pl.d_pre2, (long long)N * H1 * 16, 128, G("conv2/biases"), 0, 0, st));
+  {
+    gemm_tn::Params p = tn_conv(N, H1, 16, 64, 128, G("conv2/weights"));
+    p.num_n_tiles = 1;
+    CRNN_TRY((launch_gemm_tn<128, gemm_tn::TN_CONV, 6>(pl.tA_c2, pl.tG_p2, p, sms, st)));
+  }
+  {
+    gemm::Params p = conv_params(N, H1, 16, 128, 64, 64, nullptr, pl.d_a1);
+    CRNN_TRY((launch_gemm<64, gemm::A_CONV3, gemm::EPI_CONV_STORE, 8>(pl.tG_p2, m->tD_c2, p, sms, st)));
+  }
+  // ------------------------------------------------------------------ conv1 (K = 9, SIMT): pool1 + ReLU folded in
+  CRNN_TRY(launch_conv1_wgrad(pl.d_a1, pl.a1, pl.am1, data, G("conv1/weights"), G("conv1/biases"), N, W, st));
+  return CRNN_OK;
+}
+
+// grads <- grads + wd*wd_mul*w on the regularised tensors; g <- g*grad_mul; clip by global norm; TF Adam.
+// Data-parallel use: all-reduce(SUM) the flat gradient buffer first, then call with grad_mul = 1/world, wd_mul = world.
+extern "C" int crnn_clip_adam_step(crnn_model* m, float lr, float clip, int step, float grad_mul, float wd_mul,
+                                   crnn_stream_t stream) {
+  if (!m || step < 1) return crnn_fail(CRNN_INVALID_VALUE, "clip_adam_step: bad args");
+  if (!m->params || !m->grads || !m->adam_m || !m->adam_v) return crnn_fail(CRNN_NOT_BOUND, "clip_adam_step: bind params, grads and Adam slots");
+  if (!m->grad_sumsq) return crnn_fail(CRNN_INVALID_VALUE, "clip_adam_step: call crnn_model_set_training(m, 1) first");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  WdSegs segs;
+  segs.n = 0;
+  for (auto& c : kConvs) {
+    const TensorInfo* t = m->find(std::string(c.name) + "/weights");
+    segs.off[segs.n] = t->offset; segs.cnt[segs.n] = t->count; segs.n++;
+  }
+  const TensorInfo* t = m->find("logits/weights");
+  segs.off[segs.n] = t->offset; segs.cnt[segs.n] = t->count; segs.n++;
+  CRNN_TRY(launch_grad_finish(m->grads, m->params, segs, m->cfg.weight_decay * wd_mul, m->total, m->grad_sumsq, st));
+  const double b1 = 0.9, b2 = 0.999;
+  const float lr_t = (float)(lr * std::sqrt(1.0 - std::pow(b2, step)) / (1.0 - std::pow(b1, step)));
+  CRNN_TRY(launch_clip_adam(m->params, m->grads, m->adam_m, m->adam_v, m->grad_sumsq, grad_mul, clip, lr_t, (float)b1, (float)b2, 1e-8f,
+                            m->total, st));
+  m->dirty = true;
+  m->dirty_bwd = true;
+  return CRNN_OK;
+}
+
+// global gradient norm of the last crnn_clip_adam_step (before clipping, after averaging); host-synchronising helper
+extern "C" int crnn_last_grad_norm(crnn_model* m, float grad_mul, float* out, crnn_stream_t stream) {
+  if (!m || !out || !m->grad_sumsq) return crnn_fail(CRNN_INVALID_VALUE, "last_grad_norm: bad args");
+  double v = 0;
+  CUDA_TRY(cudaMemcpyAsync(&v, m->grad_sumsq, sizeof(double), cudaMemcpyDeviceToHost, reinterpret_cast<cudaStream_t>(stream)));
+  CUDA_TRY(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+  *out = (float)(std::sqrt(v) * grad_mul);
+  return CRNN_OK;
+}
+
+// MN-major GEMM unit-test entry: D[M,N] (zeroed by the caller) += A[K,M]^T B[K,N]
+extern "C" int crnn_test_gemm_tn_bf16(const void* A, const void* B, float* D, int M, int Ncols, int K, int block_n,
+                                      int k_splits, crnn_stream_t stream) {
+  if (!A || !B || !D || M <= 0 || Ncols <= 0 || K <= 0 || (M % 8) || (Ncols % 8)) return crnn_fail(CRNN_INVALID_VALUE, "test_gemm_tn: bad args");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CUtensorMap ta, tb;
+  CRNN_TRY(make_tmap_2d_box(&ta, A, K, M, M, 64, 64));
+  CRNN_TRY(make_tmap_2d_box(&tb, B, K, Ncols, Ncols, 64, 64));
+  gemm_tn::Params p = tn_plain(M, Ncols, K, D, Ncols);
+  p.num_n_tiles = (Ncols + block_n - 1) / block_n;
+  p.k_splits = k_splits;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (block_n == 64) return launch_gemm_tn<64, gemm_tn::TN_PLAIN, 6>(ta, tb, p, sms, st);
+  if (block_n == 128) return launch_gemm_tn<128, gemm_tn::TN_PLAIN, 6>(ta, tb, p, sms, st);
+  if (block_n == 256) return launch_gemm_tn<256, gemm_tn::TN_PLAIN, 4>(ta, tb, p, sms, st);
+  return crnn_fail(CRNN_INVALID_VALUE, "test_gemm_tn: block_n must be 64/128/256");
+}

@@ -174,6 +174,7 @@ extern "C" int crnn_model_create(const crnn_config* cfg, crnn_model** out) {
 extern "C" int crnn_model_destroy(crnn_model* m) {
   if (!m) return CRNN_OK;
   if (m->wblock) cudaFree(m->wblock);
+  if (m->wblock_bwd) cudaFree(m->wblock_bwd);
   for (auto e : m->prof_events) cudaEventDestroy(e);
   delete m;
   return CRNN_OK;
@@ -194,11 +195,13 @@ extern "C" int crnn_model_bind(crnn_model* m, float* params, float* grads, float
   if (!m || !params) return crnn_fail(CRNN_INVALID_VALUE, "model_bind: null params");
   m->params = params; m->grads = grads; m->adam_m = adam_m; m->adam_v = adam_v;
   m->dirty = true;
+  m->dirty_bwd = true;
   return CRNN_OK;
 }
 extern "C" int crnn_model_params_changed(crnn_model* m) {
   if (!m) return crnn_fail(CRNN_INVALID_VALUE, "null model");
   m->dirty = true;
+  m->dirty_bwd = true;
   return CRNN_OK;
 }
 
@@ -340,22 +343,6 @@ int ensure_plan(crnn_model* m, int N, int W, void* ws, cudaStream_t st) {
   Plan& pl = m->plan;
   if (pl.N != N || pl.W != W || pl.ws != ws || pl.train != m->training) return build_plan(m, N, W, ws, st);
   return CRNN_OK;
-}
-
-static gemm::Params conv_params(int N, int H, int Wd, int Cin, int Cout, int block_n, const float* bias, void* out) {
-  gemm::Params p;
-  memset(&p, 0, sizeof(p));
-  p.bh = 32 / Wd;
-  p.Wd = Wd; p.H = H; p.Nimg = N;
-  p.sb_per_img = (H + p.bh - 1) / p.bh;
-  p.num_m_tiles = (N * p.sb_per_img + 3) / 4;
-  p.num_n_tiles = Cout / block_n;
-  p.cin_blocks = Cin / 64;
-  p.num_k_blocks = 9 * p.cin_blocks;
-  p.Nc = Cout;
-  p.bias = bias;
-  p.out = out;
-  return p;
 }
 
 extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_step_len, int N, int W, float* logits_out,

@@ -6,6 +6,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "gemm.cuh"
 
 int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride, uint32_t box_rows);
 int make_tmap_nhwc(CUtensorMap* m, const void* base, int N, int H, int Wd, int C, int bh);
@@ -90,3 +91,21 @@ struct crnn_model {
 size_t layout_plan(Plan& pl, int N, int W, uint8_t* base, bool train);
 int prepare_weights(crnn_model* m, cudaStream_t st);
 int ensure_plan(crnn_model* m, int N, int W, void* ws, cudaStream_t st);
+
+static inline gemm::Params conv_params(int N, int H, int Wd, int Cin, int Cout, int block_n, const float* bias, void* out) {
+  gemm::Params p;
+  memset(&p, 0, sizeof(p));
+  p.bh = 32 / Wd;
+  p.Wd = Wd; p.H = H; p.Nimg = N;
+  p.sb_per_img = (H + p.bh - 1) / p.bh;
+  p.num_m_tiles = (N * p.sb_per_img + 3) / 4;
+  p.num_n_tiles = Cout / block_n;
+  p.cin_blocks = Cin / 64;
+  p.num_k_blocks = 9 * p.cin_blocks;
+  p.Nc = Cout;
+  p.bias = bias;
+  p.out = out;
+  return p;
+}
+
+

@@ -48,6 +48,39 @@ class CrnnModel:
         self._bind()
         self._ws = None
         self._ws_key = None
+        self.training = False
+
+    # ---- training --------------------------------------------------------------------------
+    def set_training(self, flag=True):
+        """Allocate the gradient / Adam-slot buffers (flat f32, same layout as params) and switch the forward to the
+        variant that saves what the backward pass needs."""
+        if flag and self.grads is None:
+            self.grads = torch.zeros_like(self.params)
+            self.adam_m = torch.zeros_like(self.params)
+            self.adam_v = torch.zeros_like(self.params)
+            self._bind()
+        check(self.lib.crnn_model_set_training(self.handle, 1 if flag else 0))
+        self.training = bool(flag)
+        self._ws_key = None
+
+    def grad_tensor(self, name):
+        off, shp = self.table[name]
+        return self.grads[off:off + int(np.prod(shp))].view(*shp)
+
+    def backward(self, data, time_step_len, dlogits):
+        """dlogits [T,N,64] f32 = d loss / d logits (e.g. the CTC gradient scaled by 1/N) -> fills self.grads."""
+        N, W, _ = data.shape
+        ws, nbytes = self._workspace(N, W)
+        check(self.lib.crnn_backward(self.handle, data.data_ptr(), time_step_len.data_ptr(), dlogits.data_ptr(), N, W, ws, nbytes,
+                                     _stream()))
+
+    def clip_adam_step(self, lr, step, clip=10.0, grad_mul=1.0, wd_mul=1.0):
+        check(self.lib.crnn_clip_adam_step(self.handle, float(lr), float(clip), int(step), float(grad_mul), float(wd_mul), _stream()))
+
+    def last_grad_norm(self, grad_mul=1.0):
+        out = _lib.c_float()
+        check(self.lib.crnn_last_grad_norm(self.handle, float(grad_mul), out, _stream()))
+        return float(out.value)
 
     def _bind(self):
         check(self.lib.crnn_model_bind(self.handle, _ptr(self.params), _ptr(self.grads), _ptr(self.adam_m), _ptr(self.adam_v)))
@@ -79,10 +112,10 @@ class CrnnModel:
 
     # ---- forward ----------------------------------------------------------------------------
     def _workspace(self, N, W):
-        key = (N, W)
+        key = (N, W, self.training)
         if self._ws_key != key:
             nbytes = _lib.c_size_t()
-            check(self.lib.crnn_model_workspace_size(self.handle, N, W, 0, nbytes))
+            check(self.lib.crnn_model_workspace_size(self.handle, N, W, 1 if self.training else 0, nbytes))
             self._ws = None
             self._ws = torch.empty(nbytes.value + 1024, dtype=torch.uint8, device=self.device)
             self._ws_key = key
@@ -157,6 +190,16 @@ def dense_decoded(out, out_len):
     """sparse_tensor_to_dense(default 0) shape [N, max_len] (network.py:657); one D2H sync."""
     m = int(out_len.max().item()) if out_len.numel() else 0
     return out[:, :m].contiguous()
+
+
+def test_gemm_tn_bf16(A, B, block_n, k_splits=0):
+    """D[M,N] = A[K,M]^T @ B[K,N] through the MN-major tcgen05 path (tests only)."""
+    lib = _lib.load()
+    K, M = A.shape
+    Nc = B.shape[1]
+    D = torch.zeros((M, Nc), dtype=torch.float32, device=A.device)
+    check(lib.crnn_test_gemm_tn_bf16(A.data_ptr(), B.data_ptr(), D.data_ptr(), M, Nc, K, block_n, k_splits, _stream()))
+    return D
 
 
 def test_gemm_bf16(A, B, block_n):
