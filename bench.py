@@ -139,6 +139,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=32, help="lines per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the extra training-step measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -250,11 +251,38 @@ def main():
     ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- BASELINE configs[4] companion: full training step (fwd + CTC + backward + [NCCL grad all-reduce] + clip + Adam)
+    ms_train = None
+    if not args.no_train:
+        from lstm_ctc_ocr_b200 import parallel
+        model.set_training(True)
+        Kt = max(3, min(K, 10))
+
+        def train_step(i, stepno):
+            d, lab, ll, tsl, mll, _ = batches[i % nrot]
+            model.forward(d, tsl, out=logits)
+            engine.ctc_loss(logits, lab, ll, tsl, want_grad=True, grad_scale=1.0 / N, max_label_len=mll, costs=costs, grad=grad)
+            model.backward(d, tsl, grad)
+            if world > 1:
+                parallel.allreduce_sum_(model.grads)
+            model.clip_adam_step(lr=1e-4, step=stepno, clip=10.0, grad_mul=1.0 / world, wd_mul=float(world))
+        for i in range(3):
+            train_step(i, i + 1)
+        sync_all()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(Kt):
+            train_step(i, 4 + i)
+        g1.record()
+        sync_all()
+        ms_train = g0.elapsed_time(g1) / Kt
+
     # ---- max over ranks
     if world > 1:
-        t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_total, ms_e2e, ms_train or 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, ms_e2e = float(t[0]), float(t[1])
+        ms_train = float(t[2]) if ms_train is not None else None
     ms_step = ms_total / K
     value = world * N / (ms_step / 1e3)
     e2e_value = world * N / (ms_e2e / Ke / 1e3)
@@ -295,6 +323,10 @@ def main():
             "gpu_launches": K * (1 + 8 + T + 4 + 1 + 1),
             "roofline": roofline, "stages": stages, "clocks": clocks,
         }
+        if ms_train is not None:
+            line["train_step"] = {"ms_per_step": round(ms_train, 4), "images_per_s": round(world * N / (ms_train / 1e3), 1),
+                                  "what": "fwd + CTC loss/grad + backward + " + ("NCCL all-reduce(28.6 MB f32) + " if world > 1 else "") +
+                                          "global-norm clip + Adam (BASELINE configs[4] per-GPU shape)"}
         if world == 1 and not args.no_cpu_baseline:
             sn = args.cpu_sample
             r = cpu_reference(sn, W, steps=8, warmup=2)

@@ -119,6 +119,10 @@ class Session(object):
         self.validate_feed(data, tsl, labels, llen)
         eng = self.engine_for(net)
         dev = self.device
+        # training mode is sticky: its forward is a superset (it also saves what the backward needs), and switching back
+        # and forth would re-plan the multi-GB workspace
+        if any(k == "train_op" for k in kinds) and not eng.training:
+            eng.set_training(True)
         d_data = self._pinned.stage("data", data, dev)
         d_tsl = self._pinned.stage("tsl", tsl, dev)
         self.h2d_bytes = data.nbytes + tsl.nbytes
@@ -149,10 +153,7 @@ class Session(object):
                 o, ol = engine.ctc_greedy(logits, d_tsl)
                 v = engine.dense_decoded(o, ol).cpu().numpy()
             elif k == "train_op":
-                step = getattr(f, "step_fn", None)
-                if step is None:
-                    raise CrnnError("train_op has no step function attached")
-                v = step(eng, logits, grad, d_data, d_tsl)
+                v = f.step_fn(eng, logits, grad, d_data, d_tsl)
             elif k.startswith("layer:"):
                 name = k.split(":", 1)[1]
                 tapname = {"pool1": "conv1", "pool2": "conv3_2", "pool3": "conv4_2", "reshaped_layer": "conv5"}.get(name, name)
