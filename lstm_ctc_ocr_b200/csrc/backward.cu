@@ -177,7 +177,7 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   const size_t P4 = (size_t)N * H2 * 4;
   CRNN_TRY(launch_bn_bwd_reduce(true, pl.d_a4b, pl.a4b_pre, pl.d_pre4b, pl.bn + 2048, pl.bn_bwd_sums + 1024, P4 / 2, 512, st));
   CRNN_TRY(launch_bn_bwd_apply(pl.d_pre4b, pl.a4b_pre, pl.bn + 2048, m->P("conv4_2/conv4_2/gamma"), pl.bn_bwd_sums + 1024, (double)P4, P4,
-                               512, G("conv4_2/conv4_2/gamma"), G("conv4_2/conv4_2/beta"), st));
+                               512, pl.bn_bwd_coef, G("conv4_2/conv4_2/gamma"), G("conv4_2/conv4_2/beta"), st));
   CRNN_TRY(launch_colsum_bf16(pl.d_pre4b, (long long)P4, 512, G("conv4_2/biases"), 0, 0, st));
   {
     gemm_tn::Params p = tn_conv(N, H2, 4, 512, 512, G("conv4_2/weights"));
@@ -191,7 +191,7 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   // ------------------------------------------------------------------ conv4_1: ReLU + BN backward
   CRNN_TRY(launch_bn_bwd_reduce(false, pl.d_pre4a, pl.a4a_pre, pl.d_pre4a, pl.bn, pl.bn_bwd_sums, P4, 512, st));
   CRNN_TRY(launch_bn_bwd_apply(pl.d_pre4a, pl.a4a_pre, pl.bn, m->P("conv4_1/conv4_1/gamma"), pl.bn_bwd_sums, (double)P4, P4, 512,
-                               G("conv4_1/conv4_1/gamma"), G("conv4_1/conv4_1/beta"), st));
+                               pl.bn_bwd_coef, G("conv4_1/conv4_1/gamma"), G("conv4_1/conv4_1/beta"), st));
   CRNN_TRY(launch_colsum_bf16(pl.d_pre4a, (long long)P4, 512, G("conv4_1/biases"), 0, 0, st));
   {
     gemm_tn::Params p = tn_conv(N, H2, 4, 256, 512, G("conv4_1/weights"));

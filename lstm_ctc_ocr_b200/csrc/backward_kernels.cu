@@ -56,11 +56,21 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   float part[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) part[i] = 0.f;
-  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < R; r += (long long)gridDim.x * 8) {
-    float v[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(src + r * C + cb)), v);
+  const long long stride = (long long)gridDim.x * 8;
+  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < R; r += 4 * stride) {
+    uint4 q[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) part[i] += v[i];
+    for (int u = 0; u < 4; ++u) {
+      const long long rr = r + u * stride;
+      q[u] = (rr < R) ? __ldg(reinterpret_cast<const uint4*>(src + rr * C + cb)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float v[8];
+      unpack8(q[u], v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) part[i] += v[i];
+    }
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -146,30 +156,40 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
   }
 }
 
-// pass 2: dx = gamma*invstd * (dy - sum(dy)/M - xhat * sum(dy*xhat)/M), in place on dy; block 0 also writes dgamma/dbeta
+// pass 2a: per-channel coefficients of  dx = A*dy + B + C*x   (from dx = gamma*invstd*(dy - mean(dy) - xhat*mean(dy*xhat))),
+// plus dgamma = sum(dy*xhat), dbeta = sum(dy)
+__global__ void bn_bwd_coef_kernel(const float* __restrict__ bn, const float* __restrict__ gamma, const double* __restrict__ sums,
+                                   double count, int C, float* __restrict__ coef, float* __restrict__ dgamma,
+                                   float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mu = bn[2 * C + c], is = bn[3 * C + c], g = gamma[c];
+  const double m1 = sums[c] / count, m2 = sums[C + c] / count;
+  coef[c] = (float)(g * is);
+  coef[C + c] = (float)(-g * is * m1 + g * is * is * m2 * mu);
+  coef[2 * C + c] = (float)(-g * is * is * m2);
+  dbeta[c] += (float)sums[c];
+  dgamma[c] += (float)sums[C + c];
+}
+// pass 2b: elementwise, in place on dy
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(uint4* __restrict__ dy, const uint4* __restrict__ x_pre,
-                                                           const float* __restrict__ bn, const float* __restrict__ gamma,
-                                                           const double* __restrict__ sums, double count, size_t nvec, int C,
-                                                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                           const float* __restrict__ coef, size_t nvec, int C) {
   const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      dbeta[c] += (float)sums[c];
-      dgamma[c] += (float)sums[C + c];
-    }
-  }
   if (i0 >= nvec) return;
   const int c = (int)((i0 * 8) % C);
-  float d[8], x[8];
+  float d[8], x[8], A[8], B[8], Cc[8];
   unpack8(dy[i0], d);
   unpack8(__ldg(x_pre + i0), x);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float is = bn[3 * C + c + i], mu = bn[2 * C + c + i];
-    const float xh = (x[i] - mu) * is;
-    const float m1 = (float)(sums[c + i] / count), m2 = (float)(sums[C + c + i] / count);
-    d[i] = gamma[c + i] * is * (d[i] - m1 - xh * m2);
+  for (int h = 0; h < 2; ++h) {
+    const float4 a4 = __ldg(reinterpret_cast<const float4*>(coef + c) + h), b4 = __ldg(reinterpret_cast<const float4*>(coef + C + c) + h),
+                 c4 = __ldg(reinterpret_cast<const float4*>(coef + 2 * C + c) + h);
+    A[4 * h] = a4.x; A[4 * h + 1] = a4.y; A[4 * h + 2] = a4.z; A[4 * h + 3] = a4.w;
+    B[4 * h] = b4.x; B[4 * h + 1] = b4.y; B[4 * h + 2] = b4.z; B[4 * h + 3] = b4.w;
+    Cc[4 * h] = c4.x; Cc[4 * h + 1] = c4.y; Cc[4 * h + 2] = c4.z; Cc[4 * h + 3] = c4.w;
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d[i] = fmaf(A[i], d[i], fmaf(Cc[i], x[i], B[i]));
   dy[i0] = pack8(d);
 }
 
@@ -370,7 +390,7 @@ int launch_dlogits_rows(const float* dlogits, __nv_bfloat16* rows, float* dbias,
   LAUNCH_CHECK();
 }
 int launch_colsum_bf16(const __nv_bfloat16* src, long long R, int C, float* out, int perm_upc, long long dir_stride, cudaStream_t st) {
-  dim3 grid(296, (C + 255) / 256);
+  dim3 grid(592, (C + 255) / 256);
   colsum_bf16_kernel<<<grid, 256, 0, st>>>(src, R, C, out, perm_upc, dir_stride);
   LAUNCH_CHECK();
 }
@@ -381,10 +401,11 @@ int launch_bn_bwd_reduce(bool pool, const __nv_bfloat16* dout, const __nv_bfloat
   LAUNCH_CHECK();
 }
 int launch_bn_bwd_apply(__nv_bfloat16* dy, const __nv_bfloat16* x_pre, const float* bn, const float* gamma, const double* sums,
-                        double count, size_t positions, int C, float* dgamma, float* dbeta, cudaStream_t st) {
+                        double count, size_t positions, int C, float* coef, float* dgamma, float* dbeta, cudaStream_t st) {
   const size_t nvec = positions * C / 8;
-  bn_bwd_apply_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, st>>>((uint4*)dy, (const uint4*)x_pre, bn, gamma, sums, count, nvec, C,
-                                                                      dgamma, dbeta);
+  bn_bwd_coef_kernel<<<(C + 127) / 128, 128, 0, st>>>(bn, gamma, sums, count, C, coef, dgamma, dbeta);
+  CUDA_TRY(cudaGetLastError());
+  bn_bwd_apply_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, st>>>((uint4*)dy, (const uint4*)x_pre, coef, nvec, C);
   LAUNCH_CHECK();
 }
 int launch_relu_bwd(__nv_bfloat16* d, const __nv_bfloat16* a, size_t n, cudaStream_t st) {

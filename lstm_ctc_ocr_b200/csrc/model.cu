@@ -280,6 +280,7 @@ size_t layout_plan(Plan& pl, int N, int W, uint8_t* base, bool train) {
     pl.d_pre2 = (__nv_bfloat16*)take(n * h1 * 16 * 128 * 2);
     pl.d_a1 = (__nv_bfloat16*)take(n * h1 * 16 * 64 * 2);
     pl.bn_bwd_sums = (double*)take(2 * 2 * 512 * 8);
+    pl.bn_bwd_coef = (float*)take(3 * 512 * 4);
   }
   return off;
 }

@@ -48,6 +48,7 @@ struct Plan {
   __nv_bfloat16 *dl_rows, *d_lstm_out, *dz_all, *dz_state, *d_a5, *d_a4b, *d_pre4b, *d_pre4a, *d_a3p, *d_pre32, *d_pre31, *d_a2,
       *d_pre2, *d_a1;
   double* bn_bwd_sums;                            // [2 layers][2][512]
+  float* bn_bwd_coef;                             // [3][512] scratch
   // K-major A maps of gradient buffers (data-gradient GEMMs)
   CUtensorMap tG_dl, tG_dz, tG_da5, tG_p4b, tG_p4a, tG_p32, tG_p31, tG_p2, tG_dzstate;
   // MN-major (TN) maps: 2-D [rows, C] with 64x64 boxes, and the NHWC maps above reused for TN_CONV

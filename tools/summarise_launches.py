@@ -8,7 +8,7 @@ import sys
 def short(n):
     m = re.search(r"gemm_kernel<(\d+), ?(\d+), ?(\d+), ?(\d+)>", n)
     if m:
-        names = ["F32", "BIAS_BF16", "RELU", "RELU_POOL22", "RELU_POOL12", "STATS", "LSTM", "LOGITS", "XPROJ", "GRADIN", "WGRAD"]
+        names = ["F32", "BIAS_BF16", "RELU", "RELU_POOL22", "RELU_POOL12", "STATS", "LSTM", "LOGITS", "XPROJ", "CONV_STORE(dgrad)", "RELU_POOL22_T", "RELU_POOL12_T"]
         epi = names[int(m.group(3))] if int(m.group(3)) < len(names) else m.group(3)
         return f'gemm<{m.group(1)},{"CONV3" if m.group(2) == "1" else "PLAIN"},{epi}>'
     return re.sub(r"\(.*", "", n).replace("void ", "").replace("(anonymous namespace)::", "")[:60]
