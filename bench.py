@@ -269,6 +269,7 @@ def main():
         for i in range(3):
             train_step(i, i + 1)
         sync_all()
+        check(model.lib.crnn_profile_begin(model.handle, Kt))
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         for i in range(Kt):
@@ -276,6 +277,14 @@ def main():
         g1.record()
         sync_all()
         ms_train = g0.elapsed_time(g1) / Kt
+        nb = model.lib.crnn_profile_bwd_num_stages()
+        bbuf = np.zeros((Kt, nb), dtype=np.float32)
+        nfb = c_int()
+        check(model.lib.crnn_profile_bwd_read(model.handle, bbuf.ctypes.data, nfb))
+        bwd_stage_ms = {model.lib.crnn_profile_bwd_stage_name(i).decode(): round(float(bbuf[:nfb.value, i].mean()), 4) for i in range(nb)}
+        fbuf = np.zeros((Kt, nst), dtype=np.float32)
+        check(model.lib.crnn_profile_read(model.handle, fbuf.ctypes.data, nfb))
+        bwd_stage_ms["forward_total(train mode)"] = round(float(fbuf[:nfb.value].sum(axis=1).mean()), 4)
 
     # ---- max over ranks
     if world > 1:
@@ -326,7 +335,8 @@ def main():
         if ms_train is not None:
             line["train_step"] = {"ms_per_step": round(ms_train, 4), "images_per_s": round(world * N / (ms_train / 1e3), 1),
                                   "what": "fwd + CTC loss/grad + backward + " + ("NCCL all-reduce(28.6 MB f32) + " if world > 1 else "") +
-                                          "global-norm clip + Adam (BASELINE configs[4] per-GPU shape)"}
+                                          "global-norm clip + Adam (BASELINE configs[4] per-GPU shape)",
+                                  "stages_ms": bwd_stage_ms}
         if world == 1 and not args.no_cpu_baseline:
             sn = args.cpu_sample
             r = cpu_reference(sn, W, steps=8, warmup=2)

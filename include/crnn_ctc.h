@@ -134,6 +134,10 @@ int         crnn_profile_begin(crnn_model* m, int max_forwards);
 int         crnn_profile_num_stages(void);
 const char* crnn_profile_stage_name(int stage);
 int         crnn_profile_read(crnn_model* m, float* ms_out, int* forwards);
+/* same for crnn_backward (armed by the same crnn_profile_begin) */
+int         crnn_profile_bwd_num_stages(void);
+const char* crnn_profile_bwd_stage_name(int stage);
+int         crnn_profile_bwd_read(crnn_model* m, float* ms_out, int* backwards);
 
 /* Stand-alone bf16 GEMM test entry (tests only): D[M,Nc] f32 = A[M,K] * B[Nc,K]^T, bf16 in. */
 int     crnn_test_gemm_bf16(const void* A, const void* B, float* D, int M, int Nc, int K,

@@ -40,6 +40,9 @@ SIGNATURES = {
     "crnn_profile_num_stages": (c_int, []),
     "crnn_profile_stage_name": (c_char_p, [c_int]),
     "crnn_profile_read": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_int)]),
+    "crnn_profile_bwd_num_stages": (c_int, []),
+    "crnn_profile_bwd_stage_name": (c_char_p, [c_int]),
+    "crnn_profile_bwd_read": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_int)]),
     "crnn_model_set_training": (c_int, [c_void_p, c_int]),
     "crnn_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "crnn_clip_adam_step": (c_int, [c_void_p, c_float, c_float, c_int, c_float, c_float, c_void_p]),

@@ -92,6 +92,11 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   const int H1 = pl.H1, H2 = pl.H2, T = pl.T, sms = m->num_sms;
   const long long R = (long long)N * H2;
   auto G = [&](const std::string& n) { return m->grads + m->find(n)->offset; };
+  cudaEvent_t* ev = nullptr;
+  if (m->prof_on && m->prof_used_bwd < m->prof_slots) ev = &m->prof_events_bwd[(size_t)(m->prof_used_bwd++) * (kNumBwdStages + 1)];
+  int evi = 0;
+#define BMARK() do { if (ev) CUDA_TRY(cudaEventRecord(ev[evi++], st)); } while (0)
+  BMARK();
   CUDA_TRY(cudaMemsetAsync(m->grads, 0, (size_t)m->total * sizeof(float), st));
 
   // ------------------------------------------------------------------ 512 -> 64 projection (network.py:118-128)
@@ -108,6 +113,7 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
     p.Nc = 512; p.out = pl.d_lstm_out; p.ldo = 512;
     CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 4>(pl.tG_dl, m->tD_l, p, sms, st)));
   }
+  BMARK();
   // ------------------------------------------------------------------ BPTT through both directions
   {
     lstm_bwd::Params lp;
@@ -130,6 +136,7 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
     cfg.attrs = at; cfg.numAttrs = 1;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, lstm_bwd::lstm_bwd_kernel, pl.tG_dzstate, m->tD_h, lp));
   }
+  BMARK();
   {
     const std::string fw = "logits/bidirectional_rnn/fw/lstm_cell", bw = "logits/bidirectional_rnn/bw/lstm_cell";
     const long long dW = m->find(bw + "/weights")->offset - m->find(fw + "/weights")->offset;
@@ -158,6 +165,7 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
       CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 4>(pl.tG_dz, m->tD_x, p, sms, st)));
     }
   }
+  BMARK();
   // ------------------------------------------------------------------ conv5 (2x2 VALID)
   CRNN_TRY(launch_colsum_bf16(pl.d_a5, R, 512, G("conv5/biases"), 0, 0, st));
   for (int r = 0; r < 2; ++r) {
@@ -172,6 +180,7 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
     p.Nc = 1024; p.out = pl.d_a4b; p.ldo = 1024;
     CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 4>(pl.tG_da5, m->tD_c5, p, sms, st)));
   }
+  BMARK();
   // ------------------------------------------------------------------ conv4_2: pool3 + ReLU + batch-stat BN backward
   CUDA_TRY(cudaMemsetAsync(pl.bn_bwd_sums, 0, 2 * 2 * 512 * sizeof(double), st));
   const size_t P4 = (size_t)N * H2 * 4;
@@ -179,67 +188,84 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   CRNN_TRY(launch_bn_bwd_apply(pl.d_pre4b, pl.a4b_pre, pl.bn + 2048, m->P("conv4_2/conv4_2/gamma"), pl.bn_bwd_sums + 1024, (double)P4, P4,
                                512, pl.bn_bwd_coef, G("conv4_2/conv4_2/gamma"), G("conv4_2/conv4_2/beta"), st));
   CRNN_TRY(launch_colsum_bf16(pl.d_pre4b, (long long)P4, 512, G("conv4_2/biases"), 0, 0, st));
+  BMARK();
   {
     gemm_tn::Params p = tn_conv(N, H2, 4, 512, 512, G("conv4_2/weights"));
     p.num_n_tiles = 2;
     CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tA_c42, pl.tG_p4b, p, sms, st)));
   }
+  BMARK();
   {
     gemm::Params p = conv_params(N, H2, 4, 512, 512, 256, nullptr, pl.d_pre4a);
     CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_CONV_STORE, 4>(pl.tG_p4b, m->tD_c42, p, sms, st)));
   }
+  BMARK();
   // ------------------------------------------------------------------ conv4_1: ReLU + BN backward
   CRNN_TRY(launch_bn_bwd_reduce(false, pl.d_pre4a, pl.a4a_pre, pl.d_pre4a, pl.bn, pl.bn_bwd_sums, P4, 512, st));
   CRNN_TRY(launch_bn_bwd_apply(pl.d_pre4a, pl.a4a_pre, pl.bn, m->P("conv4_1/conv4_1/gamma"), pl.bn_bwd_sums, (double)P4, P4, 512,
                                pl.bn_bwd_coef, G("conv4_1/conv4_1/gamma"), G("conv4_1/conv4_1/beta"), st));
   CRNN_TRY(launch_colsum_bf16(pl.d_pre4a, (long long)P4, 512, G("conv4_1/biases"), 0, 0, st));
+  BMARK();
   {
     gemm_tn::Params p = tn_conv(N, H2, 4, 256, 512, G("conv4_1/weights"));
     p.num_n_tiles = 2;
     CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tA_c41, pl.tG_p4a, p, sms, st)));
   }
+  BMARK();
   {
     gemm::Params p = conv_params(N, H2, 4, 512, 256, 256, nullptr, pl.d_a3p);
     CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_CONV_STORE, 4>(pl.tG_p4a, m->tD_c41, p, sms, st)));
   }
+  BMARK();
   // ------------------------------------------------------------------ conv3_2: 1x2 pool + ReLU backward
   CRNN_TRY(launch_unpool_relu_bwd(2, pl.d_a3p, pl.a3p, pl.am3, pl.d_pre32, (size_t)N * H2 * 4, H2, 4, 256, st));
   CRNN_TRY(launch_colsum_bf16(pl.d_pre32, (long long)N * H2 * 8, 256, G("conv3_2/biases"), 0, 0, st));
+  BMARK();
   {
     gemm_tn::Params p = tn_conv(N, H2, 8, 256, 256, G("conv3_2/weights"));
     p.num_n_tiles = 1;
     CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tA_c32, pl.tG_p32, p, sms, st)));
   }
+  BMARK();
   {
     gemm::Params p = conv_params(N, H2, 8, 256, 256, 256, nullptr, pl.d_pre31);
     CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_CONV_STORE, 4>(pl.tG_p32, m->tD_c32, p, sms, st)));
   }
+  BMARK();
   // ------------------------------------------------------------------ conv3_1: ReLU backward
   CRNN_TRY(launch_relu_bwd(pl.d_pre31, pl.a3, (size_t)N * H2 * 8 * 256, st));
   CRNN_TRY(launch_colsum_bf16(pl.d_pre31, (long long)N * H2 * 8, 256, G("conv3_1/biases"), 0, 0, st));
+  BMARK();
   {
     gemm_tn::Params p = tn_conv(N, H2, 8, 128, 256, G("conv3_1/weights"));
     p.num_n_tiles = 1;
     CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tA_c31, pl.tG_p31, p, sms, st)));
   }
+  BMARK();
   {
     gemm::Params p = conv_params(N, H2, 8, 256, 128, 128, nullptr, pl.d_a2);
     CRNN_TRY((launch_gemm<128, gemm::A_CONV3, gemm::EPI_CONV_STORE, 6>(pl.tG_p31, m->tD_c31, p, sms, st)));
   }
+  BMARK();
   // ------------------------------------------------------------------ conv2: 2x2 pool + ReLU backward
   CRNN_TRY(launch_unpool_relu_bwd(4, pl.d_a2, pl.a2, pl.am2, pl.d_pre2, (size_t)N * H2 * 8, H2, 8, 128, st));
   CRNN_TRY(launch_colsum_bf16(pl.d_pre2, (long long)N * H1 * 16, 128, G("conv2/biases"), 0, 0, st));
+  BMARK();
   {
     gemm_tn::Params p = tn_conv(N, H1, 16, 64, 128, G("conv2/weights"));
     p.num_n_tiles = 1;
     CRNN_TRY((launch_gemm_tn<128, gemm_tn::TN_CONV, 6>(pl.tA_c2, pl.tG_p2, p, sms, st)));
   }
+  BMARK();
   {
     gemm::Params p = conv_params(N, H1, 16, 128, 64, 64, nullptr, pl.d_a1);
     CRNN_TRY((launch_gemm<64, gemm::A_CONV3, gemm::EPI_CONV_STORE, 8>(pl.tG_p2, m->tD_c2, p, sms, st)));
   }
+  BMARK();
   // ------------------------------------------------------------------ conv1 (K = 9, SIMT): pool1 + ReLU folded in
   CRNN_TRY(launch_conv1_wgrad(pl.d_a1, pl.a1, pl.am1, data, G("conv1/weights"), G("conv1/biases"), N, W, st));
+  BMARK();
+#undef BMARK
   return CRNN_OK;
 }
 
@@ -297,4 +323,17 @@ extern "C" int crnn_test_gemm_tn_bf16(const void* A, const void* B, float* D, in
   if (block_n == 128) return launch_gemm_tn<128, gemm_tn::TN_PLAIN, 6>(ta, tb, p, sms, st);
   if (block_n == 256) return launch_gemm_tn<256, gemm_tn::TN_PLAIN, 4>(ta, tb, p, sms, st);
   return crnn_fail(CRNN_INVALID_VALUE, "test_gemm_tn: block_n must be 64/128/256");
+}
+
+extern "C" int crnn_profile_bwd_num_stages(void) { return kNumBwdStages; }
+extern "C" const char* crnn_profile_bwd_stage_name(int i) { return (i >= 0 && i < kNumBwdStages) ? kBwdStageNames[i] : ""; }
+extern "C" int crnn_profile_bwd_read(crnn_model* m, float* ms_out, int* backwards) {
+  if (!m || !ms_out || !backwards) return crnn_fail(CRNN_INVALID_VALUE, "profile_bwd_read: null");
+  *backwards = m->prof_used_bwd;
+  for (int f = 0; f < m->prof_used_bwd; ++f) {
+    cudaEvent_t* ev = &m->prof_events_bwd[(size_t)f * (kNumBwdStages + 1)];
+    CUDA_TRY(cudaEventSynchronize(ev[kNumBwdStages]));
+    for (int s = 0; s < kNumBwdStages; ++s) CUDA_TRY(cudaEventElapsedTime(ms_out + (size_t)f * kNumBwdStages + s, ev[s], ev[s + 1]));
+  }
+  return CRNN_OK;
 }

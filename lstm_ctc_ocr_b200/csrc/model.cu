@@ -176,6 +176,7 @@ extern "C" int crnn_model_destroy(crnn_model* m) {
   if (m->wblock) cudaFree(m->wblock);
   if (m->wblock_bwd) cudaFree(m->wblock_bwd);
   for (auto e : m->prof_events) cudaEventDestroy(e);
+  for (auto e : m->prof_events_bwd) cudaEventDestroy(e);
   delete m;
   return CRNN_OK;
 }
@@ -508,7 +509,13 @@ extern "C" int crnn_profile_begin(crnn_model* m, int max_forwards) {
     CUDA_TRY(cudaEventCreate(&e));
     m->prof_events.push_back(e);
   }
-  m->prof_slots = max_forwards; m->prof_used = 0; m->prof_on = max_forwards > 0;
+  const size_t need_b = (size_t)max_forwards * (kNumBwdStages + 1);
+  while (m->prof_events_bwd.size() < need_b) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreate(&e));
+    m->prof_events_bwd.push_back(e);
+  }
+  m->prof_slots = max_forwards; m->prof_used = 0; m->prof_used_bwd = 0; m->prof_on = max_forwards > 0;
   return CRNN_OK;
 }
 extern "C" int crnn_profile_num_stages(void) { return kNumStages; }

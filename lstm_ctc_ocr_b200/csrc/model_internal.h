@@ -31,6 +31,11 @@ static const ConvSpec kConvs[7] = {   // lib/networks/LSTM_train.py:24-34
 static const char* kStageNames[] = {"conv1_pool1", "conv2_pool2", "conv3_1", "conv3_2_pool", "conv4_1_gemm", "bn4_1_apply",
                                     "conv4_2_gemm", "bn4_2_apply_pool3", "conv5", "lstm_xproj", "lstm_recurrence", "logits"};
 static const int kNumStages = 12;
+static const char* kBwdStageNames[] = {"zero+logits_bwd", "lstm_bptt", "lstm_wgrad+dx", "conv5_bwd", "bn4_2_bwd", "conv4_2_wgrad",
+                                       "conv4_2_dgrad", "bn4_1_bwd", "conv4_1_wgrad", "conv4_1_dgrad", "conv3_2_bwd_elem", "conv3_2_wgrad",
+                                       "conv3_2_dgrad", "conv3_1_bwd_elem", "conv3_1_wgrad", "conv3_1_dgrad", "conv2_bwd_elem", "conv2_wgrad",
+                                       "conv2_dgrad", "conv1_wgrad"};
+static const int kNumBwdStages = 20;
 
 struct Plan {
   int N = 0, W = 0, H1 = 0, H2 = 0, T = 0, Npad = 0;
@@ -81,6 +86,8 @@ struct crnn_model {
   std::vector<cudaEvent_t> prof_events;   // [slots][kNumStages + 1]
   int prof_slots = 0, prof_used = 0;
   bool prof_on = false;
+  std::vector<cudaEvent_t> prof_events_bwd;   // [slots][kNumBwdStages + 1]
+  int prof_used_bwd = 0;
 
   const TensorInfo* find(const std::string& n) const {
     for (auto& t : tensors) if (t.name == n) return &t;
