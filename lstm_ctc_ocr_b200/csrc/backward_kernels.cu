@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
                                                           float* __restrict__ out, int perm_upc, long long dir_stride) {
   // block handles 256 columns (8 per thread x 32 lanes) x a strided set of rows (8 warps)
   const int cb = blockIdx.y * 256 + (threadIdx.x & 31) * 8;
-  if (cb >= C) return;
+  const bool okc = cb < C;
   float part[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) part[i] = 0.f;
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long long rr = r + u * stride;
-      q[u] = (rr < R) ? __ldg(reinterpret_cast<const uint4*>(src + rr * C + cb)) : make_uint4(0u, 0u, 0u, 0u);
+      q[u] = (okc && rr < R) ? __ldg(reinterpret_cast<const uint4*>(src + rr * C + cb)) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -72,9 +72,19 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
       for (int i = 0; i < 8; ++i) part[i] += v[i];
     }
   }
+  // block reduction over the 8 warps (same columns, different rows), then ONE atomic per column per block:
+  // same-address f32 atomics from thousands of warps serialise in L2 and used to dominate this kernel
+  __shared__ float red[8][256];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    int c = cb + i;
+  for (int i = 0; i < 8; ++i) red[w][l * 8 + i] = part[i];
+  __syncthreads();
+  const int cl = threadIdx.x;                       // one column per thread
+  const int c = blockIdx.y * 256 + cl;
+  if (c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][cl];
     float* dst;
     if (perm_upc) {
       const int dir = c >> 10, pc = c & 1023;
@@ -83,7 +93,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
     } else {
       dst = out + c;
     }
-    atomicAdd(dst, part[i]);
+    atomicAdd(dst, t);
   }
 }
 
@@ -390,14 +400,14 @@ int launch_dlogits_rows(const float* dlogits, __nv_bfloat16* rows, float* dbias,
   LAUNCH_CHECK();
 }
 int launch_colsum_bf16(const __nv_bfloat16* src, long long R, int C, float* out, int perm_upc, long long dir_stride, cudaStream_t st) {
-  dim3 grid(592, (C + 255) / 256);
+  dim3 grid(296, (C + 255) / 256);
   colsum_bf16_kernel<<<grid, 256, 0, st>>>(src, R, C, out, perm_upc, dir_stride);
   LAUNCH_CHECK();
 }
 int launch_bn_bwd_reduce(bool pool, const __nv_bfloat16* dout, const __nv_bfloat16* x_pre, __nv_bfloat16* dy, const float* bn,
                          double* sums, size_t out_positions, int C, cudaStream_t st) {
-  if (pool) bn_bwd_reduce_kernel<true><<<1184, 256, 0, st>>>((const uint4*)dout, (const uint4*)x_pre, (uint4*)dy, bn, sums, out_positions, C);
-  else bn_bwd_reduce_kernel<false><<<1184, 256, 0, st>>>((const uint4*)dout, (const uint4*)x_pre, (uint4*)dy, bn, sums, out_positions, C);
+  if (pool) bn_bwd_reduce_kernel<true><<<592, 256, 0, st>>>((const uint4*)dout, (const uint4*)x_pre, (uint4*)dy, bn, sums, out_positions, C);
+  else bn_bwd_reduce_kernel<false><<<592, 256, 0, st>>>((const uint4*)dout, (const uint4*)x_pre, (uint4*)dy, bn, sums, out_positions, C);
   LAUNCH_CHECK();
 }
 int launch_bn_bwd_apply(__nv_bfloat16* dy, const __nv_bfloat16* x_pre, const float* bn, const float* gamma, const double* sums,
