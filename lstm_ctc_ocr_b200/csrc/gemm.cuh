@@ -111,6 +111,328 @@ struct Smem {
   static constexpr int BYTES = BAR_OFFSET + 256 + 1024;   // barriers + alignment slack
 };
 
+// Per-tile epilogue shared by the 1-CTA and 2-CTA kernels: thread (q, lane) owns accumulator row q*32+lane of the 128-row
+// tile held in its CTA's TMEM at `tbase` (lane quadrant and accumulator stage already applied).
+template <int BLOCK_N, int EPI>
+__device__ __forceinline__ void run_epilogue(const Params& p, const uint32_t tbase, const int m_blk, const int n_blk, const int q,
+                                             const int lane) {
+  const int row = q * 32 + lane;
+  const int col0 = n_blk * BLOCK_N;
+
+  // ---- conv row geometry (one sub-box of 32 positions per warp)
+  int n_img = 0, h = 0, w = 0;
+  bool valid = true;
+  if (EPI == EPI_RELU || EPI == EPI_RELU_POOL22 || EPI == EPI_RELU_POOL12 || EPI == EPI_STATS || EPI == EPI_CONV_STORE ||
+      EPI == EPI_RELU_POOL22_T || EPI == EPI_RELU_POOL12_T) {
+    const int g = m_blk * 4 + q;
+    n_img = g / p.sb_per_img;
+    const int hb = g - n_img * p.sb_per_img;
+    const int hl = lane / p.Wd;
+    w = lane - hl * p.Wd;
+    h = hb * p.bh + hl;
+    valid = (n_img < p.Nimg) && (h < p.H);
+  }
+
+  if (EPI == EPI_F32) {
+    const int grow = m_blk * BLOCK_M + row;
+    float* out = reinterpret_cast<float*>(p.out) + (size_t)grow * p.Nc + col0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(tbase + c0, v);
+      ptx::tmem_ld_wait();
+      if (grow < p.M) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<uint4*>(out + c0 + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    }
+  } else if (EPI == EPI_BIAS_BF16 || EPI == EPI_XPROJ) {
+    const int grow = m_blk * BLOCK_M + row;
+    int drow = grow;
+    if (EPI == EPI_XPROJ && col0 >= 1024 && grow < p.M) {
+      // tf.reverse_sequence(len) on the backward direction's input, done once at write time
+      const int n = grow / p.H, t = grow - n * p.H;
+      const int len = min(max(__ldg(p.seq_len + n), 0), p.T);
+      if (t < len) drow = n * p.H + (len - 1 - t);
+    }
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)drow * p.ldo + col0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(tbase + c0, v);
+      ptx::tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        pk[i / 2] = ptx::pack_bf16x2(__uint_as_float(v[i]) + b.x, __uint_as_float(v[i + 1]) + b.y);
+        pk[i / 2 + 1] = ptx::pack_bf16x2(__uint_as_float(v[i + 2]) + b.z, __uint_as_float(v[i + 3]) + b.w);
+      }
+      if (grow < p.M) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<uint4*>(out + c0 + 2 * i) = make_uint4(pk[i], pk[i + 1], pk[i + 2], pk[i + 3]);
+      }
+    }
+  } else if (EPI == EPI_LOGITS) {
+    const int grow = m_blk * BLOCK_M + row;
+    const int n = grow / p.H, t = grow - n * p.H;
+    const bool ok = (grow < p.M) && (t < p.T);
+    float* out = reinterpret_cast<float*>(p.out) + ((size_t)t * p.Nimg + n) * p.Nc + col0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(tbase + c0, v);
+      ptx::tmem_ld_wait();
+      if (ok) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c0 + i));
+          *reinterpret_cast<float4*>(out + c0 + i) =
+              make_float4(__uint_as_float(v[i]) + b.x, __uint_as_float(v[i + 1]) + b.y,
+                          __uint_as_float(v[i + 2]) + b.z, __uint_as_float(v[i + 3]) + b.w);
+        }
+      }
+    }
+  } else if (EPI == EPI_RELU || EPI == EPI_RELU_POOL22 || EPI == EPI_RELU_POOL12) {
+    __nv_bfloat16* outb = reinterpret_cast<__nv_bfloat16*>(p.out);
+    size_t off;
+    if (EPI == EPI_RELU) off = (((size_t)n_img * p.H + h) * p.Wd + w) * p.Nc;
+    else if (EPI == EPI_RELU_POOL22) off = (((size_t)n_img * (p.H >> 1) + (h >> 1)) * (p.Wd >> 1) + (w >> 1)) * p.Nc;
+    else off = (((size_t)n_img * p.H + h) * (p.Wd >> 1) + (w >> 1)) * p.Nc;
+    __nv_bfloat16* out = outb + off + col0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(tbase + c0, v);
+      ptx::tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c0 + i));
+        pk[i / 2] = ptx::pack_bf16x2(fmaxf(__uint_as_float(v[i]) + b.x, 0.f), fmaxf(__uint_as_float(v[i + 1]) + b.y, 0.f));
+        pk[i / 2 + 1] = ptx::pack_bf16x2(fmaxf(__uint_as_float(v[i + 2]) + b.z, 0.f), fmaxf(__uint_as_float(v[i + 3]) + b.w, 0.f));
+      }
+      if (EPI == EPI_RELU) {
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            *reinterpret_cast<uint4*>(out + c0 + 2 * i) = make_uint4(pk[i], pk[i + 1], pk[i + 2], pk[i + 3]);
+        }
+      } else if (EPI == EPI_RELU_POOL22) {
+        // lane = hl*16 + w : partners lane^1 (w pair) and lane^16 (h pair); rounding to bf16 is monotonic,
+        // so max after packing == packing after max
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          pk[i] = ptx::hmax2_bf16(pk[i], __shfl_xor_sync(0xffffffffu, pk[i], 1));
+          pk[i] = ptx::hmax2_bf16(pk[i], __shfl_xor_sync(0xffffffffu, pk[i], 16));
+        }
+        const int sub = (lane & 1) | ((lane >> 3) & 2);     // which quarter of the 32 columns this lane stores
+        uint4 o;
+        o.x = sub == 0 ? pk[0] : sub == 1 ? pk[4] : sub == 2 ? pk[8] : pk[12];
+        o.y = sub == 0 ? pk[1] : sub == 1 ? pk[5] : sub == 2 ? pk[9] : pk[13];
+        o.z = sub == 0 ? pk[2] : sub == 1 ? pk[6] : sub == 2 ? pk[10] : pk[14];
+        o.w = sub == 0 ? pk[3] : sub == 1 ? pk[7] : sub == 2 ? pk[11] : pk[15];
+        if (valid) *reinterpret_cast<uint4*>(out + c0 + 8 * sub) = o;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = ptx::hmax2_bf16(pk[i], __shfl_xor_sync(0xffffffffu, pk[i], 1));
+        const int sub = lane & 1;
+        uint4 o0, o1;
+        o0.x = sub ? pk[8] : pk[0];  o0.y = sub ? pk[9] : pk[1];  o0.z = sub ? pk[10] : pk[2]; o0.w = sub ? pk[11] : pk[3];
+        o1.x = sub ? pk[12] : pk[4]; o1.y = sub ? pk[13] : pk[5]; o1.z = sub ? pk[14] : pk[6]; o1.w = sub ? pk[15] : pk[7];
+        if (valid) {
+          *reinterpret_cast<uint4*>(out + c0 + 16 * sub) = o0;
+          *reinterpret_cast<uint4*>(out + c0 + 16 * sub + 8) = o1;
+        }
+      }
+    }
+  } else if (EPI == EPI_CONV_STORE) {
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (((size_t)n_img * p.H + h) * p.Wd + w) * p.Nc + col0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(tbase + c0, v);
+      ptx::tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8)
+          *reinterpret_cast<uint4*>(out + c0 + i) =
+              make_uint4(ptx::pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
+                         ptx::pack_bf16x2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])),
+                         ptx::pack_bf16x2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])),
+                         ptx::pack_bf16x2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
+      }
+    }
+  } else if (EPI == EPI_RELU_POOL22_T || EPI == EPI_RELU_POOL12_T) {
+    // Training variants: max over the pooling window carried as an integer key
+    //   key = (bf16 bits of relu(x) << 2) | (3 - window_index)
+    // post-ReLU bf16 bit patterns are monotone as unsigned integers, so max(key) picks the largest value and, among
+    // equal values, the FIRST window position (row-major (dy,dx), the tie-break of TF/torch max-pool gradients).
+    constexpr bool P22 = (EPI == EPI_RELU_POOL22_T);
+    size_t off;
+    if (P22) off = (((size_t)n_img * (p.H >> 1) + (h >> 1)) * (p.Wd >> 1) + (w >> 1)) * p.Nc;
+    else off = (((size_t)n_img * p.H + h) * (p.Wd >> 1) + (w >> 1)) * p.Nc;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + off + col0;
+    uint8_t* amx = p.argmax + off + col0;
+    const uint32_t kidx = P22 ? (uint32_t)((((lane >> 4) & 1) << 1) | (lane & 1)) : (uint32_t)(lane & 1);
+    const uint32_t kinv = (P22 ? 3u : 1u) - kidx;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(tbase + c0, v);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c0 + i));
+        const uint32_t p0 = ptx::pack_bf16x2(fmaxf(__uint_as_float(v[i]) + b.x, 0.f), fmaxf(__uint_as_float(v[i + 1]) + b.y, 0.f));
+        const uint32_t p1 = ptx::pack_bf16x2(fmaxf(__uint_as_float(v[i + 2]) + b.z, 0.f), fmaxf(__uint_as_float(v[i + 3]) + b.w, 0.f));
+        v[i] = ((p0 & 0xFFFFu) << 2) | kinv;
+        v[i + 1] = ((p0 >> 16) << 2) | kinv;
+        v[i + 2] = ((p1 & 0xFFFFu) << 2) | kinv;
+        v[i + 3] = ((p1 >> 16) << 2) | kinv;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        v[i] = max(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
+        if (P22) v[i] = max(v[i], __shfl_xor_sync(0xffffffffu, v[i], 16));
+      }
+      // each lane of the window stores its share of the 32 columns: 8 (2x2 window) or 16 (1x2 window)
+      constexpr int NS = P22 ? 4 : 2, PER = 32 / NS;
+      const int sub = P22 ? ((lane & 1) | ((lane >> 3) & 2)) : (lane & 1);
+      uint32_t sel[PER];
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        uint32_t x = v[i];
+#pragma unroll
+        for (int j = 1; j < NS; ++j) x = (sub == j) ? v[j * PER + i] : x;
+        sel[i] = x;
+      }
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < PER; i += 8) {
+          uint4 o;
+          o.x = ((sel[i] >> 2) & 0xFFFFu) | ((sel[i + 1] >> 2) << 16);
+          o.y = ((sel[i + 2] >> 2) & 0xFFFFu) | ((sel[i + 3] >> 2) << 16);
+          o.z = ((sel[i + 4] >> 2) & 0xFFFFu) | ((sel[i + 5] >> 2) << 16);
+          o.w = ((sel[i + 6] >> 2) & 0xFFFFu) | ((sel[i + 7] >> 2) << 16);
+          *reinterpret_cast<uint4*>(out + c0 + sub * PER + i) = o;
+          const uint32_t km = P22 ? 3u : 1u;
+          uint2 a;
+          a.x = (km - (sel[i] & km)) | ((km - (sel[i + 1] & km)) << 8) | ((km - (sel[i + 2] & km)) << 16) | ((km - (sel[i + 3] & km)) << 24);
+          a.y = (km - (sel[i + 4] & km)) | ((km - (sel[i + 5] & km)) << 8) | ((km - (sel[i + 6] & km)) << 16) | ((km - (sel[i + 7] & km)) << 24);
+          *reinterpret_cast<uint2*>(amx + c0 + sub * PER + i) = a;
+        }
+      }
+    }
+  } else if (EPI == EPI_STATS) {
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (((size_t)n_img * p.H + h) * p.Wd + w) * p.Nc + col0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(tbase + c0, v);
+      ptx::tmem_ld_wait();
+      float f[32], f2[32];
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c0 + i));
+        f[i] = __uint_as_float(v[i]) + b.x;
+        f[i + 1] = __uint_as_float(v[i + 1]) + b.y;
+        f[i + 2] = __uint_as_float(v[i + 2]) + b.z;
+        f[i + 3] = __uint_as_float(v[i + 3]) + b.w;
+        pk[i / 2] = ptx::pack_bf16x2(f[i], f[i + 1]);
+        pk[i / 2 + 1] = ptx::pack_bf16x2(f[i + 2], f[i + 3]);
+      }
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<uint4*>(out + c0 + 2 * i) = make_uint4(pk[i], pk[i + 1], pk[i + 2], pk[i + 3]);
+      }
+      // statistics of the values the next layer will actually read (bf16-rounded), masked to valid rows
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float a = valid ? ptx::bf16_lo(pk[i]) : 0.f, b = valid ? ptx::bf16_hi(pk[i]) : 0.f;
+        f[2 * i] = a; f[2 * i + 1] = b;
+        f2[2 * i] = a * a; f2[2 * i + 1] = b * b;
+      }
+      const float s1 = warp_colsum32(f, lane);
+      const float s2 = warp_colsum32(f2, lane);
+      atomicAdd(p.stats + col0 + c0 + lane, (double)s1);
+      atomicAdd(p.stats + p.Nc + col0 + c0 + lane, (double)s2);
+    }
+  } else if (EPI == EPI_LSTM) {
+    // row = sample within the direction-stacked batch; tile columns = [i(64) j(64) f(64) o(64)] of 64 units
+    const int grow = m_blk * BLOCK_M + row;
+    const int dir = (m_blk >= p.m_tiles_per_dir) ? 1 : 0;
+    const int n = grow - dir * p.Npad;
+    const bool okn = n < p.Nimg;
+    const int len = okn ? min(max(__ldg(p.seq_len + n), 0), p.T) : 0;
+    const bool active = p.step < len;
+    const int t = active ? (dir ? (len - 1 - p.step) : p.step) : p.step;
+    const size_t rt = (size_t)n * p.H + t;
+    const __nv_bfloat16* xp = p.xproj + rt * 2048 + dir * 1024 + n_blk * 256;
+    float* cst = p.c_state + ((size_t)dir * p.Npad + n) * 256 + n_blk * 64;
+    __nv_bfloat16* hn = p.h_next + ((size_t)dir * p.Npad + n) * 256 + n_blk * 64;
+    __nv_bfloat16* lo = p.lstm_out + rt * 512 + dir * 256 + n_blk * 64;
+#pragma unroll 1
+    for (int u0 = 0; u0 < 64; u0 += 16) {
+      uint32_t gi[16], gj[16], gf[16], go[16];
+      ptx::tmem_ld_32x32b_x16(tbase + u0, gi);
+      ptx::tmem_ld_32x32b_x16(tbase + 64 + u0, gj);
+      ptx::tmem_ld_32x32b_x16(tbase + 128 + u0, gf);
+      ptx::tmem_ld_32x32b_x16(tbase + 192 + u0, go);
+      ptx::tmem_ld_wait();
+      uint32_t hp[8];
+      if (active) {
+        uint4 xi[2], xj[2], xf[2], xo[2];
+        float4 cp[4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          xi[i] = __ldg(reinterpret_cast<const uint4*>(xp + u0) + i);
+          xj[i] = __ldg(reinterpret_cast<const uint4*>(xp + 64 + u0) + i);
+          xf[i] = __ldg(reinterpret_cast<const uint4*>(xp + 128 + u0) + i);
+          xo[i] = __ldg(reinterpret_cast<const uint4*>(xp + 192 + u0) + i);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cp[i] = *(reinterpret_cast<const float4*>(cst + u0) + i);
+        const uint32_t* xiw = reinterpret_cast<const uint32_t*>(xi);
+        const uint32_t* xjw = reinterpret_cast<const uint32_t*>(xj);
+        const uint32_t* xfw = reinterpret_cast<const uint32_t*>(xf);
+        const uint32_t* xow = reinterpret_cast<const uint32_t*>(xo);
+        float* cpf = reinterpret_cast<float*>(cp);
+        float hv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float zi = __uint_as_float(gi[i]) + ((i & 1) ? ptx::bf16_hi(xiw[i >> 1]) : ptx::bf16_lo(xiw[i >> 1]));
+          const float zj = __uint_as_float(gj[i]) + ((i & 1) ? ptx::bf16_hi(xjw[i >> 1]) : ptx::bf16_lo(xjw[i >> 1]));
+          const float zf = __uint_as_float(gf[i]) + ((i & 1) ? ptx::bf16_hi(xfw[i >> 1]) : ptx::bf16_lo(xfw[i >> 1]));
+          const float zo = __uint_as_float(go[i]) + ((i & 1) ? ptx::bf16_hi(xow[i >> 1]) : ptx::bf16_lo(xow[i >> 1]));
+          // forget_bias (+1.0) is folded into the projected bias at weight-prep time
+          const float c = ptx::fast_sigmoid(zf) * cpf[i] + ptx::fast_sigmoid(zi) * ptx::fast_tanh(zj);
+          cpf[i] = c;
+          hv[i] = ptx::fast_sigmoid(zo) * ptx::fast_tanh(c);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) *(reinterpret_cast<float4*>(cst + u0) + i) = cp[i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hp[i] = ptx::pack_bf16x2(hv[2 * i], hv[2 * i + 1]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hp[i] = 0u;    // zero output past sequence_length; state no longer used
+      }
+      if (okn) {
+        *reinterpret_cast<uint4*>(hn + u0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        *reinterpret_cast<uint4*>(hn + u0 + 8) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+        *reinterpret_cast<uint4*>(lo + u0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        *reinterpret_cast<uint4*>(lo + u0 + 8) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+      }
+    }
+  }
+
+}
+
 template <int BLOCK_N, int AMODE, int EPI, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
@@ -220,7 +542,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else {
     // ===================== epilogue warps =====================
     const int q = warp_idx & 3;                      // TMEM lane quadrant accessible to this warp
-    const int row = q * 32 + lane;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
@@ -229,320 +550,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
-      const int col0 = n_blk * BLOCK_N;
-
-      // ---- conv row geometry (one sub-box of 32 positions per warp)
-      int n_img = 0, h = 0, w = 0;
-      bool valid = true;
-      if (EPI == EPI_RELU || EPI == EPI_RELU_POOL22 || EPI == EPI_RELU_POOL12 || EPI == EPI_STATS || EPI == EPI_CONV_STORE ||
-          EPI == EPI_RELU_POOL22_T || EPI == EPI_RELU_POOL12_T) {
-        const int g = m_blk * 4 + q;
-        n_img = g / p.sb_per_img;
-        const int hb = g - n_img * p.sb_per_img;
-        const int hl = lane / p.Wd;
-        w = lane - hl * p.Wd;
-        h = hb * p.bh + hl;
-        valid = (n_img < p.Nimg) && (h < p.H);
-      }
-
-      if (EPI == EPI_F32) {
-        const int grow = m_blk * BLOCK_M + row;
-        float* out = reinterpret_cast<float*>(p.out) + (size_t)grow * p.Nc + col0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(tbase + c0, v);
-          ptx::tmem_ld_wait();
-          if (grow < p.M) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<uint4*>(out + c0 + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          }
-        }
-      } else if (EPI == EPI_BIAS_BF16 || EPI == EPI_XPROJ) {
-        const int grow = m_blk * BLOCK_M + row;
-        int drow = grow;
-        if (EPI == EPI_XPROJ && col0 >= 1024 && grow < p.M) {
-          // tf.reverse_sequence(len) on the backward direction's input, done once at write time
-          const int n = grow / p.H, t = grow - n * p.H;
-          const int len = min(max(__ldg(p.seq_len + n), 0), p.T);
-          if (t < len) drow = n * p.H + (len - 1 - t);
-        }
-        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)drow * p.ldo + col0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(tbase + c0, v);
-          ptx::tmem_ld_wait();
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            pk[i / 2] = ptx::pack_bf16x2(__uint_as_float(v[i]) + b.x, __uint_as_float(v[i + 1]) + b.y);
-            pk[i / 2 + 1] = ptx::pack_bf16x2(__uint_as_float(v[i + 2]) + b.z, __uint_as_float(v[i + 3]) + b.w);
-          }
-          if (grow < p.M) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4)
-              *reinterpret_cast<uint4*>(out + c0 + 2 * i) = make_uint4(pk[i], pk[i + 1], pk[i + 2], pk[i + 3]);
-          }
-        }
-      } else if (EPI == EPI_LOGITS) {
-        const int grow = m_blk * BLOCK_M + row;
-        const int n = grow / p.H, t = grow - n * p.H;
-        const bool ok = (grow < p.M) && (t < p.T);
-        float* out = reinterpret_cast<float*>(p.out) + ((size_t)t * p.Nimg + n) * p.Nc + col0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(tbase + c0, v);
-          ptx::tmem_ld_wait();
-          if (ok) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c0 + i));
-              *reinterpret_cast<float4*>(out + c0 + i) =
-                  make_float4(__uint_as_float(v[i]) + b.x, __uint_as_float(v[i + 1]) + b.y,
-                              __uint_as_float(v[i + 2]) + b.z, __uint_as_float(v[i + 3]) + b.w);
-            }
-          }
-        }
-      } else if (EPI == EPI_RELU || EPI == EPI_RELU_POOL22 || EPI == EPI_RELU_POOL12) {
-        __nv_bfloat16* outb = reinterpret_cast<__nv_bfloat16*>(p.out);
-        size_t off;
-        if (EPI == EPI_RELU) off = (((size_t)n_img * p.H + h) * p.Wd + w) * p.Nc;
-        else if (EPI == EPI_RELU_POOL22) off = (((size_t)n_img * (p.H >> 1) + (h >> 1)) * (p.Wd >> 1) + (w >> 1)) * p.Nc;
-        else off = (((size_t)n_img * p.H + h) * (p.Wd >> 1) + (w >> 1)) * p.Nc;
-        __nv_bfloat16* out = outb + off + col0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(tbase + c0, v);
-          ptx::tmem_ld_wait();
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c0 + i));
-            pk[i / 2] = ptx::pack_bf16x2(fmaxf(__uint_as_float(v[i]) + b.x, 0.f), fmaxf(__uint_as_float(v[i + 1]) + b.y, 0.f));
-            pk[i / 2 + 1] = ptx::pack_bf16x2(fmaxf(__uint_as_float(v[i + 2]) + b.z, 0.f), fmaxf(__uint_as_float(v[i + 3]) + b.w, 0.f));
-          }
-          if (EPI == EPI_RELU) {
-            if (valid) {
-#pragma unroll
-              for (int i = 0; i < 16; i += 4)
-                *reinterpret_cast<uint4*>(out + c0 + 2 * i) = make_uint4(pk[i], pk[i + 1], pk[i + 2], pk[i + 3]);
-            }
-          } else if (EPI == EPI_RELU_POOL22) {
-            // lane = hl*16 + w : partners lane^1 (w pair) and lane^16 (h pair); rounding to bf16 is monotonic,
-            // so max after packing == packing after max
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              pk[i] = ptx::hmax2_bf16(pk[i], __shfl_xor_sync(0xffffffffu, pk[i], 1));
-              pk[i] = ptx::hmax2_bf16(pk[i], __shfl_xor_sync(0xffffffffu, pk[i], 16));
-            }
-            const int sub = (lane & 1) | ((lane >> 3) & 2);     // which quarter of the 32 columns this lane stores
-            uint4 o;
-            o.x = sub == 0 ? pk[0] : sub == 1 ? pk[4] : sub == 2 ? pk[8] : pk[12];
-            o.y = sub == 0 ? pk[1] : sub == 1 ? pk[5] : sub == 2 ? pk[9] : pk[13];
-            o.z = sub == 0 ? pk[2] : sub == 1 ? pk[6] : sub == 2 ? pk[10] : pk[14];
-            o.w = sub == 0 ? pk[3] : sub == 1 ? pk[7] : sub == 2 ? pk[11] : pk[15];
-            if (valid) *reinterpret_cast<uint4*>(out + c0 + 8 * sub) = o;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pk[i] = ptx::hmax2_bf16(pk[i], __shfl_xor_sync(0xffffffffu, pk[i], 1));
-            const int sub = lane & 1;
-            uint4 o0, o1;
-            o0.x = sub ? pk[8] : pk[0];  o0.y = sub ? pk[9] : pk[1];  o0.z = sub ? pk[10] : pk[2]; o0.w = sub ? pk[11] : pk[3];
-            o1.x = sub ? pk[12] : pk[4]; o1.y = sub ? pk[13] : pk[5]; o1.z = sub ? pk[14] : pk[6]; o1.w = sub ? pk[15] : pk[7];
-            if (valid) {
-              *reinterpret_cast<uint4*>(out + c0 + 16 * sub) = o0;
-              *reinterpret_cast<uint4*>(out + c0 + 16 * sub + 8) = o1;
-            }
-          }
-        }
-      } else if (EPI == EPI_CONV_STORE) {
-        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (((size_t)n_img * p.H + h) * p.Wd + w) * p.Nc + col0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(tbase + c0, v);
-          ptx::tmem_ld_wait();
-          if (valid) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 8)
-              *reinterpret_cast<uint4*>(out + c0 + i) =
-                  make_uint4(ptx::pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
-                             ptx::pack_bf16x2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])),
-                             ptx::pack_bf16x2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])),
-                             ptx::pack_bf16x2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
-          }
-        }
-      } else if (EPI == EPI_RELU_POOL22_T || EPI == EPI_RELU_POOL12_T) {
-        // Training variants: max over the pooling window carried as an integer key
-        //   key = (bf16 bits of relu(x) << 2) | (3 - window_index)
-        // post-ReLU bf16 bit patterns are monotone as unsigned integers, so max(key) picks the largest value and, among
-        // equal values, the FIRST window position (row-major (dy,dx), the tie-break of TF/torch max-pool gradients).
-        constexpr bool P22 = (EPI == EPI_RELU_POOL22_T);
-        size_t off;
-        if (P22) off = (((size_t)n_img * (p.H >> 1) + (h >> 1)) * (p.Wd >> 1) + (w >> 1)) * p.Nc;
-        else off = (((size_t)n_img * p.H + h) * (p.Wd >> 1) + (w >> 1)) * p.Nc;
-        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + off + col0;
-        uint8_t* amx = p.argmax + off + col0;
-        const uint32_t kidx = P22 ? (uint32_t)((((lane >> 4) & 1) << 1) | (lane & 1)) : (uint32_t)(lane & 1);
-        const uint32_t kinv = (P22 ? 3u : 1u) - kidx;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(tbase + c0, v);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c0 + i));
-            const uint32_t p0 = ptx::pack_bf16x2(fmaxf(__uint_as_float(v[i]) + b.x, 0.f), fmaxf(__uint_as_float(v[i + 1]) + b.y, 0.f));
-            const uint32_t p1 = ptx::pack_bf16x2(fmaxf(__uint_as_float(v[i + 2]) + b.z, 0.f), fmaxf(__uint_as_float(v[i + 3]) + b.w, 0.f));
-            v[i] = ((p0 & 0xFFFFu) << 2) | kinv;
-            v[i + 1] = ((p0 >> 16) << 2) | kinv;
-            v[i + 2] = ((p1 & 0xFFFFu) << 2) | kinv;
-            v[i + 3] = ((p1 >> 16) << 2) | kinv;
-          }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            v[i] = max(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
-            if (P22) v[i] = max(v[i], __shfl_xor_sync(0xffffffffu, v[i], 16));
-          }
-          // each lane of the window stores its share of the 32 columns: 8 (2x2 window) or 16 (1x2 window)
-          constexpr int NS = P22 ? 4 : 2, PER = 32 / NS;
-          const int sub = P22 ? ((lane & 1) | ((lane >> 3) & 2)) : (lane & 1);
-          uint32_t sel[PER];
-#pragma unroll
-          for (int i = 0; i < PER; ++i) {
-            uint32_t x = v[i];
-#pragma unroll
-            for (int j = 1; j < NS; ++j) x = (sub == j) ? v[j * PER + i] : x;
-            sel[i] = x;
-          }
-          if (valid) {
-#pragma unroll
-            for (int i = 0; i < PER; i += 8) {
-              uint4 o;
-              o.x = ((sel[i] >> 2) & 0xFFFFu) | ((sel[i + 1] >> 2) << 16);
-              o.y = ((sel[i + 2] >> 2) & 0xFFFFu) | ((sel[i + 3] >> 2) << 16);
-              o.z = ((sel[i + 4] >> 2) & 0xFFFFu) | ((sel[i + 5] >> 2) << 16);
-              o.w = ((sel[i + 6] >> 2) & 0xFFFFu) | ((sel[i + 7] >> 2) << 16);
-              *reinterpret_cast<uint4*>(out + c0 + sub * PER + i) = o;
-              const uint32_t km = P22 ? 3u : 1u;
-              uint2 a;
-              a.x = (km - (sel[i] & km)) | ((km - (sel[i + 1] & km)) << 8) | ((km - (sel[i + 2] & km)) << 16) | ((km - (sel[i + 3] & km)) << 24);
-              a.y = (km - (sel[i + 4] & km)) | ((km - (sel[i + 5] & km)) << 8) | ((km - (sel[i + 6] & km)) << 16) | ((km - (sel[i + 7] & km)) << 24);
-              *reinterpret_cast<uint2*>(amx + c0 + sub * PER + i) = a;
-            }
-          }
-        }
-      } else if (EPI == EPI_STATS) {
-        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (((size_t)n_img * p.H + h) * p.Wd + w) * p.Nc + col0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(tbase + c0, v);
-          ptx::tmem_ld_wait();
-          float f[32], f2[32];
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c0 + i));
-            f[i] = __uint_as_float(v[i]) + b.x;
-            f[i + 1] = __uint_as_float(v[i + 1]) + b.y;
-            f[i + 2] = __uint_as_float(v[i + 2]) + b.z;
-            f[i + 3] = __uint_as_float(v[i + 3]) + b.w;
-            pk[i / 2] = ptx::pack_bf16x2(f[i], f[i + 1]);
-            pk[i / 2 + 1] = ptx::pack_bf16x2(f[i + 2], f[i + 3]);
-          }
-          if (valid) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4)
-              *reinterpret_cast<uint4*>(out + c0 + 2 * i) = make_uint4(pk[i], pk[i + 1], pk[i + 2], pk[i + 3]);
-          }
-          // statistics of the values the next layer will actually read (bf16-rounded), masked to valid rows
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float a = valid ? ptx::bf16_lo(pk[i]) : 0.f, b = valid ? ptx::bf16_hi(pk[i]) : 0.f;
-            f[2 * i] = a; f[2 * i + 1] = b;
-            f2[2 * i] = a * a; f2[2 * i + 1] = b * b;
-          }
-          const float s1 = warp_colsum32(f, lane);
-          const float s2 = warp_colsum32(f2, lane);
-          atomicAdd(p.stats + col0 + c0 + lane, (double)s1);
-          atomicAdd(p.stats + p.Nc + col0 + c0 + lane, (double)s2);
-        }
-      } else if (EPI == EPI_LSTM) {
-        // row = sample within the direction-stacked batch; tile columns = [i(64) j(64) f(64) o(64)] of 64 units
-        const int grow = m_blk * BLOCK_M + row;
-        const int dir = (m_blk >= p.m_tiles_per_dir) ? 1 : 0;
-        const int n = grow - dir * p.Npad;
-        const bool okn = n < p.Nimg;
-        const int len = okn ? min(max(__ldg(p.seq_len + n), 0), p.T) : 0;
-        const bool active = p.step < len;
-        const int t = active ? (dir ? (len - 1 - p.step) : p.step) : p.step;
-        const size_t rt = (size_t)n * p.H + t;
-        const __nv_bfloat16* xp = p.xproj + rt * 2048 + dir * 1024 + n_blk * 256;
-        float* cst = p.c_state + ((size_t)dir * p.Npad + n) * 256 + n_blk * 64;
-        __nv_bfloat16* hn = p.h_next + ((size_t)dir * p.Npad + n) * 256 + n_blk * 64;
-        __nv_bfloat16* lo = p.lstm_out + rt * 512 + dir * 256 + n_blk * 64;
-#pragma unroll 1
-        for (int u0 = 0; u0 < 64; u0 += 16) {
-          uint32_t gi[16], gj[16], gf[16], go[16];
-          ptx::tmem_ld_32x32b_x16(tbase + u0, gi);
-          ptx::tmem_ld_32x32b_x16(tbase + 64 + u0, gj);
-          ptx::tmem_ld_32x32b_x16(tbase + 128 + u0, gf);
-          ptx::tmem_ld_32x32b_x16(tbase + 192 + u0, go);
-          ptx::tmem_ld_wait();
-          uint32_t hp[8];
-          if (active) {
-            uint4 xi[2], xj[2], xf[2], xo[2];
-            float4 cp[4];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              xi[i] = __ldg(reinterpret_cast<const uint4*>(xp + u0) + i);
-              xj[i] = __ldg(reinterpret_cast<const uint4*>(xp + 64 + u0) + i);
-              xf[i] = __ldg(reinterpret_cast<const uint4*>(xp + 128 + u0) + i);
-              xo[i] = __ldg(reinterpret_cast<const uint4*>(xp + 192 + u0) + i);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) cp[i] = *(reinterpret_cast<const float4*>(cst + u0) + i);
-            const uint32_t* xiw = reinterpret_cast<const uint32_t*>(xi);
-            const uint32_t* xjw = reinterpret_cast<const uint32_t*>(xj);
-            const uint32_t* xfw = reinterpret_cast<const uint32_t*>(xf);
-            const uint32_t* xow = reinterpret_cast<const uint32_t*>(xo);
-            float* cpf = reinterpret_cast<float*>(cp);
-            float hv[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float zi = __uint_as_float(gi[i]) + ((i & 1) ? ptx::bf16_hi(xiw[i >> 1]) : ptx::bf16_lo(xiw[i >> 1]));
-              const float zj = __uint_as_float(gj[i]) + ((i & 1) ? ptx::bf16_hi(xjw[i >> 1]) : ptx::bf16_lo(xjw[i >> 1]));
-              const float zf = __uint_as_float(gf[i]) + ((i & 1) ? ptx::bf16_hi(xfw[i >> 1]) : ptx::bf16_lo(xfw[i >> 1]));
-              const float zo = __uint_as_float(go[i]) + ((i & 1) ? ptx::bf16_hi(xow[i >> 1]) : ptx::bf16_lo(xow[i >> 1]));
-              // forget_bias (+1.0) is folded into the projected bias at weight-prep time
-              const float c = ptx::fast_sigmoid(zf) * cpf[i] + ptx::fast_sigmoid(zi) * ptx::fast_tanh(zj);
-              cpf[i] = c;
-              hv[i] = ptx::fast_sigmoid(zo) * ptx::fast_tanh(c);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) *(reinterpret_cast<float4*>(cst + u0) + i) = cp[i];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) hp[i] = ptx::pack_bf16x2(hv[2 * i], hv[2 * i + 1]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) hp[i] = 0u;    // zero output past sequence_length; state no longer used
-          }
-          if (okn) {
-            *reinterpret_cast<uint4*>(hn + u0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-            *reinterpret_cast<uint4*>(hn + u0 + 8) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
-            *reinterpret_cast<uint4*>(lo + u0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-            *reinterpret_cast<uint4*>(lo + u0 + 8) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
-          }
-        }
-      }
-
+      run_epilogue<BLOCK_N, EPI>(p, tbase, m_blk, n_blk, q, lane);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);

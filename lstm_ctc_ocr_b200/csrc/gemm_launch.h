@@ -1,6 +1,7 @@
 // Launch helpers for the tcgen05 GEMM kernels (shared by model.cu and backward.cu).
 #pragma once
 #include "gemm.cuh"
+#include "gemm2.cuh"
 #include "gemm_tn.cuh"
 
 template <int BN, int AM, int EPI, int ST>
@@ -15,6 +16,24 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const gemm::P
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms ? tiles : num_sms;
   kern<<<grid, gemm::NUM_THREADS, smem, st>>>(a, b, p);
+  CUDA_TRY(cudaGetLastError());
+  return CRNN_OK;
+}
+
+// 2-CTA pairs: B map must have box rows = 128 (each CTA stages half of the 256-row N tile)
+template <int AM, int EPI, int ST>
+static int launch_gemm2(const CUtensorMap& a, const CUtensorMap& b_half, const gemm::Params& p, int num_sms, cudaStream_t st) {
+  auto kern = gemm::gemm2_kernel<AM, EPI, ST>;
+  constexpr int smem = gemm::Smem2<ST>::BYTES;
+  static bool attr = false;
+  if (!attr) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  const int pairs = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+  int clusters = num_sms / 2;
+  if (pairs < clusters) clusters = pairs;
+  kern<<<2 * clusters, gemm::NUM_THREADS, smem, st>>>(a, b_half, p);
   CUDA_TRY(cudaGetLastError());
   return CRNN_OK;
 }

@@ -142,6 +142,7 @@ extern "C" int crnn_model_create(const crnn_config* cfg, crnn_model** out) {
     return crnn_fail(CRNN_UNSUPPORTED, "model_create: needs sm_100 (found sm_%d%d)", prop.major, prop.minor);
   }
   m->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("CRNN_GEMM2")) m->use_2cta = std::string(e) != "0";
   if (const char* e = getenv("CRNN_LSTM_IMPL")) m->lstm_upc = (std::string(e) == "step") ? 64 : 32;   // debug A/B switch
 
   // one allocation for all derived operand copies
@@ -166,6 +167,12 @@ extern "C" int crnn_model_create(const crnn_config* cfg, crnn_model** out) {
   if (st == CRNN_OK) st = make_tmap_2d(&m->tB_h, m->Bh, 2048, 256, 256, 256);
   if (st == CRNN_OK) st = make_tmap_2d(&m->tB_h128, m->Bh, 2048, 256, 256, 128);
   if (st == CRNN_OK) st = make_tmap_2d(&m->tB_l, m->Bl, 64, 512, 512, 64);
+  if (st == CRNN_OK) st = make_tmap_2d(&m->tBh_c31, m->Bc31, 256, 1152, 1152, 128);
+  if (st == CRNN_OK) st = make_tmap_2d(&m->tBh_c32, m->Bc32, 256, 2304, 2304, 128);
+  if (st == CRNN_OK) st = make_tmap_2d(&m->tBh_c41, m->Bc41, 512, 2304, 2304, 128);
+  if (st == CRNN_OK) st = make_tmap_2d(&m->tBh_c42, m->Bc42, 512, 4608, 4608, 128);
+  if (st == CRNN_OK) st = make_tmap_2d(&m->tBh_c5, m->Bc5, 512, 2048, 2048, 128);
+  if (st == CRNN_OK) st = make_tmap_2d(&m->tBh_x, m->Bx, 2048, 512, 512, 128);
   if (st != CRNN_OK) { cudaFree(m->wblock); delete m; return st; }
   *out = m;
   return CRNN_OK;
@@ -384,7 +391,8 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
   // conv3_1 + ReLU
   {
     gemm::Params p = conv_params(N, H2, 8, 128, 256, 256, m->P("conv3_1/biases"), pl.a3);
-    CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_RELU, 4>(pl.tA_c31, m->tB_c31, p, sms, st)));
+    if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_RELU, 6>(pl.tA_c31, m->tBh_c31, p, sms, st)));
+    else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_RELU, 4>(pl.tA_c31, m->tB_c31, p, sms, st)));
   }
   STAGE_MARK();
   // conv3_2 + ReLU + height pool
@@ -392,9 +400,11 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
     gemm::Params p = conv_params(N, H2, 8, 256, 256, 256, m->P("conv3_2/biases"), pl.a3p);
     if (pl.train) {
       p.argmax = pl.am3;
-      CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_RELU_POOL12_T, 4>(pl.tA_c32, m->tB_c32, p, sms, st)));
+      if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_RELU_POOL12_T, 6>(pl.tA_c32, m->tBh_c32, p, sms, st)));
+      else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_RELU_POOL12_T, 4>(pl.tA_c32, m->tB_c32, p, sms, st)));
     } else {
-      CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_RELU_POOL12, 4>(pl.tA_c32, m->tB_c32, p, sms, st)));
+      if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_RELU_POOL12, 6>(pl.tA_c32, m->tBh_c32, p, sms, st)));
+      else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_RELU_POOL12, 4>(pl.tA_c32, m->tB_c32, p, sms, st)));
     }
   }
   STAGE_MARK();
@@ -404,7 +414,8 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
   {
     gemm::Params p = conv_params(N, H2, 4, 256, 512, 256, m->P("conv4_1/biases"), pl.a4a_pre);
     p.stats = pl.stats;
-    CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_STATS, 4>(pl.tA_c41, m->tB_c41, p, sms, st)));
+    if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_STATS, 6>(pl.tA_c41, m->tBh_c41, p, sms, st)));
+    else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_STATS, 4>(pl.tA_c41, m->tB_c41, p, sms, st)));
     STAGE_MARK();
     float* bn = pl.bn;
     CRNN_TRY(launch_bn_finalize(pl.stats, bn_count, m->P("conv4_1/conv4_1/gamma"), m->P("conv4_1/conv4_1/beta"),
@@ -416,7 +427,8 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
   {
     gemm::Params p = conv_params(N, H2, 4, 512, 512, 256, m->P("conv4_2/biases"), pl.a4b_pre);
     p.stats = pl.stats + 1024;
-    CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_STATS, 4>(pl.tA_c42, m->tB_c42, p, sms, st)));
+    if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_STATS, 6>(pl.tA_c42, m->tBh_c42, p, sms, st)));
+    else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_STATS, 4>(pl.tA_c42, m->tB_c42, p, sms, st)));
     STAGE_MARK();
     float* bn = pl.bn + 2048;
     CRNN_TRY(launch_bn_finalize(pl.stats + 1024, bn_count, m->P("conv4_2/conv4_2/gamma"), m->P("conv4_2/conv4_2/beta"),
@@ -431,7 +443,8 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
     p.M = N * H2;
     p.num_m_tiles = (p.M + 127) / 128; p.num_n_tiles = 2; p.num_k_blocks = 32; p.kb_per_shift = 16; p.row_shift_mul = 1;
     p.Nc = 512; p.bias = m->P("conv5/biases"); p.out = pl.a5; p.ldo = 512;
-    CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 4>(pl.tA_c5, m->tB_c5, p, sms, st)));
+    if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 6>(pl.tA_c5, m->tBh_c5, p, sms, st)));
+    else CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 4>(pl.tA_c5, m->tB_c5, p, sms, st)));
   }
   STAGE_MARK();
   // LSTM input projection for all frames and both directions: [N*H2, 512] x [512, 2048]
@@ -442,7 +455,8 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
     p.num_m_tiles = (p.M + 127) / 128; p.num_n_tiles = 8; p.num_k_blocks = 8; p.kb_per_shift = 8;
     p.Nc = 2048; p.bias = m->xbias; p.out = pl.xproj; p.ldo = 2048;
     p.H = H2; p.T = T; p.seq_len = time_step_len;
-    if (m->lstm_upc == 32) CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_XPROJ, 4>(pl.tA_x, m->tB_x, p, sms, st)));
+    if (m->lstm_upc == 32 && m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_PLAIN, gemm::EPI_XPROJ, 6>(pl.tA_x, m->tBh_x, p, sms, st)));
+    else if (m->lstm_upc == 32) CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_XPROJ, 4>(pl.tA_x, m->tB_x, p, sms, st)));
     else CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 4>(pl.tA_x, m->tB_x, p, sms, st)));
   }
   STAGE_MARK();
@@ -566,14 +580,14 @@ extern "C" int crnn_debug_tap(crnn_model* m, const char* name, float* dst, size_
 
 extern "C" int crnn_test_gemm_bf16(const void* A, const void* B, float* D, int M, int Nc, int K, int block_n,
                                    crnn_stream_t stream) {
-  if (!A || !B || !D || M <= 0 || Nc <= 0 || K <= 0 || (K % 64) != 0 || (Nc % block_n) != 0)
+  if (!A || !B || !D || M <= 0 || Nc <= 0 || K <= 0 || (K % 64) != 0 || (block_n != 512 && (Nc % block_n) != 0))
     return crnn_fail(CRNN_INVALID_VALUE, "test_gemm: bad args");
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   CUtensorMap ta, tb;
   CRNN_TRY(make_tmap_2d(&ta, A, M, K, K, 128));
-  CRNN_TRY(make_tmap_2d(&tb, B, Nc, K, K, block_n));
+  CRNN_TRY(make_tmap_2d(&tb, B, Nc, K, K, block_n == 512 ? 256 : block_n));
   gemm::Params p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.Nc = Nc;
@@ -583,5 +597,12 @@ extern "C" int crnn_test_gemm_bf16(const void* A, const void* B, float* D, int M
   if (block_n == 64) return launch_gemm<64, gemm::A_PLAIN, gemm::EPI_F32, 8>(ta, tb, p, sms, st);
   if (block_n == 128) return launch_gemm<128, gemm::A_PLAIN, gemm::EPI_F32, 6>(ta, tb, p, sms, st);
   if (block_n == 256) return launch_gemm<256, gemm::A_PLAIN, gemm::EPI_F32, 4>(ta, tb, p, sms, st);
-  return crnn_fail(CRNN_INVALID_VALUE, "test_gemm: block_n must be 64/128/256");
+  if (block_n == 512) {      // 2-CTA pairs (cta_group::2), 256 x 256 tile per cluster
+    if (Nc % 256) return crnn_fail(CRNN_INVALID_VALUE, "test_gemm: 2-CTA path needs Nc % 256 == 0");
+    CUtensorMap tbh;
+    CRNN_TRY(make_tmap_2d(&tbh, B, Nc, K, K, 128));
+    p.num_n_tiles = Nc / 256;
+    return launch_gemm2<gemm::A_PLAIN, gemm::EPI_F32, 6>(ta, tbh, p, sms, st);
+  }
+  return crnn_fail(CRNN_INVALID_VALUE, "test_gemm: block_n must be 64/128/256 (or 512 = 2-CTA pairs)");
 }
