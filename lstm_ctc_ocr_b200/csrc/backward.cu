@@ -33,6 +33,11 @@ extern "C" int crnn_model_set_training(crnn_model* m, int flag) {
     CRNN_TRY(make_tmap_2d(&m->tD_l, m->Bld, 512, 64, 64, 256));
     CRNN_TRY(make_tmap_2d(&m->tD_x, m->Bxb, 512, 2048, 2048, 256));
     CRNN_TRY(make_tmap_2d(&m->tD_h, m->Bhb, 512, 1024, 1024, 32));
+    CRNN_TRY(make_tmap_2d(&m->tDh_c42, m->Bd_c42, 512, 4608, 4608, 128));
+    CRNN_TRY(make_tmap_2d(&m->tDh_c41, m->Bd_c41, 256, 4608, 4608, 128));
+    CRNN_TRY(make_tmap_2d(&m->tDh_c32, m->Bd_c32, 256, 2304, 2304, 128));
+    CRNN_TRY(make_tmap_2d(&m->tDh_c5, m->Bd_c5, 1024, 1024, 1024, 128));
+    CRNN_TRY(make_tmap_2d(&m->tDh_x, m->Bxb, 512, 2048, 2048, 128));
     m->dirty_bwd = true;
   }
   m->training = flag != 0;
@@ -162,7 +167,8 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
       memset(&p, 0, sizeof(p));
       p.M = (int)R; p.num_m_tiles = (p.M + 127) / 128; p.num_n_tiles = 2; p.num_k_blocks = 32; p.kb_per_shift = 32;
       p.Nc = 512; p.out = pl.d_a5; p.ldo = 512;
-      CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 4>(pl.tG_dz, m->tD_x, p, sms, st)));
+      if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 6>(pl.tG_dz, m->tDh_x, p, sms, st)));
+      else CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 4>(pl.tG_dz, m->tD_x, p, sms, st)));
     }
   }
   BMARK();
@@ -178,7 +184,8 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
     memset(&p, 0, sizeof(p));
     p.M = (int)R; p.num_m_tiles = (p.M + 127) / 128; p.num_n_tiles = 4; p.num_k_blocks = 16; p.kb_per_shift = 8; p.row_shift_mul = -1;
     p.Nc = 1024; p.out = pl.d_a4b; p.ldo = 1024;
-    CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 4>(pl.tG_da5, m->tD_c5, p, sms, st)));
+    if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 6>(pl.tG_da5, m->tDh_c5, p, sms, st)));
+    else CRNN_TRY((launch_gemm<256, gemm::A_PLAIN, gemm::EPI_BIAS_BF16, 4>(pl.tG_da5, m->tD_c5, p, sms, st)));
   }
   BMARK();
   // ------------------------------------------------------------------ conv4_2: pool3 + ReLU + batch-stat BN backward
@@ -197,7 +204,8 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   BMARK();
   {
     gemm::Params p = conv_params(N, H2, 4, 512, 512, 256, nullptr, pl.d_pre4a);
-    CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_CONV_STORE, 4>(pl.tG_p4b, m->tD_c42, p, sms, st)));
+    if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_CONV_STORE, 6>(pl.tG_p4b, m->tDh_c42, p, sms, st)));
+    else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_CONV_STORE, 4>(pl.tG_p4b, m->tD_c42, p, sms, st)));
   }
   BMARK();
   // ------------------------------------------------------------------ conv4_1: ReLU + BN backward
@@ -214,7 +222,8 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   BMARK();
   {
     gemm::Params p = conv_params(N, H2, 4, 512, 256, 256, nullptr, pl.d_a3p);
-    CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_CONV_STORE, 4>(pl.tG_p4a, m->tD_c41, p, sms, st)));
+    if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_CONV_STORE, 6>(pl.tG_p4a, m->tDh_c41, p, sms, st)));
+    else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_CONV_STORE, 4>(pl.tG_p4a, m->tD_c41, p, sms, st)));
   }
   BMARK();
   // ------------------------------------------------------------------ conv3_2: 1x2 pool + ReLU backward
@@ -229,7 +238,8 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   BMARK();
   {
     gemm::Params p = conv_params(N, H2, 8, 256, 256, 256, nullptr, pl.d_pre31);
-    CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_CONV_STORE, 4>(pl.tG_p32, m->tD_c32, p, sms, st)));
+    if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_CONV_STORE, 6>(pl.tG_p32, m->tDh_c32, p, sms, st)));
+    else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_CONV_STORE, 4>(pl.tG_p32, m->tD_c32, p, sms, st)));
   }
   BMARK();
   // ------------------------------------------------------------------ conv3_1: ReLU backward
