@@ -68,7 +68,7 @@ static gemm_tn::Params tn_plain(int M, int Ncols, long long rows, float* out, lo
   p.out = out; p.ldo = ldo;
   return p;
 }
-static gemm_tn::Params tn_conv(int N, int H, int Wd, int Cin, int Cout, float* out) {
+static gemm_tn::Params tn_conv(int N, int H, int Wd, int Cin, int Cout, float* out, int merged) {
   gemm_tn::Params p;
   memset(&p, 0, sizeof(p));
   p.num_taps = 9;
@@ -76,7 +76,9 @@ static gemm_tn::Params tn_conv(int N, int H, int Wd, int Cin, int Cout, float* o
   p.M = Cin; p.N = Cout;
   p.bh = 32 / Wd; p.Wd = Wd; p.H = H; p.Nimg = N; p.Cin = Cin;
   p.sb_per_img = (H + p.bh - 1) / p.bh;
-  p.k_blocks_total = (N * p.sb_per_img + 1) / 2;
+  p.merged = merged;
+  p.kb_per_img = p.sb_per_img / 2;
+  p.k_blocks_total = merged ? N * p.kb_per_img : (N * p.sb_per_img + 1) / 2;
   p.out = out; p.ldo = Cout; p.tap_stride = (long long)Cin * Cout;
   return p;
 }
@@ -197,13 +199,13 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   CRNN_TRY(launch_colsum_bf16(pl.d_pre4b, (long long)P4, 512, G("conv4_2/biases"), 0, 0, st));
   BMARK();
   {
-    gemm_tn::Params p = tn_conv(N, H2, 4, 512, 512, G("conv4_2/weights"));
+    gemm_tn::Params p = tn_conv(N, H2, 4, 512, 512, G("conv4_2/weights"), pl.wm4);
     p.num_n_tiles = 2;
-    CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tA_c42, pl.tG_p4b, p, sms, st)));
+    CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tW_a4a, pl.tW_p4b, p, sms, st)));
   }
   BMARK();
   {
-    gemm::Params p = conv_params(N, H2, 4, 512, 512, 256, nullptr, pl.d_pre4a);
+    gemm::Params p = conv_params(N, H2, 4, 512, 512, 256, nullptr, pl.d_pre4a, pl.mg4);
     if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_CONV_STORE, 6>(pl.tG_p4b, m->tDh_c42, p, sms, st)));
     else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_CONV_STORE, 4>(pl.tG_p4b, m->tD_c42, p, sms, st)));
   }
@@ -215,13 +217,13 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   CRNN_TRY(launch_colsum_bf16(pl.d_pre4a, (long long)P4, 512, G("conv4_1/biases"), 0, 0, st));
   BMARK();
   {
-    gemm_tn::Params p = tn_conv(N, H2, 4, 256, 512, G("conv4_1/weights"));
+    gemm_tn::Params p = tn_conv(N, H2, 4, 256, 512, G("conv4_1/weights"), pl.wm4);
     p.num_n_tiles = 2;
-    CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tA_c41, pl.tG_p4a, p, sms, st)));
+    CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tW_a3p, pl.tW_p4a, p, sms, st)));
   }
   BMARK();
   {
-    gemm::Params p = conv_params(N, H2, 4, 512, 256, 256, nullptr, pl.d_a3p);
+    gemm::Params p = conv_params(N, H2, 4, 512, 256, 256, nullptr, pl.d_a3p, pl.mg4);
     if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_CONV_STORE, 6>(pl.tG_p4a, m->tDh_c41, p, sms, st)));
     else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_CONV_STORE, 4>(pl.tG_p4a, m->tD_c41, p, sms, st)));
   }
@@ -231,13 +233,13 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   CRNN_TRY(launch_colsum_bf16(pl.d_pre32, (long long)N * H2 * 8, 256, G("conv3_2/biases"), 0, 0, st));
   BMARK();
   {
-    gemm_tn::Params p = tn_conv(N, H2, 8, 256, 256, G("conv3_2/weights"));
+    gemm_tn::Params p = tn_conv(N, H2, 8, 256, 256, G("conv3_2/weights"), pl.wm3);
     p.num_n_tiles = 1;
-    CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tA_c32, pl.tG_p32, p, sms, st)));
+    CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tW_a3, pl.tW_p32, p, sms, st)));
   }
   BMARK();
   {
-    gemm::Params p = conv_params(N, H2, 8, 256, 256, 256, nullptr, pl.d_pre31);
+    gemm::Params p = conv_params(N, H2, 8, 256, 256, 256, nullptr, pl.d_pre31, pl.mg3);
     if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_CONV_STORE, 6>(pl.tG_p32, m->tDh_c32, p, sms, st)));
     else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_CONV_STORE, 4>(pl.tG_p32, m->tD_c32, p, sms, st)));
   }
@@ -247,13 +249,13 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   CRNN_TRY(launch_colsum_bf16(pl.d_pre31, (long long)N * H2 * 8, 256, G("conv3_1/biases"), 0, 0, st));
   BMARK();
   {
-    gemm_tn::Params p = tn_conv(N, H2, 8, 128, 256, G("conv3_1/weights"));
+    gemm_tn::Params p = tn_conv(N, H2, 8, 128, 256, G("conv3_1/weights"), pl.wm3);
     p.num_n_tiles = 1;
-    CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tA_c31, pl.tG_p31, p, sms, st)));
+    CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tW_a2, pl.tW_p31, p, sms, st)));
   }
   BMARK();
   {
-    gemm::Params p = conv_params(N, H2, 8, 256, 128, 128, nullptr, pl.d_a2);
+    gemm::Params p = conv_params(N, H2, 8, 256, 128, 128, nullptr, pl.d_a2, pl.mg3);
     CRNN_TRY((launch_gemm<128, gemm::A_CONV3, gemm::EPI_CONV_STORE, 6>(pl.tG_p31, m->tD_c31, p, sms, st)));
   }
   BMARK();
@@ -262,13 +264,13 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   CRNN_TRY(launch_colsum_bf16(pl.d_pre2, (long long)N * H1 * 16, 128, G("conv2/biases"), 0, 0, st));
   BMARK();
   {
-    gemm_tn::Params p = tn_conv(N, H1, 16, 64, 128, G("conv2/weights"));
+    gemm_tn::Params p = tn_conv(N, H1, 16, 64, 128, G("conv2/weights"), pl.wm2);
     p.num_n_tiles = 1;
-    CRNN_TRY((launch_gemm_tn<128, gemm_tn::TN_CONV, 6>(pl.tA_c2, pl.tG_p2, p, sms, st)));
+    CRNN_TRY((launch_gemm_tn<128, gemm_tn::TN_CONV, 6>(pl.tW_a1, pl.tW_p2, p, sms, st)));
   }
   BMARK();
   {
-    gemm::Params p = conv_params(N, H1, 16, 128, 64, 64, nullptr, pl.d_a1);
+    gemm::Params p = conv_params(N, H1, 16, 128, 64, 64, nullptr, pl.d_a1, pl.mg2);
     CRNN_TRY((launch_gemm<64, gemm::A_CONV3, gemm::EPI_CONV_STORE, 8>(pl.tG_p2, m->tD_c2, p, sms, st)));
   }
   BMARK();

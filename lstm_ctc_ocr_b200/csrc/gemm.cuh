@@ -50,6 +50,8 @@ struct Params {
   int num_m_tiles, num_n_tiles, num_k_blocks;
   int kb_per_shift;      // A_PLAIN: K-block kb reads A columns (kb % kb_per_shift)*64 of row (m + kb / kb_per_shift);
                          // == num_k_blocks for an ordinary GEMM; conv5 (2x2 VALID) uses 16 -> rows t and t+1
+  int merged;            // conv: the tile's 4 sub-boxes are contiguous H rows of one image -> one 128-position TMA box
+  int debug_skip_tma;    // probe only: producer arrives without loading (measures the MMA/epilogue ceiling)
   int row_shift_mul;     // +1 (conv5 forward: rows m, m+1) or -1 (conv5 data gradient: rows m, m-1)
   int M;                 // valid rows (plain modes)
   int Nc;                // total output columns
@@ -479,32 +481,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // One lane per TMA box: a single thread issuing 5 boxes per K-block was the bottleneck of the conv mainloop
+    // (~200 cycles per cp.async.bulk.tensor issue vs 512 MMA cycles per K-block).  Lanes 0..nA-1 load the A sub-boxes,
+    // lane nA loads B; lane 0 also arms the transaction count.  conv: when the tile's 4 sub-boxes are contiguous rows of
+    // one image (p.merged), a single 128-position box replaces them.
+    const int nA = (AMODE == A_CONV3 && !p.merged) ? 4 : 1;
+    if (lane <= nA) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
         int b_row = n_blk * BLOCK_N;
         if (EPI == EPI_LSTM) b_row += (m_blk >= p.m_tiles_per_dir) ? 1024 : 0;
+        // per-tile coordinates of this lane's A box (conv): image n, first H row h0
+        int cn = 0, ch0 = 0;
+        if (AMODE == A_CONV3 && lane < nA) {
+          const int g = m_blk * 4 + lane;
+          cn = g / p.sb_per_img;
+          ch0 = (g - cn * p.sb_per_img) * p.bh;
+        }
+        int tap = 0, cb = 0;                    // conv K-block decomposition, advanced incrementally
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-          uint8_t* a_dst = smem_a + stage * A_STAGE_BYTES;
-          if (AMODE == A_PLAIN) {
-            const int rs = kb / p.kb_per_shift, kc = kb - rs * p.kb_per_shift;
-            ptx::tma_load_2d(&tmA, &full_bar[stage], a_dst, kc * BLOCK_K, m_blk * BLOCK_M + rs * p.row_shift_mul);
+          if (p.debug_skip_tma) {
+            if (lane == 0) ptx::mbar_arrive(&full_bar[stage]);
           } else {
-            const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
-            const int r = tap / 3, s = tap - 3 * r;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int g = m_blk * 4 + j;
-              const int n = g / p.sb_per_img;
-              const int h0 = (g - n * p.sb_per_img) * p.bh;
-              ptx::tma_load_4d(&tmA, &full_bar[stage], a_dst + j * 4096, cb * BLOCK_K, s - 1, h0 + r - 1, n);
+            if (lane == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+            if (lane < nA) {
+              uint8_t* a_dst = smem_a + stage * A_STAGE_BYTES;
+              if (AMODE == A_PLAIN) {
+                const int rs = kb / p.kb_per_shift, kc = kb - rs * p.kb_per_shift;
+                ptx::tma_load_2d(&tmA, &full_bar[stage], a_dst, kc * BLOCK_K, m_blk * BLOCK_M + rs * p.row_shift_mul);
+              } else {
+                const int r = tap / 3, sx = tap - 3 * r;
+                ptx::tma_load_4d(&tmA, &full_bar[stage], a_dst + lane * 4096, cb * BLOCK_K, sx - 1, ch0 + r - 1, cn);
+              }
+            } else {
+              ptx::tma_load_2d(&tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, b_row);
             }
           }
-          ptx::tma_load_2d(&tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, b_row);
+          if (++cb == p.cin_blocks) { cb = 0; ++tap; }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }

@@ -63,32 +63,41 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp_idx == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (both CTAs): one lane per TMA box, see gemm.cuh =====================
+    const int nA = (AMODE == A_CONV3 && !p.merged) ? 4 : 1;
+    if (lane <= nA) {
       int stage = 0; uint32_t phase = 0;
       for (int pr = cluster_id; pr < num_pairs; pr += num_clusters) {
         const int m_blk = (pr / p.num_n_tiles) * 2 + (int)rank, n_blk = pr % p.num_n_tiles;
         const int b_row = n_blk * BLOCK_N + (int)rank * 128;
+        int cn = 0, ch0 = 0;
+        if (AMODE == A_CONV3 && lane < nA) {
+          const int g = m_blk * 4 + lane;
+          cn = g / p.sb_per_img;
+          ch0 = (g - cn * p.sb_per_img) * p.bh;
+        }
+        int tap = 0, cb = 0;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          const uint32_t lead_full = ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0);
-          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_STAGE + B_STAGE));
-          uint8_t* a_dst = smem_a + stage * A_STAGE;
-          if (AMODE == A_PLAIN) {
-            const int rs = kb / p.kb_per_shift, kc = kb - rs * p.kb_per_shift;
-            ptx::tma_load_2d_2cta(&tmA, lead_full, a_dst, kc * BLOCK_K, m_blk * BLOCK_M + rs * p.row_shift_mul);
+          if (p.debug_skip_tma) {
+            if (leader && lane == 0) ptx::mbar_arrive(&full_bar[stage]);
           } else {
-            const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
-            const int r = tap / 3, s = tap - 3 * r;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int g = m_blk * 4 + j;
-              const int n = g / p.sb_per_img;
-              const int h0 = (g - n * p.sb_per_img) * p.bh;
-              ptx::tma_load_4d_2cta(&tmA, lead_full, a_dst + j * 4096, cb * BLOCK_K, s - 1, h0 + r - 1, n);
+            const uint32_t lead_full = ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0);
+            if (leader && lane == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_STAGE + B_STAGE));
+            if (lane < nA) {
+              uint8_t* a_dst = smem_a + stage * A_STAGE;
+              if (AMODE == A_PLAIN) {
+                const int rs = kb / p.kb_per_shift, kc = kb - rs * p.kb_per_shift;
+                ptx::tma_load_2d_2cta(&tmA, lead_full, a_dst, kc * BLOCK_K, m_blk * BLOCK_M + rs * p.row_shift_mul);
+              } else {
+                const int r = tap / 3, sx = tap - 3 * r;
+                ptx::tma_load_4d_2cta(&tmA, lead_full, a_dst + lane * 4096, cb * BLOCK_K, sx - 1, ch0 + r - 1, cn);
+              }
+            } else {
+              ptx::tma_load_2d_2cta(&tmB, lead_full, smem_b + stage * B_STAGE, kb * BLOCK_K, b_row);
             }
           }
-          ptx::tma_load_2d_2cta(&tmB, lead_full, smem_b + stage * B_STAGE, kb * BLOCK_K, b_row);
+          if (++cb == p.cin_blocks) { cb = 0; ++tap; }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }

@@ -33,6 +33,7 @@ struct Params {
   int M, N;                                  // valid output rows / cols
   // TN_CONV geometry
   int sb_per_img, bh, Wd, H, Nimg, Cin;
+  int merged, kb_per_img;                    // TN_CONV: 64-position boxes (2*bh rows) when H % (2*bh) == 0
   int a_row_shift;                           // TN_PLAIN: A rows are read at k + a_row_shift (conv5's second tap)
   // output
   float* out;
@@ -114,37 +115,35 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   };
 
   if (warp_idx == 0) {
-    if (lane == 0) {
+    // one lane per 64-channel operand block (JA blocks of A, JB blocks of B); lane 0 also arms the transaction count
+    if (lane < JA + JB) {
+      const bool isA = lane < JA;
+      const int j = isA ? lane : lane - JA;
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         int tap, m_blk, n_blk, kb0, kb1;
         decode(item, tap, m_blk, n_blk, kb0, kb1);
         const int r = tap / 3, s = tap - 3 * r;
+        const int ccol = isA ? (m_blk * BLOCK_M + 64 * j) : (n_blk * BLOCK_N + 64 * j);
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], A_STAGE + B_STAGE);
-          uint8_t* a_dst = smem_a + stage * A_STAGE;
-          uint8_t* b_dst = smem_b + stage * B_STAGE;
+          if (lane == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], A_STAGE + B_STAGE);
+          uint8_t* dst = (isA ? smem_a + stage * A_STAGE : smem_b + stage * B_STAGE) + j * BLK_BYTES;
+          const CUtensorMap* tm = isA ? &tmA : &tmB;
           if (AMODE == TN_PLAIN) {
-#pragma unroll
-            for (int j = 0; j < JA; ++j)
-              ptx::tma_load_2d(&tmA, &full_bar[stage], a_dst + j * BLK_BYTES, m_blk * BLOCK_M + 64 * j, kb * BLOCK_K + p.a_row_shift);
-#pragma unroll
-            for (int j = 0; j < JB; ++j)
-              ptx::tma_load_2d(&tmB, &full_bar[stage], b_dst + j * BLK_BYTES, n_blk * BLOCK_N + 64 * j, kb * BLOCK_K);
+            ptx::tma_load_2d(tm, &full_bar[stage], dst, ccol, kb * BLOCK_K + (isA ? p.a_row_shift : 0));
+          } else if (p.merged) {
+            // 64 consecutive positions = 2*bh rows of one image in one box
+            const int n = kb / p.kb_per_img;
+            const int h0 = (kb - n * p.kb_per_img) * 2 * p.bh;
+            ptx::tma_load_4d(tm, &full_bar[stage], dst, ccol, isA ? s - 1 : 0, h0 + (isA ? r - 1 : 0), n);
           } else {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               const int g = kb * 2 + half;                     // 32-position sub-box index
               const int n = g / p.sb_per_img;
               const int h0 = (g - n * p.sb_per_img) * p.bh;
-#pragma unroll
-              for (int j = 0; j < JA; ++j)
-                ptx::tma_load_4d(&tmA, &full_bar[stage], a_dst + j * BLK_BYTES + half * 4096, m_blk * BLOCK_M + 64 * j, s - 1,
-                                 h0 + r - 1, n);
-#pragma unroll
-              for (int j = 0; j < JB; ++j)
-                ptx::tma_load_4d(&tmB, &full_bar[stage], b_dst + j * BLK_BYTES + half * 4096, n_blk * BLOCK_N + 64 * j, 0, h0, n);
+              ptx::tma_load_4d(tm, &full_bar[stage], dst + half * 4096, ccol, isA ? s - 1 : 0, h0 + (isA ? r - 1 : 0), n);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }

@@ -305,11 +305,13 @@ static int build_plan(crnn_model* m, int N, int W, void* ws, cudaStream_t st) {
   Plan& pl = m->plan;
   layout_plan(pl, N, W, reinterpret_cast<uint8_t*>(ws), m->training);
   pl.ws = ws;
-  CRNN_TRY(make_tmap_nhwc(&pl.tA_c2, pl.a1, N, pl.H1, 16, 64, 2));
-  CRNN_TRY(make_tmap_nhwc(&pl.tA_c31, pl.a2, N, pl.H2, 8, 128, 4));
-  CRNN_TRY(make_tmap_nhwc(&pl.tA_c32, pl.a3, N, pl.H2, 8, 256, 4));
-  CRNN_TRY(make_tmap_nhwc(&pl.tA_c41, pl.a3p, N, pl.H2, 4, 256, 8));
-  CRNN_TRY(make_tmap_nhwc(&pl.tA_c42, pl.a4a, N, pl.H2, 4, 512, 8));
+  pl.mg2 = (pl.H1 % 8) == 0; pl.mg3 = (pl.H2 % 16) == 0; pl.mg4 = (pl.H2 % 32) == 0;
+  pl.wm2 = (pl.H1 % 4) == 0; pl.wm3 = (pl.H2 % 8) == 0; pl.wm4 = (pl.H2 % 16) == 0;
+  CRNN_TRY(make_tmap_nhwc(&pl.tA_c2, pl.a1, N, pl.H1, 16, 64, pl.mg2 ? 8 : 2));
+  CRNN_TRY(make_tmap_nhwc(&pl.tA_c31, pl.a2, N, pl.H2, 8, 128, pl.mg3 ? 16 : 4));
+  CRNN_TRY(make_tmap_nhwc(&pl.tA_c32, pl.a3, N, pl.H2, 8, 256, pl.mg3 ? 16 : 4));
+  CRNN_TRY(make_tmap_nhwc(&pl.tA_c41, pl.a3p, N, pl.H2, 4, 256, pl.mg4 ? 32 : 8));
+  CRNN_TRY(make_tmap_nhwc(&pl.tA_c42, pl.a4a, N, pl.H2, 4, 512, pl.mg4 ? 32 : 8));
   // conv5 (2x2 VALID over [N,H2,2,512]): output (n,t) = rows n*H2+t and n*H2+t+1 of the [N*H2, 1024] view
   CRNN_TRY(make_tmap_2d(&pl.tA_c5, pl.a4b, (uint64_t)N * pl.H2, 1024, 1024, 128));
   CRNN_TRY(make_tmap_2d(&pl.tA_x, pl.a5, (uint64_t)N * pl.H2, 512, 512, 128));
@@ -326,11 +328,22 @@ static int build_plan(crnn_model* m, int N, int W, void* ws, cudaStream_t st) {
     CRNN_TRY(make_tmap_2d(&pl.tG_dz, pl.dz_all, R, 2048, 2048, 128));
     CRNN_TRY(make_tmap_2d(&pl.tG_da5, pl.d_a5, R, 512, 512, 128));
     CRNN_TRY(make_tmap_2d(&pl.tG_dzstate, pl.dz_state, (uint64_t)4 * pl.Npad, 1024, 1024, 128));
-    CRNN_TRY(make_tmap_nhwc(&pl.tG_p4b, pl.d_pre4b, N, pl.H2, 4, 512, 8));
-    CRNN_TRY(make_tmap_nhwc(&pl.tG_p4a, pl.d_pre4a, N, pl.H2, 4, 512, 8));
-    CRNN_TRY(make_tmap_nhwc(&pl.tG_p32, pl.d_pre32, N, pl.H2, 8, 256, 4));
-    CRNN_TRY(make_tmap_nhwc(&pl.tG_p31, pl.d_pre31, N, pl.H2, 8, 256, 4));
-    CRNN_TRY(make_tmap_nhwc(&pl.tG_p2, pl.d_pre2, N, pl.H1, 16, 128, 2));
+    CRNN_TRY(make_tmap_nhwc(&pl.tG_p4b, pl.d_pre4b, N, pl.H2, 4, 512, pl.mg4 ? 32 : 8));
+    CRNN_TRY(make_tmap_nhwc(&pl.tG_p4a, pl.d_pre4a, N, pl.H2, 4, 512, pl.mg4 ? 32 : 8));
+    CRNN_TRY(make_tmap_nhwc(&pl.tG_p32, pl.d_pre32, N, pl.H2, 8, 256, pl.mg3 ? 16 : 4));
+    CRNN_TRY(make_tmap_nhwc(&pl.tG_p31, pl.d_pre31, N, pl.H2, 8, 256, pl.mg3 ? 16 : 4));
+    CRNN_TRY(make_tmap_nhwc(&pl.tG_p2, pl.d_pre2, N, pl.H1, 16, 128, pl.mg2 ? 8 : 2));
+    // weight-gradient (TN_CONV) views: 64-position boxes when two sub-boxes are contiguous rows of one image, else 32
+    CRNN_TRY(make_tmap_nhwc(&pl.tW_a1, pl.a1, N, pl.H1, 16, 64, pl.wm2 ? 4 : 2));
+    CRNN_TRY(make_tmap_nhwc(&pl.tW_p2, pl.d_pre2, N, pl.H1, 16, 128, pl.wm2 ? 4 : 2));
+    CRNN_TRY(make_tmap_nhwc(&pl.tW_a2, pl.a2, N, pl.H2, 8, 128, pl.wm3 ? 8 : 4));
+    CRNN_TRY(make_tmap_nhwc(&pl.tW_p31, pl.d_pre31, N, pl.H2, 8, 256, pl.wm3 ? 8 : 4));
+    CRNN_TRY(make_tmap_nhwc(&pl.tW_a3, pl.a3, N, pl.H2, 8, 256, pl.wm3 ? 8 : 4));
+    CRNN_TRY(make_tmap_nhwc(&pl.tW_p32, pl.d_pre32, N, pl.H2, 8, 256, pl.wm3 ? 8 : 4));
+    CRNN_TRY(make_tmap_nhwc(&pl.tW_a3p, pl.a3p, N, pl.H2, 4, 256, pl.wm4 ? 16 : 8));
+    CRNN_TRY(make_tmap_nhwc(&pl.tW_p4a, pl.d_pre4a, N, pl.H2, 4, 512, pl.wm4 ? 16 : 8));
+    CRNN_TRY(make_tmap_nhwc(&pl.tW_a4a, pl.a4a, N, pl.H2, 4, 512, pl.wm4 ? 16 : 8));
+    CRNN_TRY(make_tmap_nhwc(&pl.tW_p4b, pl.d_pre4b, N, pl.H2, 4, 512, pl.wm4 ? 16 : 8));
     // MN-major (TN) operands: box = [64 channels, 64 rows]
     CRNN_TRY(make_tmap_2d_box(&pl.tT_lstm_all, pl.lstm_out, R, 512, 512, 64, 64));
     CRNN_TRY(make_tmap_2d_box(&pl.tT_lstm_fw, pl.lstm_out, R, 256, 512, 64, 64));
@@ -379,7 +392,7 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
   STAGE_MARK();
   // conv2 + ReLU + pool2
   {
-    gemm::Params p = conv_params(N, H1, 16, 64, 128, 128, m->P("conv2/biases"), pl.a2);
+    gemm::Params p = conv_params(N, H1, 16, 64, 128, 128, m->P("conv2/biases"), pl.a2, pl.mg2);
     if (pl.train) {
       p.argmax = pl.am2;
       CRNN_TRY((launch_gemm<128, gemm::A_CONV3, gemm::EPI_RELU_POOL22_T, 6>(pl.tA_c2, m->tB_c2, p, sms, st)));
@@ -390,14 +403,14 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
   STAGE_MARK();
   // conv3_1 + ReLU
   {
-    gemm::Params p = conv_params(N, H2, 8, 128, 256, 256, m->P("conv3_1/biases"), pl.a3);
+    gemm::Params p = conv_params(N, H2, 8, 128, 256, 256, m->P("conv3_1/biases"), pl.a3, pl.mg3);
     if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_RELU, 6>(pl.tA_c31, m->tBh_c31, p, sms, st)));
     else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_RELU, 4>(pl.tA_c31, m->tB_c31, p, sms, st)));
   }
   STAGE_MARK();
   // conv3_2 + ReLU + height pool
   {
-    gemm::Params p = conv_params(N, H2, 8, 256, 256, 256, m->P("conv3_2/biases"), pl.a3p);
+    gemm::Params p = conv_params(N, H2, 8, 256, 256, 256, m->P("conv3_2/biases"), pl.a3p, pl.mg3);
     if (pl.train) {
       p.argmax = pl.am3;
       if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_RELU_POOL12_T, 6>(pl.tA_c32, m->tBh_c32, p, sms, st)));
@@ -412,7 +425,7 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
   const double bn_count = (double)N * H2 * 4;
   // conv4_1 + bias -> batch statistics -> BN + ReLU
   {
-    gemm::Params p = conv_params(N, H2, 4, 256, 512, 256, m->P("conv4_1/biases"), pl.a4a_pre);
+    gemm::Params p = conv_params(N, H2, 4, 256, 512, 256, m->P("conv4_1/biases"), pl.a4a_pre, pl.mg4);
     p.stats = pl.stats;
     if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_STATS, 6>(pl.tA_c41, m->tBh_c41, p, sms, st)));
     else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_STATS, 4>(pl.tA_c41, m->tB_c41, p, sms, st)));
@@ -425,7 +438,7 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
   STAGE_MARK();
   // conv4_2 + bias -> batch statistics -> BN + ReLU + height pool (pool3)
   {
-    gemm::Params p = conv_params(N, H2, 4, 512, 512, 256, m->P("conv4_2/biases"), pl.a4b_pre);
+    gemm::Params p = conv_params(N, H2, 4, 512, 512, 256, m->P("conv4_2/biases"), pl.a4b_pre, pl.mg4);
     p.stats = pl.stats + 1024;
     if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_STATS, 6>(pl.tA_c42, m->tBh_c42, p, sms, st)));
     else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_STATS, 4>(pl.tA_c42, m->tB_c42, p, sms, st)));
@@ -593,6 +606,7 @@ extern "C" int crnn_test_gemm_bf16(const void* A, const void* B, float* D, int M
   p.M = M; p.Nc = Nc;
   p.num_m_tiles = (M + 127) / 128; p.num_n_tiles = Nc / block_n; p.num_k_blocks = K / 64; p.kb_per_shift = p.num_k_blocks;
   p.out = D;
+  if (const char* e = getenv("CRNN_PROBE_SKIP_TMA")) p.debug_skip_tma = (e[0] == '1');
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (block_n == 64) return launch_gemm<64, gemm::A_PLAIN, gemm::EPI_F32, 8>(ta, tb, p, sms, st);
   if (block_n == 128) return launch_gemm<128, gemm::A_PLAIN, gemm::EPI_F32, 6>(ta, tb, p, sms, st);

@@ -45,6 +45,10 @@ struct Plan {
   double* stats;        // [2 layers][2][512]
   float* bn;            // [2 layers][4][512]: scale, shift, mean, invstd
   CUtensorMap tA_c2, tA_c31, tA_c32, tA_c41, tA_c42, tA_c5, tA_x, tA_h[2], tA_l, tA_hall;
+  // conv A maps use 128-position boxes (`mg*` = 1) when a tile's 4 sub-boxes are contiguous rows of one image;
+  // the weight-gradient GEMMs read the same tensors through 64- or 32-position boxes (tW_*)
+  int mg2 = 0, mg3 = 0, mg4 = 0, wm2 = 0, wm3 = 0, wm4 = 0;
+  CUtensorMap tW_a1, tW_a2, tW_a3, tW_a3p, tW_a4a, tW_p4b, tW_p4a, tW_p32, tW_p31, tW_p2;
   // ---- training only -------------------------------------------------------------------------------------------
   bool train = false;
   uint8_t *am1, *am2, *am3;                       // arg-max window indices of pool1 / pool2 / the 1x2 pool after conv3_2
@@ -103,7 +107,8 @@ size_t layout_plan(Plan& pl, int N, int W, uint8_t* base, bool train);
 int prepare_weights(crnn_model* m, cudaStream_t st);
 int ensure_plan(crnn_model* m, int N, int W, void* ws, cudaStream_t st);
 
-static inline gemm::Params conv_params(int N, int H, int Wd, int Cin, int Cout, int block_n, const float* bias, void* out) {
+static inline gemm::Params conv_params(int N, int H, int Wd, int Cin, int Cout, int block_n, const float* bias, void* out,
+                                       int merged = 0) {
   gemm::Params p;
   memset(&p, 0, sizeof(p));
   p.bh = 32 / Wd;
@@ -116,6 +121,7 @@ static inline gemm::Params conv_params(int N, int H, int Wd, int Cin, int Cout, 
   p.Nc = Cout;
   p.bias = bias;
   p.out = out;
+  p.merged = merged;
   return p;
 }
 

@@ -8,14 +8,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from lstm_ctc_ocr_b200 import engine  # noqa: E402
 
 dev = torch.device("cuda:0")
-for (M, Nc, K, bn) in [(300, 256, 512, 512), (1000, 512, 576, 512), (8192, 8192, 8192, 512), (262144, 512, 4608, 512), (8192, 8192, 8192, 256), (8192, 8192, 8192, 128), (8192, 8192, 8192, 64), (262144, 512, 4608, 256), (262144, 512, 2304, 256),
+SKIP = os.environ.get('CRNN_PROBE_SKIP_TMA') == '1'
+for (M, Nc, K, bn) in [(8192, 8192, 8192, 512), (262144, 512, 4608, 512), (8192, 8192, 8192, 256), (8192, 8192, 8192, 128), (8192, 8192, 8192, 64), (262144, 512, 4608, 256), (262144, 512, 2304, 256),
                        (16384, 256, 8192, 256)]:
     A = torch.randn(M, K, device=dev).to(torch.bfloat16)
     B = torch.randn(Nc, K, device=dev).to(torch.bfloat16)
     for _ in range(2):
         D = engine.test_gemm_bf16(A, B, bn)
     torch.cuda.synchronize()
-    if M <= 8192:
+    if M <= 8192 and not SKIP:
         ref = A.float() @ B.float().t()
         print('   rel_err', float((D - ref).abs().max() / ref.abs().max()), flush=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
