@@ -118,13 +118,11 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_con
 
   for (int s = 0; s < p.T; ++s) {
     if (warp_idx == 0) {
-      if (lane == 0 && s > 0) {
+      if (lane < 4 && s > 0) {        // one lane per K-block: the four TMA issues overlap instead of serialising
         fence_proxy_async_all();
         const int hrow = ((s & 1) * 2 + dir) * p.Npad + tile * BLOCK_M;
-        for (int kb = 0; kb < 4; ++kb) {
-          ptx::mbar_arrive_expect_tx(&a_full[kb], BLOCK_M * 128);
-          ptx::tma_load_2d(&tmH, &a_full[kb], smem_a + kb * BLOCK_M * 128, kb * 64, hrow);
-        }
+        ptx::mbar_arrive_expect_tx(&a_full[lane], BLOCK_M * 128);
+        ptx::tma_load_2d(&tmH, &a_full[lane], smem_a + lane * BLOCK_M * 128, lane * 64, hrow);
       }
       __syncwarp();
     } else if (warp_idx == 1) {

@@ -11,6 +11,6 @@ if [ "$1" != "noncu" ]; then
 echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train > gpurun_out/ncu_list.log 2>&1; tail -2 gpurun_out/ncu_list.log
 echo "== ncu full"
-timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:"Li1ELi5E|ctc_loss|Li1ELi3E" -s 12 -c 4 -o gpurun_out/prof_r1 -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log
+timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:"gemm2_kernelILi1ELi5E|ctc_loss|lstm_persistent|gemm_kernelILi128ELi1ELi3E" -s 15 -c 5 -o gpurun_out/prof_r1 -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log
 fi
 ls -la gpurun_out
