@@ -150,3 +150,18 @@ def test_golden_fixture_is_reproducible_from_seeds():
     assert np.allclose(logits, g["logits"], atol=1e-5)
     costs, _ = O.ctc_loss_np(logits, lab, ll, tsl)
     assert np.allclose(costs, g["costs"], rtol=1e-9)
+
+
+def test_eval_line_preparation_and_cli_flags():
+    from lstm_ctc_ocr_b200.lib.lstm.test import decodeRes, prepare_line
+    from lstm_ctc_ocr_b200.lstm import test_net, train_net
+    img = (np.arange(32 * 85) % 256).astype(np.uint8).reshape(32, 85)
+    data, tsl = prepare_line(img)
+    assert data.shape == (1, 88, 32) and data.dtype == np.float32            # right-padded to a multiple of 4
+    assert tsl.tolist() == [85 // 4 - 1] and np.all(data[0, 85:] == 0)
+    assert np.allclose(data[0, :85, :], img.T / 255.0)
+    assert "".join(decodeRes([1, 0, 11, 37, 0])) == "0aA"
+    a = train_net.parse_args(["--network=LSTM_train", "--cfg=./lstm/lstm.yml", "--restore=0", "--set", "TRAIN.BATCH_SIZE", "32"])
+    assert a.network_name == "LSTM_train" and a.restore == 0 and a.set_cfgs == ["TRAIN.BATCH_SIZE", "32"] and a.max_iters == 1000000
+    b = test_net.parse_args(["--network=LSTM_test", "--testDir", "x"])
+    assert b.test_dir == "x" and b.restore == 1

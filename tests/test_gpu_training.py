@@ -151,3 +151,28 @@ def test_solver_loop_reads_like_the_reference_and_learns(tmp_path, capsys):
             assert len(hist2) == 3 and hist2[0] < 0.9 * hist[0]
     finally:
         cfg.TRAIN.LEARNING_RATE, cfg.TRAIN.DISPLAY, cfg.TRAIN.SNAPSHOT_ITERS, cfg.TRAIN.WEIGHT_DECAY = old
+
+
+def test_eval_solver_walks_a_directory_like_the_reference(tmp_path, capsys):
+    """lib/lstm/test.py surface: images named <idx>_<chars>.png, decode, exact-match accuracy print."""
+    from PIL import Image
+    from lstm_ctc_ocr_b200 import synthetic
+    from lstm_ctc_ocr_b200.lib.lstm import test as E, train as T
+    from lstm_ctc_ocr_b200.lib.lstm.utils import gen
+    from lstm_ctc_ocr_b200.lib.networks.factory import get_network
+    from lstm_ctc_ocr_b200.session import Session
+    d = tmp_path / "val"
+    d.mkdir()
+    for i, chars in enumerate(["ab12", "Zx9Q0", "7777"]):
+        Image.fromarray(gen.render_line(chars)).save(str(d / f"{i:08d}_{chars}.png"))
+    net = get_network("LSTM_test")
+    with Session(device=DEV) as sess:
+        sess.assign(net, synthetic.init_params(3))
+        # write a checkpoint through the train solver's snapshot, then evaluate with restore=True
+        ts = T.SolverWrapper(sess, net, None, None, str(tmp_path / "out"), str(tmp_path / "log"))
+        ts.snapshot(sess, 9)
+        sw = E.SolverWrapper(sess, net, None, str(tmp_path / "out"), str(tmp_path / "log"))
+        correct, total = sw.test_model(sess, testDir=str(d), restore=True)
+    out = capsys.readouterr().out
+    assert total == 3 and 0 <= correct <= 3
+    assert "total acc:" in out and "cost time:" in out and "Restoring from" in out
