@@ -11,11 +11,22 @@ namespace {
 // 72 filter taps held in registers; input tile (18 x 34 f32, zero halo) staged in shared memory.
 // ------------------------------------------------------------------------------------------------
 constexpr int C1_ROWS = 8;                         // pooled rows per tile
+constexpr int C1_TILE_ELEMS = (2 * C1_ROWS + 2) * 34;
+
+__device__ __forceinline__ float conv1_fetch(const float* __restrict__ data, int n, int ho0, int W, int i) {
+  // element i of the staged tile: rows 2*ho0-1 .. 2*ho0+16 (18 rows) x cols -1..32 (34), zero outside the image
+  const int r = i / 34, c = i - r * 34;
+  const int gr = 2 * ho0 - 1 + r, gc = c - 1;
+  return (gr >= 0 && gr < W && gc >= 0 && gc < 32) ? __ldg(data + ((size_t)n * W + gr) * 32 + gc) : 0.f;
+}
+
+// TRAIN additionally records the arg-max window index of pool1 (needed by the backward pass).
+template <bool TRAIN>
 __global__ void __launch_bounds__(256) conv1_pool_kernel(const float* __restrict__ data,
                                                          const float* __restrict__ wgt,   // HWIO [3,3,1,64]
                                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                                                          uint8_t* __restrict__ argmax, int N, int W) {
-  __shared__ float s_in[2 * C1_ROWS + 2][36];
+  __shared__ __align__(16) float s_in[2][2 * C1_ROWS + 2][36];      // double buffered: next tile is prefetched during compute
   const int H1 = W >> 1;
   const int tiles_per_img = (H1 + C1_ROWS - 1) / C1_ROWS;
   const int num_tiles = N * tiles_per_img;
@@ -31,19 +42,27 @@ __global__ void __launch_bounds__(256) conv1_pool_kernel(const float* __restrict
 #pragma unroll
   for (int j = 0; j < 8; ++j) br[j] = __ldg(bias + cg * 8 + j);
 
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+  int tile = blockIdx.x;
+  if (tile < num_tiles) {
+    const int n = tile / tiles_per_img, ho0 = (tile - n * tiles_per_img) * C1_ROWS;
+    for (int i = threadIdx.x; i < C1_TILE_ELEMS; i += 256) s_in[0][i / 34][i % 34] = conv1_fetch(data, n, ho0, W, i);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (; tile < num_tiles; tile += gridDim.x) {
     const int n = tile / tiles_per_img;
     const int ho0 = (tile - n * tiles_per_img) * C1_ROWS;
-    __syncthreads();
-    // stage rows 2*ho0-1 .. 2*ho0+16 (18 rows) x cols -1..32 (34)
-    for (int i = threadIdx.x; i < (2 * C1_ROWS + 2) * 34; i += 256) {
-      const int r = i / 34, c = i - r * 34;
-      const int gr = 2 * ho0 - 1 + r, gc = c - 1;
-      float v = 0.f;
-      if (gr >= 0 && gr < W && gc >= 0 && gc < 32) v = __ldg(data + ((size_t)n * W + gr) * 32 + gc);
-      s_in[r][c] = v;
+    // prefetch the next tile into registers (<= 3 elements per thread); stored to the other buffer after the compute
+    const int nxt = tile + gridDim.x;
+    float pre[3];
+    if (nxt < num_tiles) {
+      const int nn = nxt / tiles_per_img, nho0 = (nxt - nn * tiles_per_img) * C1_ROWS;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int i = threadIdx.x + 256 * k;
+        pre[k] = (i < C1_TILE_ELEMS) ? conv1_fetch(data, nn, nho0, W, i) : 0.f;
+      }
     }
-    __syncthreads();
 #pragma unroll 1
     for (int pp = 0; pp < 4; ++pp) {
       const int pidx = slot + 32 * pp;              // 0..127
@@ -51,9 +70,11 @@ __global__ void __launch_bounds__(256) conv1_pool_kernel(const float* __restrict
       const int ho = ho0 + hol;
       float patch[4][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) patch[i][j] = s_in[2 * hol + i][2 * wo + j];
+      for (int i = 0; i < 4; ++i) {
+        const float2 a = *reinterpret_cast<const float2*>(&s_in[buf][2 * hol + i][2 * wo]);
+        const float2 c = *reinterpret_cast<const float2*>(&s_in[buf][2 * hol + i][2 * wo + 2]);
+        patch[i][0] = a.x; patch[i][1] = a.y; patch[i][2] = c.x; patch[i][3] = c.y;
+      }
       float best[8];
       uint32_t bidx[8];
 #pragma unroll
@@ -75,7 +96,11 @@ __global__ void __launch_bounds__(256) conv1_pool_kernel(const float* __restrict
             }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            if (acc[j] > best[j]) { best[j] = acc[j]; bidx[j] = dy * 2 + dx; }     // strict '>' keeps the first max
+            if (TRAIN) {
+              if (acc[j] > best[j]) { best[j] = acc[j]; bidx[j] = dy * 2 + dx; }     // strict '>' keeps the first max
+            } else {
+              best[j] = fmaxf(best[j], acc[j]);
+            }
           }
         }
       if (ho < H1) {
@@ -86,7 +111,7 @@ __global__ void __launch_bounds__(256) conv1_pool_kernel(const float* __restrict
         o.w = ptx::pack_bf16x2(fmaxf(best[6] + br[6], 0.f), fmaxf(best[7] + br[7], 0.f));
         const size_t oo = (((size_t)n * H1 + ho) * 16 + wo) * 64 + cg * 8;
         *reinterpret_cast<uint4*>(out + oo) = o;
-        if (argmax != nullptr) {
+        if (TRAIN) {
           uint2 a;
           a.x = bidx[0] | (bidx[1] << 8) | (bidx[2] << 16) | (bidx[3] << 24);
           a.y = bidx[4] | (bidx[5] << 8) | (bidx[6] << 16) | (bidx[7] << 24);
@@ -94,6 +119,15 @@ __global__ void __launch_bounds__(256) conv1_pool_kernel(const float* __restrict
         }
       }
     }
+    if (nxt < num_tiles) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int i = threadIdx.x + 256 * k;
+        if (i < C1_TILE_ELEMS) s_in[buf ^ 1][i / 34][i % 34] = pre[k];
+      }
+    }
+    __syncthreads();
+    buf ^= 1;
   }
 }
 
@@ -254,7 +288,8 @@ int launch_conv1_pool(const float* data, const float* w, const float* b, __nv_bf
                       int num_sms, cudaStream_t st) {
   const int tiles = N * (((W >> 1) + C1_ROWS - 1) / C1_ROWS);
   const int grid = tiles < num_sms * 2 ? tiles : num_sms * 2;
-  conv1_pool_kernel<<<grid, 256, 0, st>>>(data, w, b, out, argmax, N, W);
+  if (argmax != nullptr) conv1_pool_kernel<true><<<grid, 256, 0, st>>>(data, w, b, out, argmax, N, W);
+  else conv1_pool_kernel<false><<<grid, 256, 0, st>>>(data, w, b, out, argmax, N, W);
   CUDA_TRY(cudaGetLastError());
   return CRNN_OK;
 }

@@ -98,35 +98,38 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
 
   if (warp_idx == 1 && lane == 0) ptx::mbar_wait(b_full, 0);
 
-  int stage = 0;
-  uint32_t phase = 0;        // ring state (used by the producer lane and, separately, by the MMA lane)
+  uint32_t prod_parity = 0;  // producer lane l: parity of ring slot l (flips on every use of that slot)
+  uint32_t mma_parity = 0;   // MMA lane: bit s = parity of ring slot s
   int nmma = 0;              // number of accumulations completed (acc_full parity)
 
   for (int s = p.T - 1; s >= 0; --s) {
     const bool has_rec = (s < p.T - 1);
     if (warp_idx == 0) {
-      if (lane == 0 && has_rec) {
+      // K-block kb of every step lives in ring slot kb % STAGES.  Lanes 0..STAGES-1 own one slot each and issue their
+      // K-blocks in lock-step (one SIMD cp.async.bulk.tensor per round instead of 16 serial single-thread issues).
+      if (lane < STAGES && has_rec) {
         lstm::fence_proxy_async_all();
         const int zrow = ((((s + 1) & 1) * 2 + dir) * p.Npad) + tile * BLOCK_M;
-        for (int kb = 0; kb < 16; ++kb) {
-          ptx::mbar_wait(&a_empty[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&a_full[stage], A_STAGE);
-          ptx::tma_load_2d(&tmDz, &a_full[stage], smem_a + stage * A_STAGE, kb * 64, zrow);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        for (int kb = lane; kb < 16; kb += STAGES) {
+          ptx::mbar_wait(&a_empty[lane], prod_parity ^ 1);
+          ptx::mbar_arrive_expect_tx(&a_full[lane], A_STAGE);
+          ptx::tma_load_2d(&tmDz, &a_full[lane], smem_a + lane * A_STAGE, kb * 64, zrow);
+          prod_parity ^= 1;
         }
       }
       __syncwarp();
     } else if (warp_idx == 1) {
       if (lane == 0 && has_rec) {
         for (int kb = 0; kb < 16; ++kb) {
-          ptx::mbar_wait(&a_full[stage], phase);
+          const int slot = kb % STAGES;
+          ptx::mbar_wait(&a_full[slot], (mma_parity >> slot) & 1u);
+          mma_parity ^= (1u << slot);
           ptx::tc_fence_after();
-          const uint64_t a_desc = ptx::make_desc_k_sw128(ptx::smem_u32(smem_a + stage * A_STAGE));
+          const uint64_t a_desc = ptx::make_desc_k_sw128(ptx::smem_u32(smem_a + slot * A_STAGE));
           const uint64_t b_desc = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b + kb * UPC * 128));
 #pragma unroll
           for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0);
-          ptx::tc_commit(&a_empty[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          ptx::tc_commit(&a_empty[slot]);
         }
         ptx::tc_commit(acc_full);
       }
