@@ -15,47 +15,48 @@ _NP2T = {np.dtype("float32"): torch.float32, np.dtype("int32"): torch.int32}
 
 
 class _Pinned(object):
-    """Host->device staging.  Large C-contiguous numpy inputs are page-locked IN PLACE (cudaHostRegister, cached by address:
-    a feeder that reuses its batch buffers pays the registration once) and DMA'd directly; everything else goes through
-    reusable pinned staging buffers."""
-    REGISTER_MIN_BYTES = 1 << 20
-    MAX_REGISTERED = 32
+    """Host->device staging.  Default: copy into reusable pinned staging buffers, then async DMA.  A LARGE C-contiguous
+    numpy input that is fed again from the same buffer (a feeder reusing its batch buffers) is page-locked IN PLACE on its
+    second sighting (cudaHostRegister) and DMA'd directly from then on.  The registry keeps a reference to every registered
+    array, so its memory cannot be freed or reused while it is pinned; the oldest entry is unregistered on overflow."""
+    REGISTER_MIN_BYTES = 8 << 20
+    MAX_REGISTERED = 16
 
     def __init__(self):
         self.bufs = {}
-        self.registered = {}          # (ptr, nbytes) -> True, insertion-ordered
+        self.registered = {}          # (ptr, nbytes) -> array (keeps the memory alive), insertion-ordered
+        self.seen_once = {}           # (ptr, nbytes) -> True, bounded
 
-    def _register(self, arr):
+    def _registered(self, arr):
         key = (arr.ctypes.data, arr.nbytes)
         if key in self.registered:
             return True
-        try:
-            rt = torch.cuda.cudart()
-            if len(self.registered) >= self.MAX_REGISTERED:
-                old, _ = next(iter(self.registered.items()))
-                rt.cudaHostUnregister(old[0])
-                del self.registered[old]
-            err = rt.cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)
-            if int(err) != 0:
-                return False
-            self.registered[key] = True
-            return True
-        except Exception:
+        if key not in self.seen_once:
+            if len(self.seen_once) > 64:
+                self.seen_once.pop(next(iter(self.seen_once)))
+            self.seen_once[key] = True
             return False
+        rt = torch.cuda.cudart()
+        if len(self.registered) >= self.MAX_REGISTERED:
+            old = next(iter(self.registered))
+            rt.cudaHostUnregister(old[0])
+            del self.registered[old]
+        if int(rt.cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)) != 0:
+            return False
+        self.registered[key] = arr
+        self.seen_once.pop(key, None)
+        return True
 
     def close(self):
-        try:
-            rt = torch.cuda.cudart()
-            for (ptr, _n) in list(self.registered):
-                rt.cudaHostUnregister(ptr)
-        except Exception:
-            pass
+        rt = torch.cuda.cudart()
+        for (ptr, _n) in list(self.registered):
+            rt.cudaHostUnregister(ptr)
         self.registered.clear()
 
     def stage(self, name, arr, device):
         arr = np.ascontiguousarray(arr)
         tdt = _NP2T[arr.dtype]
-        if arr.nbytes >= self.REGISTER_MIN_BYTES and arr.flags.writeable and self._register(arr):
+        if arr.nbytes >= self.REGISTER_MIN_BYTES and arr.flags.owndata and self._registered(arr):
             return torch.from_numpy(arr).to(device, non_blocking=True)
         t = self.bufs.get(name)
         if t is None or t.numel() < arr.size or t.dtype != tdt:
