@@ -30,11 +30,13 @@ def _font_path():
     return None
 
 
-def render_line(chars, height=60, width=160):
+def render_line(chars, height=60, width=None):
     """Gray uint8 HxW image of the text (stand-in for ImageCaptcha.generate_image + gray conversion, gen.py:31-37,79)."""
     from PIL import Image, ImageDraw, ImageFont
     fp = _font_path()
     font = ImageFont.truetype(fp, 42) if fp else ImageFont.load_default()
+    if width is None:                      # wide enough for the text: batches then mix widths (exercises the padding contract)
+        width = int(sum(font.getlength(c) for c in chars)) + 28
     img = Image.new("L", (width, height), color=random.randint(180, 255))
     d = ImageDraw.Draw(img)
     x = random.randint(2, 12)

@@ -24,14 +24,15 @@ from lstm_ctc_ocr_b200.session import Session  # noqa: E402
 def main():
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 600
     n_eval = int(sys.argv[2]) if len(sys.argv) > 2 else 512
-    cfg.TRAIN.LEARNING_RATE, cfg.TRAIN.DISPLAY, cfg.TRAIN.SNAPSHOT_ITERS, cfg.TRAIN.WEIGHT_DECAY = 1e-3, 50, 10 ** 9, 1e-5
+    lr = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-4
+    cfg.TRAIN.LEARNING_RATE, cfg.TRAIN.DISPLAY, cfg.TRAIN.SNAPSHOT_ITERS, cfg.TRAIN.WEIGHT_DECAY = lr, 500, 10 ** 9, 1e-5
     cfg.TRAIN.BATCH_SIZE, cfg.VAL.VAL_STEP, cfg.VAL.PRINT_NUM = 128, 10 ** 9, 0
     import random
     random.seed(3)
     np.random.seed(3)
     # pre-render a pool of batches on the host (rendering is the slow part), cycle through them
     t0 = time.time()
-    pool = [next(gen.generator(batch_size=cfg.TRAIN.BATCH_SIZE, render=True)) for _ in range(24)]
+    pool = [next(gen.generator(batch_size=cfg.TRAIN.BATCH_SIZE, render=True)) for _ in range(64)]
     held = [next(gen.generator(batch_size=128, render=True)) for _ in range(n_eval // 128)]
     print(f"rendered {len(pool)} train + {len(held)} eval batches in {time.time() - t0:.1f}s", flush=True)
 
@@ -48,8 +49,8 @@ def main():
         hist = sw.train_model(sess, iters + 1, restore=False, train_gen=cyc(), val_gen=cyc())
         torch.cuda.synchronize()
         out["train_seconds"] = time.time() - t0
-        out["loss_curve"] = [round(float(np.mean(hist[i:i + 25])), 4) for i in range(0, len(hist), 25)]
-        print("loss curve (mean of 25):", out["loss_curve"], flush=True)
+        out["loss_curve"] = [round(float(np.mean(hist[i:i + 100])), 3) for i in range(0, len(hist), 100)]
+        print("loss curve (mean of 100):", out["loss_curve"], flush=True)
         # ---- held-out accuracy + oracle agreement on the trained weights
         loss_h, dec_h = net.build_loss()
         params = sess.variables(net)
@@ -80,7 +81,7 @@ def main():
                    clear_margin_agreement=1.0)
     print(json.dumps(out), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "train_demo.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"train_demo_lr{lr:g}.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":
