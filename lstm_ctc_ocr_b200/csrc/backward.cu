@@ -152,7 +152,8 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
     {  // dW_x (rows 0..511 of both [768,1024] matrices) = a5^T dz
       gemm_tn::Params p = tn_plain(512, 2048, R, G(fw + "/weights"), 1024);
       p.num_n_tiles = 8; p.lstm_cols = 1; p.dir_stride = dW;
-      CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_PLAIN, 4>(pl.tT_a5, pl.tT_dz, p, sms, st)));
+      if (m->use_2cta) { p.num_m_tiles = 2; CRNN_TRY((launch_gemm_tn2<gemm_tn::TN_PLAIN, 6>(pl.tT_a5, pl.tT_dz, p, sms, st))); }
+      else CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_PLAIN, 4>(pl.tT_a5, pl.tT_dz, p, sms, st)));
     }
     {  // dW_h forward direction: previous step = frame t-1
       gemm_tn::Params p = tn_plain(256, 1024, R, G(fw + "/weights"), 1024);
@@ -179,7 +180,8 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   for (int r = 0; r < 2; ++r) {
     gemm_tn::Params p = tn_plain(1024, 512, R, G("conv5/weights") + (size_t)r * 1024 * 512, 512);
     p.num_n_tiles = 2; p.a_row_shift = r;
-    CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_PLAIN, 4>(pl.tT_a4b, pl.tT_da5, p, sms, st)));
+    if (m->use_2cta) { p.num_m_tiles = 4; CRNN_TRY((launch_gemm_tn2<gemm_tn::TN_PLAIN, 6>(pl.tT_a4b, pl.tT_da5, p, sms, st))); }
+    else CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_PLAIN, 4>(pl.tT_a4b, pl.tT_da5, p, sms, st)));
   }
   {
     gemm::Params p;
@@ -201,7 +203,8 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   {
     gemm_tn::Params p = tn_conv(N, H2, 4, 512, 512, G("conv4_2/weights"), pl.wm4);
     p.num_n_tiles = 2;
-    CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tW_a4a, pl.tW_p4b, p, sms, st)));
+    if (m->use_2cta) { p.num_m_tiles = 2; CRNN_TRY((launch_gemm_tn2<gemm_tn::TN_CONV, 6>(pl.tW_a4a, pl.tW_p4b, p, sms, st))); }
+    else CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tW_a4a, pl.tW_p4b, p, sms, st)));
   }
   BMARK();
   {
@@ -219,7 +222,8 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   {
     gemm_tn::Params p = tn_conv(N, H2, 4, 256, 512, G("conv4_1/weights"), pl.wm4);
     p.num_n_tiles = 2;
-    CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tW_a3p, pl.tW_p4a, p, sms, st)));
+    if (m->use_2cta) { p.num_m_tiles = 1; CRNN_TRY((launch_gemm_tn2<gemm_tn::TN_CONV, 6>(pl.tW_a3p, pl.tW_p4a, p, sms, st))); }
+    else CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tW_a3p, pl.tW_p4a, p, sms, st)));
   }
   BMARK();
   {
@@ -235,7 +239,8 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   {
     gemm_tn::Params p = tn_conv(N, H2, 8, 256, 256, G("conv3_2/weights"), pl.wm3);
     p.num_n_tiles = 1;
-    CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tW_a3, pl.tW_p32, p, sms, st)));
+    if (m->use_2cta) { p.num_m_tiles = 1; CRNN_TRY((launch_gemm_tn2<gemm_tn::TN_CONV, 6>(pl.tW_a3, pl.tW_p32, p, sms, st))); }
+    else CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tW_a3, pl.tW_p32, p, sms, st)));
   }
   BMARK();
   {

@@ -249,49 +249,129 @@ __global__ void __launch_bounds__(256) unpool_relu_bwd_kernel(const uint4* __res
   }
 }
 
-// ---- conv1 weight/bias gradient (Cin = 1, K = 9: SIMT).  d_a1 [N,H1,16,64] pooled gradient, a1 pooled activation
-// (ReLU mask), am1 window index; data [N,W,32].   dW1[tap][co] += data[2ho+dy+r-1][2wo+dx+s-1] * g ; db1[co] += g
+// ---- conv1 weight/bias gradient (Cin = 1, K = 9: SIMT), pool1 + ReLU backward folded in.
+// d_a1 [N,H1,16,64] pooled gradient, a1 pooled activation (ReLU mask), am1 window index (0..3 = dy*2+dx); data [N,W,32].
+//   dW1[r][s][co] += data[2ho+dy+r-1][2wo+dx+s-1] * g     db1[co] += g        (g = d_a1 where a1 > 0)
+// Same tiling as the forward conv1 kernel: tile = one image x 8 pooled rows x 16 pooled cols, input tile in shared memory,
+// thread = 8 channels x 4 pooled positions.  The window index differs per channel, so instead of indexing the patch
+// dynamically every window position k gets the masked gradient (g if idx == k else 0): 36 FMAs per channel, no branches.
+constexpr int C1W_ROWS = 8;
 __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const __nv_bfloat16* __restrict__ d_a1, const __nv_bfloat16* __restrict__ a1,
                                                           const uint8_t* __restrict__ am1, const float* __restrict__ data,
                                                           float* __restrict__ dW, float* __restrict__ db, int N, int W) {
+  __shared__ float s_in[2 * C1W_ROWS + 2][36];
+  __shared__ float s_red[8][8][80];
   const int H1 = W >> 1;
-  const int co = threadIdx.x & 63;
-  const int sub = threadIdx.x >> 6;                        // 4 position slots per block
-  float acc[10];
+  const int tiles_per_img = (H1 + C1W_ROWS - 1) / C1W_ROWS;
+  const int num_tiles = N * tiles_per_img;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cg = lane & 7;
+  const int slot = warp * 4 + (lane >> 3);
+  float acc[9][8], accb[8];
 #pragma unroll
-  for (int i = 0; i < 10; ++i) acc[i] = 0.f;
-  const size_t npos = (size_t)N * H1 * 16;
-  for (size_t pos = (size_t)blockIdx.x * 4 + sub; pos < npos; pos += (size_t)gridDim.x * 4) {
-    const float y = __bfloat162float(a1[pos * 64 + co]);
-    if (y <= 0.f) continue;
-    const float g = __bfloat162float(d_a1[pos * 64 + co]);
-    const int idx = am1[pos * 64 + co];
-    const int wo = (int)(pos & 15);
-    const size_t nh = pos >> 4;
-    const int ho = (int)(nh % H1);
-    const size_t n = nh / H1;
-    const int hr = 2 * ho + (idx >> 1), wc = 2 * wo + (idx & 1);
+  for (int k = 0; k < 9; ++k)
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+    for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int gr = hr + r - 1, gc = wc + s - 1;
-        const float x = (gr >= 0 && gr < W && gc >= 0 && gc < 32) ? __ldg(data + (n * W + gr) * 32 + gc) : 0.f;
-        acc[r * 3 + s] = fmaf(x, g, acc[r * 3 + s]);
-      }
-    acc[9] += g;
-  }
-  __shared__ float red[4][10][64];
-#pragma unroll
-  for (int i = 0; i < 10; ++i) red[sub][i][co] = acc[i];
-  __syncthreads();
-  if (sub == 0) {
-#pragma unroll
-    for (int i = 0; i < 10; ++i) {
-      const float v = red[0][i][co] + red[1][i][co] + red[2][i][co] + red[3][i][co];
-      if (i < 9) atomicAdd(dW + i * 64 + co, v);
-      else atomicAdd(db + co, v);
+  for (int j = 0; j < 8; ++j) accb[j] = 0.f;
+
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int n = tile / tiles_per_img;
+    const int ho0 = (tile - n * tiles_per_img) * C1W_ROWS;
+    __syncthreads();
+    for (int i = threadIdx.x; i < (2 * C1W_ROWS + 2) * 34; i += 256) {
+      const int r = i / 34, c = i - r * 34;
+      const int gr = 2 * ho0 - 1 + r, gc = c - 1;
+      s_in[r][c] = (gr >= 0 && gr < W && gc >= 0 && gc < 32) ? __ldg(data + ((size_t)n * W + gr) * 32 + gc) : 0.f;
     }
+    // this thread's 4 pooled positions: gradient, activation and window index for 8 channels each (loads issued together)
+    uint4 gq[4], yq[4];
+    uint2 iq[4];
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp) {
+      const int pidx = slot + 32 * pp;
+      const int hol = pidx >> 4, wo = pidx & 15;
+      const int ho = ho0 + hol;
+      if (ho < H1) {
+        const size_t oo = (((size_t)n * H1 + ho) * 16 + wo) * 64 + cg * 8;
+        gq[pp] = __ldg(reinterpret_cast<const uint4*>(d_a1 + oo));
+        yq[pp] = __ldg(reinterpret_cast<const uint4*>(a1 + oo));
+        iq[pp] = __ldg(reinterpret_cast<const uint2*>(am1 + oo));
+      } else {
+        gq[pp] = make_uint4(0u, 0u, 0u, 0u); yq[pp] = gq[pp]; iq[pp] = make_uint2(0u, 0u);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp) {
+      const int pidx = slot + 32 * pp;
+      const int hol = pidx >> 4, wo = pidx & 15;
+      float g[8], y[8];
+      unpack8(gq[pp], g);
+      unpack8(yq[pp], y);
+      const uint32_t idx[8] = {iq[pp].x & 255u, (iq[pp].x >> 8) & 255u, (iq[pp].x >> 16) & 255u, iq[pp].x >> 24,
+                               iq[pp].y & 255u, (iq[pp].y >> 8) & 255u, (iq[pp].y >> 16) & 255u, iq[pp].y >> 24};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { g[j] = (y[j] > 0.f) ? g[j] : 0.f; accb[j] += g[j]; }
+      float patch[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 p0 = *reinterpret_cast<const float2*>(&s_in[2 * hol + i][2 * wo]);
+        const float2 p1 = *reinterpret_cast<const float2*>(&s_in[2 * hol + i][2 * wo + 2]);
+        patch[i][0] = p0.x; patch[i][1] = p0.y; patch[i][2] = p1.x; patch[i][3] = p1.y;
+      }
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          float gs[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gs[j] = (idx[j] == (uint32_t)(dy * 2 + dx)) ? g[j] : 0.f;
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s2 = 0; s2 < 3; ++s2) {
+              const float x = patch[dy + r][dx + s2];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[r * 3 + s2][j] = fmaf(x, gs[j], acc[r * 3 + s2][j]);
+            }
+        }
+    }
+  }
+  // block reduction: lanes sharing a channel group (lane ^ 8, ^ 16), then the 8 warps through shared memory
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = acc[k][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      acc[k][j] = v;
+    }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float v = accb[j];
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    accb[j] = v;
+  }
+  __syncthreads();
+  if (lane < 8) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_red[warp][cg][k * 8 + j] = acc[k][j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_red[warp][cg][72 + j] = accb[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 8 * 80; i += 256) {
+    const int g8 = i / 80, e = i - g8 * 80;
+    float v = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) v += s_red[w8][g8][e];
+    if (e < 72) atomicAdd(dW + (e >> 3) * 64 + g8 * 8 + (e & 7), v);
+    else atomicAdd(db + g8 * 8 + (e - 72), v);
   }
 }
 
@@ -433,7 +513,8 @@ int launch_unpool_relu_bwd(int win, const __nv_bfloat16* dpool, const __nv_bfloa
 }
 int launch_conv1_wgrad(const __nv_bfloat16* d_a1, const __nv_bfloat16* a1, const uint8_t* am1, const float* data, float* dW, float* db,
                        int N, int W, cudaStream_t st) {
-  conv1_wgrad_kernel<<<1184, 256, 0, st>>>(d_a1, a1, am1, data, dW, db, N, W);
+  const int tiles = N * (((W >> 1) + C1W_ROWS - 1) / C1W_ROWS);
+  conv1_wgrad_kernel<<<tiles < 296 ? tiles : 296, 256, 0, st>>>(d_a1, a1, am1, data, dW, db, N, W);
   LAUNCH_CHECK();
 }
 int launch_dgrad_weight(const float* w, __nv_bfloat16* bd, int Cin, int Cout, cudaStream_t st) {

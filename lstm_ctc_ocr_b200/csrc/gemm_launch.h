@@ -60,3 +60,28 @@ static int launch_gemm_tn(const CUtensorMap& a, const CUtensorMap& b, gemm_tn::P
   CUDA_TRY(cudaGetLastError());
   return CRNN_OK;
 }
+
+// 2-CTA weight-gradient GEMM: p.num_m_tiles must count 256-row PAIRS and p.num_n_tiles 256-column tiles.
+template <int AM, int ST>
+static int launch_gemm_tn2(const CUtensorMap& a, const CUtensorMap& b, gemm_tn::Params p, int num_sms, cudaStream_t st) {
+  auto kern = gemm_tn::gemm_tn2_kernel<AM, ST>;
+  constexpr int smem = gemm_tn::Smem2<ST>::BYTES;
+  static bool attr = false;
+  if (!attr) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  const int tiles = p.num_taps * p.num_m_tiles * p.num_n_tiles;
+  const int max_clusters = num_sms / 2;
+  if (p.k_splits <= 0) {
+    int s = (3 * max_clusters + tiles - 1) / tiles;
+    if (s > p.k_blocks_total) s = p.k_blocks_total;
+    if (s < 1) s = 1;
+    p.k_splits = s;
+  }
+  const int items = tiles * p.k_splits;
+  const int clusters = items < max_clusters ? items : max_clusters;
+  kern<<<2 * clusters, gemm_tn::NUM_THREADS, smem, st>>>(a, b, p);
+  CUDA_TRY(cudaGetLastError());
+  return CRNN_OK;
+}

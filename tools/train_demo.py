@@ -32,7 +32,8 @@ def main():
     np.random.seed(3)
     # pre-render a pool of batches on the host (rendering is the slow part), cycle through them
     t0 = time.time()
-    pool = [next(gen.generator(batch_size=cfg.TRAIN.BATCH_SIZE, render=True)) for _ in range(64)]
+    npool = int(sys.argv[4]) if len(sys.argv) > 4 else 320
+    pool = [next(gen.generator(batch_size=cfg.TRAIN.BATCH_SIZE, render=True)) for _ in range(npool)]
     held = [next(gen.generator(batch_size=128, render=True)) for _ in range(n_eval // 128)]
     print(f"rendered {len(pool)} train + {len(held)} eval batches in {time.time() - t0:.1f}s", flush=True)
 
@@ -56,6 +57,15 @@ def main():
         params = sess.variables(net)
         from oracle import crnn_oracle as O      # checker only
         p64 = O.to_torch({k: v.astype(np.float64) for k, v in params.items()})
+        # accuracy on lines the model was trained on (decode correctness) ...
+        tr_ok = tr_n = 0
+        for (imgs, lab, ll, tsl) in pool[:4]:
+            feed = {net.data: np.array(imgs), net.labels: np.array(lab), net.time_step_len: np.array(tsl), net.labels_len: np.array(ll), net.keep_prob: 1.0}
+            res = sess.run(dec_h, feed_dict=feed)
+            org = sw.restoreLabel(lab, ll)
+            tr_ok += accuracy_calculation(org, res, isPrint=False) * len(org); tr_n += len(org)
+        out["train_pool_accuracy"] = tr_ok / tr_n
+        # ... and on held-out renders, plus agreement with the fp64 oracle
         acc_n = agree = clear_n = total = 0
         for (imgs, lab, ll, tsl) in held:
             data = np.array(imgs)
@@ -77,7 +87,7 @@ def main():
                 if np.all(margin[:tsl[n], n] > 2 * err[:tsl[n], n].max()):
                     clear_n += 1
                     assert got == ref[n], "decode differs from the oracle on a sample whose margins exceed the logit error"
-        out.update(eval_lines=total, accuracy=acc_n / total, decode_agreement_with_oracle=agree / total, clear_margin_lines=clear_n,
+        out.update(eval_lines=total, train_pool_lines=len(pool) * cfg.TRAIN.BATCH_SIZE, heldout_accuracy=acc_n / total, decode_agreement_with_oracle=agree / total, clear_margin_lines=clear_n,
                    clear_margin_agreement=1.0)
     print(json.dumps(out), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
