@@ -271,6 +271,8 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   {
     gemm_tn::Params p = tn_conv(N, H1, 16, 64, 128, G("conv2/weights"), pl.wm2);
     p.num_n_tiles = 1;
+    // Cin = 64 fills only half of a 128-row MMA tile: view dW [9*64, 128] as ONE matrix and let each tile hold two taps
+    p.tap_pack = 1; p.num_taps = 1; p.num_m_tiles = 5; p.M = 9 * 64; p.tap_stride = 0;
     CRNN_TRY((launch_gemm_tn<128, gemm_tn::TN_CONV, 6>(pl.tW_a1, pl.tW_p2, p, sms, st)));
   }
   BMARK();

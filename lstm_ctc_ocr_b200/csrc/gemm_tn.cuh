@@ -34,6 +34,7 @@ struct Params {
   // TN_CONV geometry
   int sb_per_img, bh, Wd, H, Nimg, Cin;
   int merged, kb_per_img;                    // TN_CONV: 64-position boxes (2*bh rows) when H % (2*bh) == 0
+  int tap_pack;                              // TN_CONV with Cin == 64: an M tile packs TWO taps (rows = (tap, ci)) -> 5 tiles, not 9 half-empty ones
   int a_row_shift;                           // TN_PLAIN: A rows are read at k + a_row_shift (conv5's second tap)
   // output
   float* out;
@@ -123,8 +124,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         int tap, m_blk, n_blk, kb0, kb1;
         decode(item, tap, m_blk, n_blk, kb0, kb1);
-        const int r = tap / 3, s = tap - 3 * r;
-        const int ccol = isA ? (m_blk * BLOCK_M + 64 * j) : (n_blk * BLOCK_N + 64 * j);
+        int r = tap / 3, s = tap - 3 * r;
+        int ccol = isA ? (m_blk * BLOCK_M + 64 * j) : (n_blk * BLOCK_N + 64 * j);
+        if (AMODE == TN_CONV && p.tap_pack && isA) {       // A block j of tile m_blk is tap 2*m_blk + j, channels 0..63
+          const int tp = min(2 * m_blk + j, 8);             // the 10th (non-existent) tap re-reads tap 8; its rows are masked
+          r = tp / 3; s = tp - 3 * r; ccol = 0;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           if (lane == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], A_STAGE + B_STAGE);

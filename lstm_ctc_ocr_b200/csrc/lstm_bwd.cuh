@@ -9,7 +9,8 @@
 // Cluster of 8 CTAs per (direction, 128-sample tile); CTA `rank` owns 32 hidden units: it keeps dc for them in
 // registers, holds W_h[units, all 1024 gate columns] (64 KB bf16, K-major over gates) resident in shared memory, and per
 // step computes dh_rec[128 x 32] = dz_{s+1}[128 x 1024] * W_h^T on tensor cores (64 x tcgen05.mma 128x32x16), streaming
-// dz_{s+1} (written to global/L2 by the whole cluster one step earlier) through a 6-stage TMA ring.
+// dz_{s+1} (written to global/L2 by the whole cluster one step earlier) through a 6-stage TMA ring.  The tile is identical
+// for the 8 CTAs of a cluster, so each K-block is read from L2 ONCE and TMA-multicast into all 8 shared memories.
 // Outputs: dz for every (sample, frame) in FRAME order (`dz_all`, consumed by the dW_x / dW_h / dx GEMMs).
 #pragma once
 #include <cuda.h>
@@ -70,7 +71,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
   if (warp_idx == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmDz);
     ptx::prefetch_tmap(&tmW);
-    for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], CS); }   // slot free = all 8 CTAs consumed it
     ptx::mbar_init(b_full, 1);
     ptx::mbar_init(acc_full, 1);
     ptx::fence_barrier_init();
@@ -111,9 +112,12 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
         lstm::fence_proxy_async_all();
         const int zrow = ((((s + 1) & 1) * 2 + dir) * p.Npad) + tile * BLOCK_M;
         for (int kb = lane; kb < 16; kb += STAGES) {
+          // all 8 CTAs of the cluster need the SAME dz tile: CTA (kb % 8) loads K-block kb once and multicasts it; every
+          // CTA arms its own barrier.  a_empty[slot] counts the MMA commits of all 8 CTAs (multicast commit below).
           ptx::mbar_wait(&a_empty[lane], prod_parity ^ 1);
           ptx::mbar_arrive_expect_tx(&a_full[lane], A_STAGE);
-          ptx::tma_load_2d(&tmDz, &a_full[lane], smem_a + lane * A_STAGE, kb * 64, zrow);
+          if ((kb & (CS - 1)) == rank)
+            ptx::tma_load_2d_mc(&tmDz, &a_full[lane], smem_a + lane * A_STAGE, kb * 64, zrow, (uint16_t)0xFF);
           prod_parity ^= 1;
         }
       }
@@ -129,7 +133,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
           const uint64_t b_desc = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b + kb * UPC * 128));
 #pragma unroll
           for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0);
-          ptx::tc_commit(&a_empty[slot]);
+          ptx::tc_commit_mc(&a_empty[slot], (uint16_t)0xFF);
         }
         ptx::tc_commit(acc_full);
       }

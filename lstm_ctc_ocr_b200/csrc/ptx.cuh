@@ -196,6 +196,20 @@ __device__ __forceinline__ void tc_commit_2cta_mc(uint64_t* bar, uint16_t cta_ma
                "h"(cta_mask)
                : "memory");
 }
+// tcgen05.commit (1-CTA MMAs) arriving on the barrier at this smem offset in EVERY CTA of `cta_mask`
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+// TMA load multicast: the box lands at the same smem offset, and completes on the mbarrier at the same offset, in every CTA
+// of `cta_mask` (one L2 read feeds the whole cluster)
+__device__ __forceinline__ void tma_load_2d_mc(const void* tmap, uint64_t* bar, void* dst, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
 // TMA loads into THIS CTA's smem whose completion bytes are credited to an mbarrier given by shared::cluster address
 // (the leader CTA's full barrier)
 __device__ __forceinline__ void tma_load_2d_2cta(const void* tmap, uint32_t bar_cluster_addr, void* dst, int c0, int c1) {
