@@ -6,11 +6,14 @@
 //   dh = d_out[t] + dz_{s+1} W_h^T          dc = dc_{s+1->s} + dh * o * (1 - tanh(c_s)^2)
 //   do = dh * tanh(c_s) * o(1-o)   di = dc * j * i(1-i)   dj = dc * i * (1-j^2)   df = dc * c_{s-1} * f(1-f)
 //   dc_{s->s-1} = dc * f
-// Cluster of 8 CTAs per (direction, 128-sample tile); CTA `rank` owns 32 hidden units: it keeps dc for them in
-// registers, holds W_h[units, all 1024 gate columns] (64 KB bf16, K-major over gates) resident in shared memory, and per
-// step computes dh_rec[128 x 32] = dz_{s+1}[128 x 1024] * W_h^T on tensor cores (64 x tcgen05.mma 128x32x16), streaming
-// dz_{s+1} (written to global/L2 by the whole cluster one step earlier) through a 6-stage TMA ring.  The tile is identical
-// for the 8 CTAs of a cluster, so each K-block is read from L2 ONCE and TMA-multicast into all 8 shared memories.
+// Cluster of 8 CTAs per (direction, 128-sample tile); CTA `rank` owns 32 hidden units (dc in registers) and their 128 gate
+// columns.  The recurrent product is split along K (the gate axis): each CTA multiplies ITS OWN dz slice [128 x 128]
+// (written by its epilogue straight into shared memory in the swizzled K-major layout -- no global round trip for the A
+// operand) with the resident W_h[all 256 units, its 128 gate columns] (64 KB bf16): 8 x tcgen05.mma 128x256x16 per step.
+// (A first version multiplied the full dz [128 x 1024] by W_h[32 units] -- 64 MMAs of N = 32 per step; a tcgen05.mma costs
+// ~128 cycles for any N <= 256, so that spent 4 us per step in the tensor pipe alone.)  The 8 partial products are reduced
+// across the cluster through L2: every CTA stores its [128 x 256] f32 partial, barrier.cluster, then each thread sums the
+// 8 partials of its own 32 units.
 // Outputs: dz for every (sample, frame) in FRAME order (`dz_all`, consumed by the dW_x / dW_h / dx GEMMs).
 #pragma once
 #include <cuda.h>
@@ -24,17 +27,16 @@ constexpr int NUM_THREADS = 192;
 constexpr int BLOCK_M = 128;
 constexpr int CS = 8;
 constexpr int UPC = 32;
-constexpr int STAGES = 6;
-constexpr int B_BYTES = 16 * UPC * 128;          // 16 K-blocks x [32 rows x 128 B] = 64 KB
-constexpr int A_STAGE = BLOCK_M * 128;           // 16 KB
-constexpr int BAR_OFFSET = B_BYTES + STAGES * A_STAGE;
-constexpr int SMEM_BYTES = BAR_OFFSET + 256 + 1024;
+constexpr int B_BYTES = 2 * 256 * 128;           // 2 K-blocks x [256 unit rows x 128 B] = 64 KB
+constexpr int A_BYTES = 2 * BLOCK_M * 128;       // 2 K-blocks x [128 rows x 128 B] = 32 KB
+constexpr int BAR_OFFSET = B_BYTES + A_BYTES;
+constexpr int SMEM_BYTES = BAR_OFFSET + 128 + 1024;
 
 struct Params {
   const __nv_bfloat16* gates;     // [2][Nimg][T][4][256]  (saved by the forward kernel)
   const float* csave;             // [2][Nimg][T][256]
   const __nv_bfloat16* d_out;     // [Nimg*H, 512] gradient w.r.t. the LSTM output (frame order)
-  __nv_bfloat16* dz_state;        // [2 bufs][2 dirs][Npad][1024] step-order exchange buffer
+  float* partial;                 // [2 bufs][2 dirs][tiles][8 src ranks][128 rows][256 units] f32 cross-CTA reduction buffer
   __nv_bfloat16* dz_all;          // [Nimg*H, 2048] frame order, permuted gate columns, [fw | bw]
   const int* seq_len;
   int Nimg, Npad, H, T, tiles_per_dir;
@@ -50,16 +52,15 @@ __device__ __forceinline__ void unpack8(const uint4 q, float* v) {
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmW, const Params p) {
-  constexpr uint32_t IDESC = ptx::make_idesc_bf16(BLOCK_M, UPC);
+lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
+  constexpr uint32_t IDESC = ptx::make_idesc_bf16(BLOCK_M, 256);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_b = smem;
   uint8_t* smem_a = smem + B_BYTES;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + BAR_OFFSET);
-  uint64_t* a_empty = a_full + STAGES;
-  uint64_t* b_full = a_empty + STAGES;
-  uint64_t* acc_full = b_full + 1;
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(smem + BAR_OFFSET);
+  uint64_t* a_ready = b_full + 1;
+  uint64_t* acc_full = a_ready + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -69,22 +70,21 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
   const int tile = unit - dir * p.tiles_per_dir;
 
   if (warp_idx == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmDz);
     ptx::prefetch_tmap(&tmW);
-    for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], CS); }   // slot free = all 8 CTAs consumed it
     ptx::mbar_init(b_full, 1);
+    ptx::mbar_init(a_ready, 4);          // one arrive per epilogue warp
     ptx::mbar_init(acc_full, 1);
     ptx::fence_barrier_init();
   }
-  if (warp_idx == 1) { ptx::tmem_alloc(tmem_ptr, 32); ptx::tmem_relinquish(); }
+  if (warp_idx == 1) { ptx::tmem_alloc(tmem_ptr, 256); ptx::tmem_relinquish(); }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp_idx == 0 && lane == 0) {      // resident W_h rows [dir*256 + rank*32, +32) x 1024 gate columns
+  if (warp_idx == 0 && lane == 0) {      // resident W_h[dir, all 256 units, gate columns rank*128 .. +128), K-major over gates
     ptx::mbar_arrive_expect_tx(b_full, B_BYTES);
-    for (int kb = 0; kb < 16; ++kb) ptx::tma_load_2d(&tmW, b_full, smem_b + kb * UPC * 128, kb * 64, dir * 256 + rank * UPC);
+    for (int kb = 0; kb < 2; ++kb) ptx::tma_load_2d(&tmW, b_full, smem_b + kb * 256 * 128, rank * 128 + kb * 64, dir * 256);
   }
 
   const int q = warp_idx & 3;
@@ -96,70 +96,53 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
   float dcr[UPC];
 #pragma unroll
   for (int i = 0; i < UPC; ++i) dcr[i] = 0.f;
+  const size_t part_tile = (size_t)CS * BLOCK_M * 256;                         // floats per (buf, dir, tile)
+  const size_t part_dt = ((size_t)dir * p.tiles_per_dir + tile) * part_tile;
+  const size_t part_buf = (size_t)2 * p.tiles_per_dir * part_tile;
 
   if (warp_idx == 1 && lane == 0) ptx::mbar_wait(b_full, 0);
 
-  uint32_t prod_parity = 0;  // producer lane l: parity of ring slot l (flips on every use of that slot)
-  uint32_t mma_parity = 0;   // MMA lane: bit s = parity of ring slot s
-  int nmma = 0;              // number of accumulations completed (acc_full parity)
-
   for (int s = p.T - 1; s >= 0; --s) {
-    const bool has_rec = (s < p.T - 1);
-    if (warp_idx == 0) {
-      // K-block kb of every step lives in ring slot kb % STAGES.  Lanes 0..STAGES-1 own one slot each and issue their
-      // K-blocks in lock-step (one SIMD cp.async.bulk.tensor per round instead of 16 serial single-thread issues).
-      if (lane < STAGES && has_rec) {
-        lstm::fence_proxy_async_all();
-        const int zrow = ((((s + 1) & 1) * 2 + dir) * p.Npad) + tile * BLOCK_M;
-        for (int kb = lane; kb < 16; kb += STAGES) {
-          // all 8 CTAs of the cluster need the SAME dz tile: CTA (kb % 8) loads K-block kb once and multicasts it; every
-          // CTA arms its own barrier.  a_empty[slot] counts the MMA commits of all 8 CTAs (multicast commit below).
-          ptx::mbar_wait(&a_empty[lane], prod_parity ^ 1);
-          ptx::mbar_arrive_expect_tx(&a_full[lane], A_STAGE);
-          if ((kb & (CS - 1)) == rank)
-            ptx::tma_load_2d_mc(&tmDz, &a_full[lane], smem_a + lane * A_STAGE, kb * 64, zrow, (uint16_t)0xFF);
-          prod_parity ^= 1;
-        }
-      }
-      __syncwarp();
-    } else if (warp_idx == 1) {
-      if (lane == 0 && has_rec) {
-        for (int kb = 0; kb < 16; ++kb) {
-          const int slot = kb % STAGES;
-          ptx::mbar_wait(&a_full[slot], (mma_parity >> slot) & 1u);
-          mma_parity ^= (1u << slot);
-          ptx::tc_fence_after();
-          const uint64_t a_desc = ptx::make_desc_k_sw128(ptx::smem_u32(smem_a + slot * A_STAGE));
-          const uint64_t b_desc = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b + kb * UPC * 128));
+    const uint32_t par = (uint32_t)(p.T - 1 - s) & 1u;                         // parity of this step's a_ready / acc_full use
+    if (warp_idx == 1) {
+      if (lane == 0 && s > 0) {                                                // step 0's partial product is never consumed
+        ptx::mbar_wait(a_ready, par);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t a_desc = ptx::make_desc_k_sw128(ptx::smem_u32(smem_a + kb * BLOCK_M * 128));
+          const uint64_t b_desc = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b + kb * 256 * 128));
 #pragma unroll
           for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0);
-          ptx::tc_commit_mc(&a_empty[slot], (uint16_t)0xFF);
         }
         ptx::tc_commit(acc_full);
       }
       __syncwarp();
-    } else {
+    } else if (warp_idx >= 2) {
       const bool active = s < len;
       const int t = active ? (dir ? (len - 1 - s) : s) : s;
       const size_t srow = ((size_t)dir * p.Nimg + n) * p.T + s;
-      if (has_rec) {
-        ptx::mbar_wait(acc_full, nmma & 1);
-        ptx::tc_fence_after();
+      // ---- recurrent gradient for this thread's 32 units = sum of the 8 CTAs' partial products of step s+1
+      float dh_rec[UPC];
+#pragma unroll
+      for (int i = 0; i < UPC; ++i) dh_rec[i] = 0.f;
+      if (s < p.T - 1) {
+        const float* src = p.partial + (size_t)((s + 1) & 1) * part_buf + part_dt + (size_t)row * 256 + rank * UPC;
+#pragma unroll
+        for (int jj = 0; jj < CS; ++jj) {
+          float4 v0[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v0[i] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)jj * BLOCK_M * 256) + i);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            dh_rec[4 * i] += v0[i].x; dh_rec[4 * i + 1] += v0[i].y; dh_rec[4 * i + 2] += v0[i].z; dh_rec[4 * i + 3] += v0[i].w;
+          }
+        }
       }
-      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-      __nv_bfloat16* zs = p.dz_state + ((size_t)(((s & 1) * 2 + dir) * p.Npad) + n) * 1024 + rank * 128;
       __nv_bfloat16* za = p.dz_all + ((size_t)n * p.H + t) * 2048 + dir * 1024 + rank * 128;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int u0 = hh * 16;
-        uint32_t acc[16];
-        if (has_rec) {
-          ptx::tmem_ld_32x32b_x16(tbase + u0, acc);
-          ptx::tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) acc[i] = 0u;
-        }
         float dzi[16], dzj[16], dzf[16], dzo[16];
         if (active) {
           const __nv_bfloat16* gs = p.gates + srow * 1024 + rank * UPC + u0;
@@ -183,7 +166,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float dht = dh[i] + __uint_as_float(acc[i]);
+            const float dht = dh[i] + dh_rec[u0 + i];
             const float tc = ptx::fast_tanh(cc[i]);
             const float dc = dcr[u0 + i] + dht * go[i] * (1.f - tc * tc);
             dzo[i] = dht * tc * go[i] * (1.f - go[i]);
@@ -196,24 +179,37 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 16; ++i) { dzi[i] = 0.f; dzj[i] = 0.f; dzf[i] = 0.f; dzo[i] = 0.f; }
         }
-        if (okn) {
 #pragma unroll
-          for (int v = 0; v < 2; ++v) {
-            const uint4 qi = pack8(dzi + 8 * v), qj = pack8(dzj + 8 * v), qf = pack8(dzf + 8 * v), qo = pack8(dzo + 8 * v);
-            *(reinterpret_cast<uint4*>(zs + 0 * 32 + u0) + v) = qi;
-            *(reinterpret_cast<uint4*>(zs + 1 * 32 + u0) + v) = qj;
-            *(reinterpret_cast<uint4*>(zs + 2 * 32 + u0) + v) = qf;
-            *(reinterpret_cast<uint4*>(zs + 3 * 32 + u0) + v) = qo;
-            *(reinterpret_cast<uint4*>(za + 0 * 32 + u0) + v) = qi;
-            *(reinterpret_cast<uint4*>(za + 1 * 32 + u0) + v) = qj;
-            *(reinterpret_cast<uint4*>(za + 2 * 32 + u0) + v) = qf;
-            *(reinterpret_cast<uint4*>(za + 3 * 32 + u0) + v) = qo;
+        for (int v = 0; v < 2; ++v) {
+          const uint4 qg[4] = {pack8(dzi + 8 * v), pack8(dzj + 8 * v), pack8(dzf + 8 * v), pack8(dzo + 8 * v)};
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            // A operand (own dz slice), K index = g*32 + u: K-block g>>1, 16-byte chunk ((g&1)*32 + u0)/8 + v, 128B swizzle
+            const int chunk = ((g & 1) * 32 + u0) / 8 + v;
+            *reinterpret_cast<uint4*>(smem_a + (g >> 1) * (BLOCK_M * 128) + row * 128 + ((chunk ^ (row & 7)) << 4)) = qg[g];
+            if (okn) *(reinterpret_cast<uint4*>(za + g * 32 + u0) + v) = qg[g];
           }
         }
       }
-      if (has_rec) ++nmma;
-      lstm::fence_proxy_async_all();
-      ptx::tc_fence_before();
+      if (s > 0) {
+        ptx::fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(a_ready);
+        // ---- this CTA's partial product P[128 x 256] -> L2, for the cross-CTA reduction of the next step
+        ptx::mbar_wait(acc_full, par);
+        ptx::tc_fence_after();
+        const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        float* dst = p.partial + (size_t)(s & 1) * part_buf + part_dt + ((size_t)rank * BLOCK_M + row) * 256;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(tbase + c0, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) __stcg(reinterpret_cast<uint4*>(dst + c0 + i), make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+        }
+        ptx::tc_fence_before();
+      }
     }
     lstm::cluster_arrive_release();
     lstm::cluster_wait_acquire();
@@ -221,7 +217,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp_idx == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 32); }
+  if (warp_idx == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 256); }
 }
 
 }  // namespace lstm_bwd
