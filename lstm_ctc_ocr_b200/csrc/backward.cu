@@ -124,7 +124,7 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   // ------------------------------------------------------------------ BPTT through both directions
   {
     lstm_bwd::Params lp;
-    lp.gates = pl.gates; lp.csave = pl.csave; lp.d_out = pl.d_lstm_out; lp.partial = pl.lstm_partial; lp.dz_all = pl.dz_all;
+    lp.gates = pl.gates; lp.csave = pl.csave; lp.d_out = pl.d_lstm_out; lp.dz_all = pl.dz_all;
     lp.seq_len = time_step_len; lp.Nimg = N; lp.Npad = pl.Npad; lp.H = H2; lp.T = T; lp.tiles_per_dir = pl.Npad / 128;
     static bool attr = false;
     if (!attr) {

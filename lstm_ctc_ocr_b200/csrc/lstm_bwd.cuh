@@ -12,8 +12,10 @@
 // operand) with the resident W_h[all 256 units, its 128 gate columns] (64 KB bf16): 8 x tcgen05.mma 128x256x16 per step.
 // (A first version multiplied the full dz [128 x 1024] by W_h[32 units] -- 64 MMAs of N = 32 per step; a tcgen05.mma costs
 // ~128 cycles for any N <= 256, so that spent 4 us per step in the tensor pipe alone.)  The 8 partial products are reduced
-// across the cluster through L2: every CTA stores its [128 x 256] f32 partial, barrier.cluster, then each thread sums the
-// 8 partials of its own 32 units.
+// across the cluster through DISTRIBUTED SHARED MEMORY: every CTA sends the [128 x 32] slice that belongs to owner CTA i
+// (bf16) straight into CTA i's double-buffered "inbox" with st.shared::cluster, barrier.cluster (release/acquire), then each
+// thread sums the 8 inbox entries of its own 32 units from local shared memory.  (A version that went through L2 with f32
+// partials spent ~40 % of the step draining 1 KB of stores per thread at the barrier and ~15 % in the 8 dependent reads.)
 // Outputs: dz for every (sample, frame) in FRAME order (`dz_all`, consumed by the dW_x / dW_h / dx GEMMs).
 #pragma once
 #include <cuda.h>
@@ -29,14 +31,14 @@ constexpr int CS = 8;
 constexpr int UPC = 32;
 constexpr int B_BYTES = 2 * 256 * 128;           // 2 K-blocks x [256 unit rows x 128 B] = 64 KB
 constexpr int A_BYTES = 2 * BLOCK_M * 128;       // 2 K-blocks x [128 rows x 128 B] = 32 KB
-constexpr int BAR_OFFSET = B_BYTES + A_BYTES;
-constexpr int SMEM_BYTES = BAR_OFFSET + 128 + 1024;
+constexpr int INBOX_BYTES = 2 * CS * BLOCK_M * UPC * 2;   // [2 bufs][8 src CTAs][128 rows][32 units] bf16 = 128 KB
+constexpr int BAR_OFFSET = B_BYTES + A_BYTES + INBOX_BYTES;
+constexpr int SMEM_BYTES = BAR_OFFSET + 64 + 1024;
 
 struct Params {
   const __nv_bfloat16* gates;     // [2][Nimg][T][4][256]  (saved by the forward kernel)
   const float* csave;             // [2][Nimg][T][256]
   const __nv_bfloat16* d_out;     // [Nimg*H, 512] gradient w.r.t. the LSTM output (frame order)
-  float* partial;                 // [2 bufs][2 dirs][tiles][8 src ranks][128 rows][256 units] f32 cross-CTA reduction buffer
   __nv_bfloat16* dz_all;          // [Nimg*H, 2048] frame order, permuted gate columns, [fw | bw]
   const int* seq_len;
   int Nimg, Npad, H, T, tiles_per_dir;
@@ -58,6 +60,7 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_b = smem;
   uint8_t* smem_a = smem + B_BYTES;
+  uint8_t* inbox = smem + B_BYTES + A_BYTES;
   uint64_t* b_full = reinterpret_cast<uint64_t*>(smem + BAR_OFFSET);
   uint64_t* a_ready = b_full + 1;
   uint64_t* acc_full = a_ready + 1;
@@ -96,9 +99,6 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
   float dcr[UPC];
 #pragma unroll
   for (int i = 0; i < UPC; ++i) dcr[i] = 0.f;
-  const size_t part_tile = (size_t)CS * BLOCK_M * 256;                         // floats per (buf, dir, tile)
-  const size_t part_dt = ((size_t)dir * p.tiles_per_dir + tile) * part_tile;
-  const size_t part_buf = (size_t)2 * p.tiles_per_dir * part_tile;
 
   if (warp_idx == 1 && lane == 0) ptx::mbar_wait(b_full, 0);
 
@@ -127,15 +127,15 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
 #pragma unroll
       for (int i = 0; i < UPC; ++i) dh_rec[i] = 0.f;
       if (s < p.T - 1) {
-        const float* src = p.partial + (size_t)((s + 1) & 1) * part_buf + part_dt + (size_t)row * 256 + rank * UPC;
+        const uint8_t* src = inbox + (size_t)((s + 1) & 1) * (CS * BLOCK_M * UPC * 2) + (size_t)row * (UPC * 2);
 #pragma unroll
         for (int jj = 0; jj < CS; ++jj) {
-          float4 v0[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v0[i] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)jj * BLOCK_M * 256) + i);
+          for (int i = 0; i < 4; ++i) {
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4*>(src + (size_t)jj * (BLOCK_M * UPC * 2) + 16 * i), f);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            dh_rec[4 * i] += v0[i].x; dh_rec[4 * i + 1] += v0[i].y; dh_rec[4 * i + 2] += v0[i].z; dh_rec[4 * i + 3] += v0[i].w;
+            for (int e = 0; e < 8; ++e) dh_rec[8 * i + e] += f[e];
           }
         }
       }
@@ -195,18 +195,26 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
         ptx::fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(a_ready);
-        // ---- this CTA's partial product P[128 x 256] -> L2, for the cross-CTA reduction of the next step
+        // ---- this CTA's partial product P[128 x 256]: columns 32*i .. 32*i+31 belong to owner CTA i -> its inbox (DSMEM)
         ptx::mbar_wait(acc_full, par);
         ptx::tc_fence_after();
         const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        float* dst = p.partial + (size_t)(s & 1) * part_buf + part_dt + ((size_t)rank * BLOCK_M + row) * 256;
+        const uint32_t my_slot = ptx::smem_u32(inbox) + (uint32_t)((s & 1) * (CS * BLOCK_M * UPC * 2) + (rank * BLOCK_M + row) * (UPC * 2));
 #pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 32) {
+        for (int owner = 0; owner < CS; ++owner) {
           uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(tbase + c0, v);
+          ptx::tmem_ld_32x32b_x32(tbase + owner * 32, v);
           ptx::tmem_ld_wait();
+          const uint32_t dst = ptx::mapa(my_slot, (uint32_t)owner);
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) __stcg(reinterpret_cast<uint4*>(dst + c0 + i), make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+          for (int i = 0; i < 32; i += 8) {
+            asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 2 * i),
+                         "r"(ptx::pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1]))),
+                         "r"(ptx::pack_bf16x2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]))),
+                         "r"(ptx::pack_bf16x2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]))),
+                         "r"(ptx::pack_bf16x2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])))
+                         : "memory");
+          }
         }
         ptx::tc_fence_before();
       }
