@@ -122,6 +122,17 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
       const bool active = s < len;
       const int t = active ? (dir ? (len - 1 - s) : s) : s;
       const size_t srow = ((size_t)dir * p.Nimg + n) * p.T + s;
+      // The saved forward state of step s-1 (gates, c, c_prev, d_out: ~0.7 KB per thread, long evicted from L2) is pulled
+      // into L2 one step ahead so the dependent loads of the next iteration do not pay HBM latency on the serial chain.
+      if (s >= 1 && (s - 1) < len) {
+        const size_t prow = srow - 1;
+        const int tp = dir ? (len - s) : (s - 1);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.gates + prow * 1024 + g * 256 + rank * UPC));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.csave + prow * 256 + rank * UPC));
+        if (s >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.csave + (prow - 1) * 256 + rank * UPC));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.d_out + ((size_t)n * p.H + tp) * 512 + dir * 256 + rank * UPC));
+      }
       // ---- recurrent gradient for this thread's 32 units = sum of the 8 CTAs' partial products of step s+1
       float dh_rec[UPC];
 #pragma unroll
