@@ -32,7 +32,7 @@ extern "C" int crnn_model_set_training(crnn_model* m, int flag) {
     CRNN_TRY(make_tmap_2d(&m->tD_c5, m->Bd_c5, 1024, 1024, 1024, 256));
     CRNN_TRY(make_tmap_2d(&m->tD_l, m->Bld, 512, 64, 64, 256));
     CRNN_TRY(make_tmap_2d(&m->tD_x, m->Bxb, 512, 2048, 2048, 256));
-    CRNN_TRY(make_tmap_2d(&m->tD_h, m->Bhb, 512, 1024, 1024, 256));
+    CRNN_TRY(make_tmap_2d(&m->tD_h, m->Bhb, 512, 1024, 1024, 32));
     CRNN_TRY(make_tmap_2d(&m->tDh_c42, m->Bd_c42, 512, 4608, 4608, 128));
     CRNN_TRY(make_tmap_2d(&m->tDh_c41, m->Bd_c41, 256, 4608, 4608, 128));
     CRNN_TRY(make_tmap_2d(&m->tDh_c32, m->Bd_c32, 256, 2304, 2304, 128));
@@ -124,7 +124,7 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   // ------------------------------------------------------------------ BPTT through both directions
   {
     lstm_bwd::Params lp;
-    lp.gates = pl.gates; lp.csave = pl.csave; lp.d_out = pl.d_lstm_out; lp.dz_all = pl.dz_all;
+    lp.gates = pl.gates; lp.csave = pl.csave; lp.d_out = pl.d_lstm_out; lp.dz_state = pl.dz_state; lp.dz_all = pl.dz_all;
     lp.seq_len = time_step_len; lp.Nimg = N; lp.Npad = pl.Npad; lp.H = H2; lp.T = T; lp.tiles_per_dir = pl.Npad / 128;
     static bool attr = false;
     if (!attr) {
@@ -141,7 +141,7 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = lstm_bwd::CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, lstm_bwd::lstm_bwd_kernel, m->tD_h, lp));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, lstm_bwd::lstm_bwd_kernel, pl.tG_dzstate, m->tD_h, lp));
   }
   BMARK();
   {

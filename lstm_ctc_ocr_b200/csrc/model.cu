@@ -277,7 +277,6 @@ size_t layout_plan(Plan& pl, int N, int W, uint8_t* base, bool train) {
     pl.d_lstm_out = (__nv_bfloat16*)take(n * h2 * 512 * 2);
     pl.dz_all = (__nv_bfloat16*)take(n * h2 * 2048 * 2);
     pl.dz_state = (__nv_bfloat16*)take((size_t)2 * 2 * pl.Npad * 1024 * 2);
-    pl.lstm_partial = (float*)take((size_t)2 * 2 * (pl.Npad / 128) * 8 * 128 * 256 * 4);
     pl.d_a5 = (__nv_bfloat16*)take(n * h2 * 512 * 2);
     pl.d_a4b = (__nv_bfloat16*)take(n * h2 * 2 * 512 * 2);
     pl.d_pre4b = (__nv_bfloat16*)take(n * h2 * 4 * 512 * 2);

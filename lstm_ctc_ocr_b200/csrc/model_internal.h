@@ -54,7 +54,6 @@ struct Plan {
   uint8_t *am1, *am2, *am3;                       // arg-max window indices of pool1 / pool2 / the 1x2 pool after conv3_2
   __nv_bfloat16* gates;                           // [2][N][T][4][256] post-activation gates
   float* csave;                                   // [2][N][T][256]
-  float* lstm_partial;                            // [2][2][tiles][8][128][256] f32: BPTT cross-CTA reduction buffer
   __nv_bfloat16 *dl_rows, *d_lstm_out, *dz_all, *dz_state, *d_a5, *d_a4b, *d_pre4b, *d_pre4a, *d_a3p, *d_pre32, *d_pre31, *d_a2,
       *d_pre2, *d_a1;
   double* bn_bwd_sums;                            // [2 layers][2][512]
