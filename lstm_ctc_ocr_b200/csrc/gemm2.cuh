@@ -17,19 +17,19 @@
 
 namespace gemm {
 
-template <int STAGES>
+template <int BLOCK_N, int STAGES>
 struct Smem2 {
   static constexpr int A_STAGE = BLOCK_M * 128;       // 16 KB
-  static constexpr int B_STAGE = 128 * 128;           // 16 KB: this CTA's half of the 256 N rows
+  static constexpr int B_STAGE = (BLOCK_N / 2) * 128; // this CTA's half of the BLOCK_N rows of B
   static constexpr int BAR_OFFSET = STAGES * (A_STAGE + B_STAGE);
   static constexpr int BYTES = BAR_OFFSET + 256 + 1024;
 };
 
-template <int AMODE, int EPI, int STAGES>
+template <int BLOCK_N, int AMODE, int EPI, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
-  constexpr int BLOCK_N = 256;
-  constexpr int A_STAGE = Smem2<STAGES>::A_STAGE, B_STAGE = Smem2<STAGES>::B_STAGE;
+  static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
+  constexpr int A_STAGE = Smem2<BLOCK_N, STAGES>::A_STAGE, B_STAGE = Smem2<BLOCK_N, STAGES>::B_STAGE;
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
   constexpr uint32_t IDESC = ptx::make_idesc_bf16(2 * BLOCK_M, BLOCK_N);     // M = 256 across the CTA pair
 
@@ -37,7 +37,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Smem2<STAGES>::BAR_OFFSET);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Smem2<BLOCK_N, STAGES>::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -69,7 +69,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int stage = 0; uint32_t phase = 0;
       for (int pr = cluster_id; pr < num_pairs; pr += num_clusters) {
         const int m_blk = (pr / p.num_n_tiles) * 2 + (int)rank, n_blk = pr % p.num_n_tiles;
-        const int b_row = n_blk * BLOCK_N + (int)rank * 128;
+        const int b_row = n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2);
         int cn = 0, ch0 = 0;
         if (AMODE == A_CONV3 && lane < nA) {
           const int g = m_blk * 4 + lane;

@@ -21,10 +21,10 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const gemm::P
 }
 
 // 2-CTA pairs: B map must have box rows = 128 (each CTA stages half of the 256-row N tile)
-template <int AM, int EPI, int ST>
+template <int AM, int EPI, int ST, int BN = 256>
 static int launch_gemm2(const CUtensorMap& a, const CUtensorMap& b_half, const gemm::Params& p, int num_sms, cudaStream_t st) {
-  auto kern = gemm::gemm2_kernel<AM, EPI, ST>;
-  constexpr int smem = gemm::Smem2<ST>::BYTES;
+  auto kern = gemm::gemm2_kernel<BN, AM, EPI, ST>;
+  constexpr int smem = gemm::Smem2<BN, ST>::BYTES;
   static bool attr = false;
   if (!attr) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

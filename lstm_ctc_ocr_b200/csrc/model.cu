@@ -167,6 +167,7 @@ extern "C" int crnn_model_create(const crnn_config* cfg, crnn_model** out) {
   if (st == CRNN_OK) st = make_tmap_2d(&m->tB_h, m->Bh, 2048, 256, 256, 256);
   if (st == CRNN_OK) st = make_tmap_2d(&m->tB_h128, m->Bh, 2048, 256, 256, 128);
   if (st == CRNN_OK) st = make_tmap_2d(&m->tB_l, m->Bl, 64, 512, 512, 64);
+  if (st == CRNN_OK) st = make_tmap_2d(&m->tBh_c2, m->Bc2, 128, 576, 576, 64);
   if (st == CRNN_OK) st = make_tmap_2d(&m->tBh_c31, m->Bc31, 256, 1152, 1152, 128);
   if (st == CRNN_OK) st = make_tmap_2d(&m->tBh_c32, m->Bc32, 256, 2304, 2304, 128);
   if (st == CRNN_OK) st = make_tmap_2d(&m->tBh_c41, m->Bc41, 512, 2304, 2304, 128);
@@ -395,9 +396,11 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
     gemm::Params p = conv_params(N, H1, 16, 64, 128, 128, m->P("conv2/biases"), pl.a2, pl.mg2);
     if (pl.train) {
       p.argmax = pl.am2;
-      CRNN_TRY((launch_gemm<128, gemm::A_CONV3, gemm::EPI_RELU_POOL22_T, 6>(pl.tA_c2, m->tB_c2, p, sms, st)));
+      if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_RELU_POOL22_T, 8, 128>(pl.tA_c2, m->tBh_c2, p, sms, st)));
+      else CRNN_TRY((launch_gemm<128, gemm::A_CONV3, gemm::EPI_RELU_POOL22_T, 6>(pl.tA_c2, m->tB_c2, p, sms, st)));
     } else {
-      CRNN_TRY((launch_gemm<128, gemm::A_CONV3, gemm::EPI_RELU_POOL22, 6>(pl.tA_c2, m->tB_c2, p, sms, st)));
+      if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_RELU_POOL22, 8, 128>(pl.tA_c2, m->tBh_c2, p, sms, st)));
+      else CRNN_TRY((launch_gemm<128, gemm::A_CONV3, gemm::EPI_RELU_POOL22, 6>(pl.tA_c2, m->tB_c2, p, sms, st)));
     }
   }
   STAGE_MARK();
@@ -593,14 +596,14 @@ extern "C" int crnn_debug_tap(crnn_model* m, const char* name, float* dst, size_
 
 extern "C" int crnn_test_gemm_bf16(const void* A, const void* B, float* D, int M, int Nc, int K, int block_n,
                                    crnn_stream_t stream) {
-  if (!A || !B || !D || M <= 0 || Nc <= 0 || K <= 0 || (K % 64) != 0 || (block_n != 512 && (Nc % block_n) != 0))
+  if (!A || !B || !D || M <= 0 || Nc <= 0 || K <= 0 || (K % 64) != 0 || (block_n != 512 && block_n != 384 && (Nc % block_n) != 0))
     return crnn_fail(CRNN_INVALID_VALUE, "test_gemm: bad args");
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   CUtensorMap ta, tb;
   CRNN_TRY(make_tmap_2d(&ta, A, M, K, K, 128));
-  CRNN_TRY(make_tmap_2d(&tb, B, Nc, K, K, block_n == 512 ? 256 : block_n));
+  CRNN_TRY(make_tmap_2d(&tb, B, Nc, K, K, block_n >= 384 ? 256 : block_n));
   gemm::Params p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.Nc = Nc;
@@ -617,6 +620,13 @@ extern "C" int crnn_test_gemm_bf16(const void* A, const void* B, float* D, int M
     CRNN_TRY(make_tmap_2d(&tbh, B, Nc, K, K, 128));
     p.num_n_tiles = Nc / 256;
     return launch_gemm2<gemm::A_PLAIN, gemm::EPI_F32, 6>(ta, tbh, p, sms, st);
+  }
+  if (block_n == 384) {      // 2-CTA pairs with a 128-column N tile (probe: does M = 256 restore the MMA rate at N = 128?)
+    if (Nc % 128) return crnn_fail(CRNN_INVALID_VALUE, "test_gemm: Nc % 128");
+    CUtensorMap tbh;
+    CRNN_TRY(make_tmap_2d(&tbh, B, Nc, K, K, 64));
+    p.num_n_tiles = Nc / 128;
+    return launch_gemm2<gemm::A_PLAIN, gemm::EPI_F32, 8, 128>(ta, tbh, p, sms, st);
   }
   return crnn_fail(CRNN_INVALID_VALUE, "test_gemm: block_n must be 64/128/256 (or 512 = 2-CTA pairs)");
 }

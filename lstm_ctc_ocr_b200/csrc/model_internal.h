@@ -85,7 +85,7 @@ struct crnn_model {
   CUtensorMap tD_c42, tD_c41, tD_c32, tD_c31, tD_c2, tD_c5, tD_l, tD_x, tD_h;
   CUtensorMap tDh_c42, tDh_c41, tDh_c32, tDh_c5, tDh_x;     // box = 128 rows (2-CTA pairs)
   double* grad_sumsq = nullptr;
-  CUtensorMap tBh_c31, tBh_c32, tBh_c41, tBh_c42, tBh_c5, tBh_x;   // same weights, box = 128 rows: per-CTA half of a 256-row N tile
+  CUtensorMap tBh_c2, tBh_c31, tBh_c32, tBh_c41, tBh_c42, tBh_c5, tBh_x;   // same weights, box = 128 rows: per-CTA half of a 256-row N tile
   bool use_2cta = true;      // cta_group::2 GEMM pairs for the Nc % 256 == 0 layers (CRNN_GEMM2=0 disables; debug A/B switch)
   int lstm_upc = 32;         // hidden units per gate tile: 32 = persistent cluster kernel (default), 64 = per-step launches
   Plan plan;
