@@ -396,11 +396,11 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
     gemm::Params p = conv_params(N, H1, 16, 64, 128, 128, m->P("conv2/biases"), pl.a2, pl.mg2);
     if (pl.train) {
       p.argmax = pl.am2;
-      if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_RELU_POOL22_T, 8, 128>(pl.tA_c2, m->tBh_c2, p, sms, st)));
-      else CRNN_TRY((launch_gemm<128, gemm::A_CONV3, gemm::EPI_RELU_POOL22_T, 6>(pl.tA_c2, m->tB_c2, p, sms, st)));
+      // (CTA pairs with a 128-column N tile were measured slower here: 0.371 vs 0.348 ms -- conv2 is bound by the MMA rate at
+      //  N = 128 and its 2x2-pool epilogue, not by the operand feed)
+      CRNN_TRY((launch_gemm<128, gemm::A_CONV3, gemm::EPI_RELU_POOL22_T, 6>(pl.tA_c2, m->tB_c2, p, sms, st)));
     } else {
-      if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_RELU_POOL22, 8, 128>(pl.tA_c2, m->tBh_c2, p, sms, st)));
-      else CRNN_TRY((launch_gemm<128, gemm::A_CONV3, gemm::EPI_RELU_POOL22, 6>(pl.tA_c2, m->tB_c2, p, sms, st)));
+      CRNN_TRY((launch_gemm<128, gemm::A_CONV3, gemm::EPI_RELU_POOL22, 6>(pl.tA_c2, m->tB_c2, p, sms, st)));
     }
   }
   STAGE_MARK();
