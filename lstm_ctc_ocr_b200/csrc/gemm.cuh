@@ -2,8 +2,9 @@
 //
 //   D[128 x BLOCK_N tile, f32 in TMEM] = A[rows x K] (bf16, K-major, TMA) * B[Nc x K]^T (bf16, K-major, TMA)
 //
-// Roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = tcgen05.mma issuer (one lane,
-// also owns the TMEM allocation), warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4).
+// Roles (320 threads): warp 0 = TMA producer (one lane per box), warp 1 = tcgen05.mma issuer (one lane,
+// also owns the TMEM allocation), warps 2..9 = epilogue (TMEM lane quadrant = warp_idx % 4; two warps per quadrant,
+// each draining half of the tile's columns -- the plain-store epilogues were the bottleneck of the short-K GEMMs).
 // Pipelines: STAGES-deep smem ring (full/empty mbarriers, TMA <-> MMA) and a 2-deep TMEM accumulator
 // ring (tmem_full/tmem_empty, MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
@@ -27,7 +28,8 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                      // bf16 elements per K-block = one 128 B swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * 128;     // 16 KB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;                 // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int NUM_EPI_WARPS = 8;                 // two warps per TMEM lane quadrant, each draining half of the tile's columns
 constexpr int EPI_WARP0 = 2;
 
 enum AMode { A_PLAIN = 0, A_CONV3 = 1 };
@@ -117,7 +119,7 @@ struct Smem {
 // tile held in its CTA's TMEM at `tbase` (lane quadrant and accumulator stage already applied).
 template <int BLOCK_N, int EPI>
 __device__ __forceinline__ void run_epilogue(const Params& p, const uint32_t tbase, const int m_blk, const int n_blk, const int q,
-                                             const int lane) {
+                                             const int lane, const int c_lo = 0, const int c_hi = BLOCK_N) {
   const int row = q * 32 + lane;
   const int col0 = n_blk * BLOCK_N;
 
@@ -139,7 +141,7 @@ __device__ __forceinline__ void run_epilogue(const Params& p, const uint32_t tba
     const int grow = m_blk * BLOCK_M + row;
     float* out = reinterpret_cast<float*>(p.out) + (size_t)grow * p.Nc + col0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
       uint32_t v[32];
       ptx::tmem_ld_32x32b_x32(tbase + c0, v);
       ptx::tmem_ld_wait();
@@ -160,7 +162,7 @@ __device__ __forceinline__ void run_epilogue(const Params& p, const uint32_t tba
     }
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)drow * p.ldo + col0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
       uint32_t v[32];
       ptx::tmem_ld_32x32b_x32(tbase + c0, v);
       ptx::tmem_ld_wait();
@@ -183,7 +185,7 @@ __device__ __forceinline__ void run_epilogue(const Params& p, const uint32_t tba
     const bool ok = (grow < p.M) && (t < p.T);
     float* out = reinterpret_cast<float*>(p.out) + ((size_t)t * p.Nimg + n) * p.Nc + col0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
       uint32_t v[32];
       ptx::tmem_ld_32x32b_x32(tbase + c0, v);
       ptx::tmem_ld_wait();
@@ -205,7 +207,7 @@ __device__ __forceinline__ void run_epilogue(const Params& p, const uint32_t tba
     else off = (((size_t)n_img * p.H + h) * (p.Wd >> 1) + (w >> 1)) * p.Nc;
     __nv_bfloat16* out = outb + off + col0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
       uint32_t v[32];
       ptx::tmem_ld_32x32b_x32(tbase + c0, v);
       ptx::tmem_ld_wait();
@@ -253,7 +255,7 @@ __device__ __forceinline__ void run_epilogue(const Params& p, const uint32_t tba
   } else if (EPI == EPI_CONV_STORE) {
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (((size_t)n_img * p.H + h) * p.Wd + w) * p.Nc + col0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
       uint32_t v[32];
       ptx::tmem_ld_32x32b_x32(tbase + c0, v);
       ptx::tmem_ld_wait();
@@ -281,7 +283,7 @@ __device__ __forceinline__ void run_epilogue(const Params& p, const uint32_t tba
     const uint32_t kidx = P22 ? (uint32_t)((((lane >> 4) & 1) << 1) | (lane & 1)) : (uint32_t)(lane & 1);
     const uint32_t kinv = (P22 ? 3u : 1u) - kidx;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
       uint32_t v[32];
       ptx::tmem_ld_32x32b_x32(tbase + c0, v);
       ptx::tmem_ld_wait();
@@ -331,7 +333,7 @@ __device__ __forceinline__ void run_epilogue(const Params& p, const uint32_t tba
   } else if (EPI == EPI_STATS) {
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (((size_t)n_img * p.H + h) * p.Wd + w) * p.Nc + col0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
       uint32_t v[32];
       ptx::tmem_ld_32x32b_x32(tbase + c0, v);
       ptx::tmem_ld_wait();
@@ -379,7 +381,7 @@ __device__ __forceinline__ void run_epilogue(const Params& p, const uint32_t tba
     __nv_bfloat16* hn = p.h_next + ((size_t)dir * p.Npad + n) * 256 + n_blk * 64;
     __nv_bfloat16* lo = p.lstm_out + rt * 512 + dir * 256 + n_blk * 64;
 #pragma unroll 1
-    for (int u0 = 0; u0 < 64; u0 += 16) {
+    for (int u0 = (c_lo >> 2); u0 < (c_hi >> 2); u0 += 16) {
       uint32_t gi[16], gj[16], gf[16], go[16];
       ptx::tmem_ld_32x32b_x16(tbase + u0, gi);
       ptx::tmem_ld_32x32b_x16(tbase + 64 + u0, gj);
@@ -466,7 +468,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
-      ptx::mbar_init(&tmem_empty[s], 4);   // one arrive per epilogue warp
+      ptx::mbar_init(&tmem_empty[s], NUM_EPI_WARPS);   // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -566,7 +568,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
-      run_epilogue<BLOCK_N, EPI>(p, tbase, m_blk, n_blk, q, lane);
+      const int chalf = (warp_idx - 2) >> 2;           // warps 2..5 take columns [0, N/2), warps 6..9 take [N/2, N)
+      run_epilogue<BLOCK_N, EPI>(p, tbase, m_blk, n_blk, q, lane, chalf * (BLOCK_N / 2), (chalf + 1) * (BLOCK_N / 2));
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);

@@ -53,7 +53,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 8); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 2 * NUM_EPI_WARPS); }
     ptx::fence_barrier_init();
   }
   if (warp_idx == 1) { ptx::tmem_alloc_2cta(tmem_ptr, TMEM_COLS); ptx::tmem_relinquish_2cta(); }
@@ -138,7 +138,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
-      if (m_blk < p.num_m_tiles) run_epilogue<BLOCK_N, EPI>(p, tbase, m_blk, n_blk, q, lane);
+      const int chalf = (warp_idx - 2) >> 2;
+      if (m_blk < p.num_m_tiles)
+        run_epilogue<BLOCK_N, EPI>(p, tbase, m_blk, n_blk, q, lane, chalf * (BLOCK_N / 2), (chalf + 1) * (BLOCK_N / 2));
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tmem_empty[acc]), 0));
