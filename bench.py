@@ -335,7 +335,7 @@ def main():
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": int(sess.h2d_bytes),
                     "d2h_bytes_per_step": int(sess.d2h_bytes), "steps": Ke, "api": "Session.run(loss, feed_dict=host numpy)",
                     "loss": float(e2e_loss)},
-            "gpu_launches": K * (1 + 8 + T + 4 + 1 + 1),
+            "gpu_launches": K * 16,      # per step: conv1, 8 tcgen05 GEMMs, 2x(bn finalize + apply), persistent LSTM, CTC, loss
             "roofline": roofline, "stages": stages, "clocks": clocks,
         }
         if ms_train is not None:
