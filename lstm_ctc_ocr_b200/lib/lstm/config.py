@@ -22,36 +22,36 @@ class AttrDict(dict):
         self[k] = v
 
 
+_CHARSET = "0123456789abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ"
+
+# key -> default, exactly the reference's values (lib/lstm/config.py:12-72); nested sections are AttrDicts
+_DEFAULTS = {
+    "GPU_ID": 1, "GPU_USAGE": 0.9,
+    "OFFSET_TIME_STEP": -1, "POOL_SCALE": 4,                   # time_step = nw // POOL_SCALE + OFFSET_TIME_STEP
+    "IMG_SHAPE": [32, 100], "IMG_HEIGHT": 32, "NCHANNELS": 1,
+    "MAX_CHAR_LEN": 6, "MIN_LEN": 4, "MAX_LEN": 6,
+    "BLANK_TOKEN": 0, "SPACE_INDEX": 0, "SPACE_TOKEN": "",
+    "CHARSET": _CHARSET, "NCLASSES": len(_CHARSET) + 2,        # + CTC blank (0) + decoder blank (63)
+    "FONT": "fonts/Ubuntu-M.ttf",
+    "NET_NAME": "lstm", "EXP_DIR": "default", "LOG_DIR": "default", "RNG_SEED": 3,
+    "TRAIN": {
+        "SOLVER": "Adam", "TXT": "annotation_train.txt",
+        "LEARNING_RATE": 0.01, "MOMENTUM": 0.9, "GAMMA": 0.1, "STEPSIZE": 50000, "WEIGHT_DECAY": 0.0005,
+        "DISPLAY": 10, "LOG_IMAGE_ITERS": 100, "NUM_EPOCHS": 2000,
+        "NUM_HID": 512, "NUM_LAYERS": 2, "BATCH_SIZE": 64,
+        "SNAPSHOT_ITERS": 5000, "SNAPSHOT_PREFIX": "lstm", "SNAPSHOT_INFIX": "",
+    },
+    "VAL": {"TXT": "annotation_val.txt", "VAL_STEP": 1000, "NUM_EPOCHS": 1000, "BATCH_SIZE": 128, "PRINT_NUM": 5},
+    "TEST": {},
+}
+
+
 def _defaults():
     c = AttrDict()
-    c.GPU_ID = 1
-    c.GPU_USAGE = 0.9
-    c.OFFSET_TIME_STEP = -1
-    c.POOL_SCALE = 4
-    c.IMG_SHAPE = [32, 100]
-    c.IMG_HEIGHT = 32
-    c.MAX_CHAR_LEN = 6
-    c.BLANK_TOKEN = 0
-    c.CHARSET = "0123456789abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ"
-    c.NCLASSES = len(c.CHARSET) + 2
-    c.MIN_LEN = 4
-    c.MAX_LEN = 6
-    c.FONT = "fonts/Ubuntu-M.ttf"
-    c.NCHANNELS = 1
+    for k, v in _DEFAULTS.items():
+        c[k] = AttrDict(v) if isinstance(v, dict) else (list(v) if isinstance(v, list) else v)
     c.NUM_FEATURES = c.IMG_HEIGHT * c.NCHANNELS
-    c.NET_NAME = "lstm"
-    c.TRAIN = AttrDict(SOLVER="Adam", TXT="annotation_train.txt", WEIGHT_DECAY=0.0005, LEARNING_RATE=0.01,
-                       MOMENTUM=0.9, GAMMA=0.1, STEPSIZE=50000, DISPLAY=10, LOG_IMAGE_ITERS=100, NUM_EPOCHS=2000,
-                       NUM_HID=512, NUM_LAYERS=2, BATCH_SIZE=64, SNAPSHOT_ITERS=5000, SNAPSHOT_PREFIX="lstm",
-                       SNAPSHOT_INFIX="")
-    c.VAL = AttrDict(TXT="annotation_val.txt", VAL_STEP=1000, NUM_EPOCHS=1000, BATCH_SIZE=128, PRINT_NUM=5)
-    c.RNG_SEED = 3
     c.ROOT_DIR = osp.abspath(osp.join(osp.dirname(__file__), "..", "..", ".."))
-    c.TEST = AttrDict()
-    c.EXP_DIR = "default"
-    c.LOG_DIR = "default"
-    c.SPACE_INDEX = 0
-    c.SPACE_TOKEN = ""
     return c
 
 

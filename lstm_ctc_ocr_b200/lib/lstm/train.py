@@ -106,84 +106,84 @@ class SolverWrapper(object):
         return labels
 
     # ---- the loop (train.py:63-162) -----------------------------------------------------------------------------
-    def train_model(self, sess, max_iters, restore=False, train_gen=None, val_gen=None):
-        from ... import parallel
-        train_gen = train_gen or get_batch(num_workers=12, batch_size=cfg.TRAIN.BATCH_SIZE, vis=False)
-        val_gen = val_gen or get_batch(num_workers=1, batch_size=cfg.VAL.BATCH_SIZE, vis=False)
-        loss, dense_decoded = self.net.build_loss()
-        if cfg.TRAIN.SOLVER != "Adam":
-            raise NotImplementedError("only the Adam solver of lstm/lstm.yml is implemented (RMS/Momentum are unused upstream)")
-        lr = Variable(cfg.TRAIN.LEARNING_RATE)
-        global_step = Variable(0)
-        self._lr, self._global_step = lr, global_step
-        train_op = TrainOp(self.net, lr, global_step, clip=10.0)
+    def _feed(self, batch, keep_prob):
+        """feed_dict for one data-layer tuple (train.py:119-127)."""
+        imgs, flat_labels, label_len, time_steps = batch
+        net = self.net
+        return {net.data: np.array(imgs), net.labels: np.array(flat_labels), net.time_step_len: np.array(time_steps),
+                net.labels_len: np.array(label_len), net.keep_prob: keep_prob}
+
+    def _prepare(self, sess, restore, lr, global_step):
+        """Variable initialisation, data-parallel broadcast and the optional resume (train.py:88-106)."""
+        from ... import parallel, synthetic
         eng = sess.engine_for(self.net)
         if not getattr(eng, "_initialised", False):
-            from ... import synthetic
             eng.load_params(synthetic.init_params(cfg.RNG_SEED))       # global_variables_initializer
             eng._initialised = True
         eng.set_training(True)
         if parallel.world_size() > 1:
             parallel.broadcast_(eng.params)
             eng.lib.crnn_model_params_changed(eng.handle)
-        restore_iter = 1
-        if restore:
-            path = self._latest_checkpoint()
-            try:
-                print("Restoring from {}...".format(path), end=" ")
-                blob = self.restore(sess, path)
-                stem = os.path.splitext(os.path.basename(path))[0]
-                restore_iter = int(stem.split("_")[-1])
-                global_step.assign(restore_iter)
-                lr.assign(float(blob["lr"]))
-                print("done")
-            except Exception:
-                raise Exception("Check your pretrained {:s}".format(str(path)))
-        timer = Timer()
-        loss_min = 0.015
-        first_val = True
-        history = []
-        for iter in range(restore_iter, max_iters):
+        if not restore:
+            return 1
+        path = self._latest_checkpoint()
+        try:
+            print("Restoring from {}...".format(path), end=" ")
+            blob = self.restore(sess, path)
+            first_iter = int(os.path.splitext(os.path.basename(path))[0].split("_")[-1])   # iteration from the file name
+            global_step.assign(first_iter)
+            lr.assign(float(blob["lr"]))
+            print("done")
+            return first_iter
+        except Exception:
+            raise Exception("Check your pretrained {:s}".format(str(path)))
+
+    def _validate(self, sess, dense_decoded, val_gen, cache):
+        """Accuracy on ONE cached validation batch (train.py:145-162)."""
+        if "batch" not in cache:
+            cache["batch"] = next(val_gen)
+            cache["org"] = self.restoreLabel(cache["batch"][1], cache["batch"][2])
+        res = sess.run(fetches=dense_decoded, feed_dict=self._feed(cache["batch"], 1.0))
+        acc = accuracy_calculation(cache["org"], res, ignore_value=0)
+        print("accuracy: {:.5f}".format(acc))
+        return acc
+
+    def train_model(self, sess, max_iters, restore=False, train_gen=None, val_gen=None):
+        from ... import parallel
+        if cfg.TRAIN.SOLVER != "Adam":
+            raise NotImplementedError("only the Adam solver of lstm/lstm.yml is implemented (RMS/Momentum are unused upstream)")
+        train_gen = train_gen or get_batch(num_workers=12, batch_size=cfg.TRAIN.BATCH_SIZE, vis=False)
+        val_gen = val_gen or get_batch(num_workers=1, batch_size=cfg.VAL.BATCH_SIZE, vis=False)
+        loss, dense_decoded = self.net.build_loss()
+        lr, global_step = Variable(cfg.TRAIN.LEARNING_RATE), Variable(0)
+        self._lr, self._global_step = lr, global_step
+        train_op = TrainOp(self.net, lr, global_step, clip=10.0)
+        first_iter = self._prepare(sess, restore, lr, global_step)
+        timer, history, val_cache = Timer(), [], {}
+        loss_min = 0.015                                   # best-loss snapshot threshold (train.py:109)
+        is_chief = parallel.rank() == 0
+        for iter in range(first_iter, max_iters):
             timer.tic()
             if iter != 0 and iter % cfg.TRAIN.STEPSIZE == 0:
                 lr.assign(lr.eval() * cfg.TRAIN.GAMMA)
-            img_Batch, label_Batch, label_len_Batch, time_step_Batch = next(train_gen)
-            feed_dict = {
-                self.net.data: np.array(img_Batch),
-                self.net.labels: np.array(label_Batch),
-                self.net.time_step_len: np.array(time_step_Batch),
-                self.net.labels_len: np.array(label_len_Batch),
-                self.net.keep_prob: 0.5,
-            }
-            ctc_loss, _ = sess.run(fetches=[loss, train_op], feed_dict=feed_dict)
+            ctc_loss, _ = sess.run(fetches=[loss, train_op], feed_dict=self._feed(next(train_gen), 0.5))
             history.append(float(ctc_loss))
-            _diff_time = timer.toc(average=False)
+            step_seconds = timer.toc(average=False)
             if iter % cfg.TRAIN.DISPLAY == 0:
                 print("iter: %d / %d, total loss: %.7f, lr: %.7f" % (iter, max_iters, ctc_loss, lr.eval()), end=" ")
-                print("speed: {:.3f}s / iter".format(_diff_time))
-            if (iter + 1) % cfg.TRAIN.SNAPSHOT_ITERS == 0 or ctc_loss < loss_min:
-                if parallel.rank() == 0:
-                    if ctc_loss < loss_min:
+                print("speed: {:.3f}s / iter".format(step_seconds))
+            new_best = ctc_loss < loss_min
+            if new_best or (iter + 1) % cfg.TRAIN.SNAPSHOT_ITERS == 0:
+                if is_chief:
+                    if new_best:
                         print("loss: ", ctc_loss, end=" ")
-                        self.snapshot(sess, 1)
-                        loss_min = ctc_loss
+                        self.snapshot(sess, 1)             # the reference always names the best-loss snapshot iter_2
                     else:
                         self.snapshot(sess, iter)
-            if (iter + 1) % cfg.VAL.VAL_STEP == 0 or loss_min == ctc_loss:
-                if first_val:
-                    val_img_Batch, val_label_Batch, val_label_len_Batch, val_time_step_Batch = next(val_gen)
-                    org = self.restoreLabel(val_label_Batch, val_label_len_Batch)
-                    first_val = False
-                feed_dict = {
-                    self.net.data: np.array(val_img_Batch),
-                    self.net.labels: np.array(val_label_Batch),
-                    self.net.time_step_len: np.array(val_time_step_Batch),
-                    self.net.labels_len: np.array(val_label_len_Batch),
-                    self.net.keep_prob: 1.0,
-                }
-                res = sess.run(fetches=dense_decoded, feed_dict=feed_dict)
-                acc = accuracy_calculation(org, res, ignore_value=0)
-                print("accuracy: {:.5f}".format(acc))
+                if new_best:
+                    loss_min = ctc_loss
+            if new_best or (iter + 1) % cfg.VAL.VAL_STEP == 0:
+                self._validate(sess, dense_decoded, val_gen, val_cache)
         return history
 
 

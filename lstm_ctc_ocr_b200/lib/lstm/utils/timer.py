@@ -1,21 +1,27 @@
-"""Wall-clock tic/toc (reference lib/lstm/utils/timer.py:19-32)."""
-import time
+"""Interval timer exposing the reference's ``Timer`` surface (``tic`` / ``toc(average)`` and the public counters
+``total_time, calls, diff, average_time``) used for the ``speed: %.3fs / iter`` print of the solver loop."""
+from time import perf_counter
 
 
 class Timer(object):
+    __slots__ = ("total_time", "calls", "start_time", "diff", "average_time")
+
     def __init__(self):
-        self.total_time = 0.0
+        self.reset()
+
+    def reset(self):
+        self.total_time = self.diff = self.average_time = self.start_time = 0.0
         self.calls = 0
-        self.start_time = 0.0
-        self.diff = 0.0
-        self.average_time = 0.0
 
     def tic(self):
-        self.start_time = time.time()
+        self.start_time = perf_counter()
 
     def toc(self, average=True):
-        self.diff = time.time() - self.start_time
-        self.total_time += self.diff
+        now = perf_counter()
+        self.diff = now - self.start_time
         self.calls += 1
+        self.total_time += self.diff
         self.average_time = self.total_time / self.calls
-        return self.average_time if average else self.diff
+        if average:
+            return self.average_time
+        return self.diff
