@@ -3,7 +3,18 @@
 // Replaces warpctc_tensorflow.ctc at lib/networks/network.py:653-654 and the decode at
 // lib/networks/network.py:656-657 (+ zero stripping, lib/lstm/utils/training.py:32).
 //
-// ctc_loss_kernel: one CTA (4 warps) per utterance; warps 0/1 run the two recursions, all 4 share the frame-parallel phases.
+// Two kernels, same arithmetic (log2-space recursions, softmax with max subtraction inside):
+//
+// ctc_fast_kernel (S = 2L+1 <= 32, the captcha/text-line case): one 64-thread CTA per utterance, 8 CTAs per SM.
+//   load     every thread pulls its own frames' 256-B logit rows into shared memory with 1-D bulk copies (no LSU work)
+//   phase 0  thread = frame: row max, p = 2^(x-m) written back in place, normaliser, the L+1 emission scores of the frame
+//   phase 1  the alpha and the (state-reversed) beta recursion are the SAME instruction stream -- value from lane-1 / lane-2
+//            via warp shuffles -- so for S <= 16 they share one warp (lanes 0-15 alpha, 16-31 beta); for S <= 32 warp 0 / warp 1
+//   phase 2  thread = frame: row <- scale*p/sum, minus the state posteriors scattered into the thread's own row (no
+//            atomics), then one 256-B bulk store of the row to the gradient
+//
+// ctc_loss_kernel<KS> (S <= 32*KS, generic): one CTA (4 warps) per utterance; warps 0/1 run the two recursions, all 4 share
+// the frame-parallel phases.
 //   phase 0  both warps, rows interleaved: log2-softmax normaliser per frame and the S <= 32*KS
 //            emission scores e[t][s] = log2 y_t(l'_s), kept in shared memory (HBM read #1, coalesced 256 B rows)
 //   phase 1  warp 0 runs the alpha recursion forward while warp 1 runs the beta recursion backward --
@@ -13,6 +24,8 @@
 //            sum of alpha*beta/y via shared-memory accumulators, write grad row (HBM write, coalesced)
 // No tensor cores: the dynamic program is a scan, not a contraction.
 #include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -34,6 +47,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+// 3-input maximum as ONE instruction (sm_100 FMNMX3); opaque to the compiler so that it cannot re-associate the operands
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
 }
 // log2(2^a + 2^b + 2^c) with -inf handling
 __device__ __forceinline__ float lse3(float a, float b, float c) {
@@ -301,6 +320,209 @@ __global__ void __launch_bounds__(CTC_THREADS, 8) ctc_loss_kernel(const float* _
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Fast path: S <= 32.  Shared-memory rows use a stride of 68 floats (272 B: 16-B aligned for the bulk copies and
+// conflict-free when every thread of a quarter-warp reads a float4 of its own row); alpha/beta/emission tables use odd
+// strides so that both "lane = state" (phase 1) and "thread = frame" (phase 2) accesses are conflict-free.
+constexpr int FAST_THREADS = 64;
+constexpr int FAST_XS = 68;
+
+__host__ __device__ inline int fast_alpha_stride(int max_label_len) { return (2 * max_label_len + 1) | 1; }
+__host__ __device__ inline int fast_label_stride(int max_label_len) { return max_label_len | 1; }
+
+__global__ void __launch_bounds__(FAST_THREADS, 8)
+ctc_fast_kernel(const float* __restrict__ logits, float* __restrict__ grad, const int* __restrict__ flat_labels,
+                const int* __restrict__ label_len, const int* __restrict__ input_len, int T, int N, int blank,
+                int max_label_len, float grad_scale, float* __restrict__ costs) {
+  extern __shared__ __align__(16) float sm[];
+  const int AS = fast_alpha_stride(max_label_len), ES = fast_label_stride(max_label_len);
+  float* s_x = sm;                                 // [T][68]  logits -> p -> gradient row
+  float* s_alpha = s_x + (size_t)T * FAST_XS;      // [T][AS]
+  float* s_beta = s_alpha + (size_t)T * AS;        // [T][AS]
+  float* s_el = s_beta + (size_t)T * AS;           // [T][ES]  log2 y_t(label k)
+  float* s_eb = s_el + (size_t)T * ES;             // [T]      log2 y_t(blank)
+  float* s_k = s_eb + T;                           // [T]      grad_scale / sum_c 2^(x-m)
+  __shared__ uint64_t s_bar;
+  __shared__ int s_ext[32];
+  __shared__ int s_off, s_repeats;
+
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int L = label_len[n];
+  const int Tn = max(0, min(input_len[n], T));
+  const int S = 2 * L + 1;
+
+  if (tid == 0) {
+    ptx::mbar_init(&s_bar, FAST_THREADS);
+    ptx::fence_barrier_init();
+    s_repeats = 0;
+  }
+  __syncthreads();
+  {   // every thread fetches its own frames; rows past input_len are never read
+    const int rows = (Tn > tid) ? (Tn - tid + FAST_THREADS - 1) / FAST_THREADS : 0;
+    ptx::mbar_arrive_expect_tx(&s_bar, (uint32_t)rows * CTC_C * (uint32_t)sizeof(float));
+    for (int t = tid; t < Tn; t += FAST_THREADS)
+      ptx::bulk_load_1d(s_x + (size_t)t * FAST_XS, logits + ((size_t)t * N + n) * CTC_C, CTC_C * sizeof(float), &s_bar);
+  }
+  // label bookkeeping while the rows are in flight: offset = sum(label_len[0..n)), extended labels, repeat count
+  if (warp == 0) {
+    int acc = 0;
+    for (int i = lane; i < n; i += 32) acc += __ldg(label_len + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_off = acc;
+  }
+  __syncthreads();
+  const bool too_long = (L < 0) || (L > max_label_len) || (S > 32);
+  if (!too_long && tid < 32) {
+    int v = blank, rep = 0;
+    if (tid < S && (tid & 1)) {
+      v = flat_labels[s_off + (tid >> 1)];
+      if (tid >= 3 && v == flat_labels[s_off + (tid >> 1) - 1]) rep = 1;
+    }
+    s_ext[tid] = v;
+    rep = __popc(__ballot_sync(0xffffffffu, rep));
+    if (tid == 0) s_repeats = rep;
+  }
+  __syncthreads();
+  ptx::mbar_wait(&s_bar, 0);                        // also required before an early exit: the copies target this CTA's smem
+
+  const bool feasible = !too_long && Tn > 0 && (L + s_repeats <= Tn);
+  if (!feasible) {
+    if (tid == 0) costs[n] = too_long ? __int_as_float(0x7fc00000) : 0.0f;
+    if (grad != nullptr)
+      for (int i = tid; i < T * (CTC_C / 4); i += FAST_THREADS)
+        reinterpret_cast<float4*>(grad + ((size_t)(i / (CTC_C / 4)) * N + n) * CTC_C)[i % (CTC_C / 4)] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+
+  // ---------------- phase 0: thread = frame ----------------
+  for (int t = tid; t < Tn; t += FAST_THREADS) {
+    float4* row4 = reinterpret_cast<float4*>(s_x + (size_t)t * FAST_XS);
+    const float* row = s_x + (size_t)t * FAST_XS;
+    float v[CTC_C];
+#pragma unroll
+    for (int q = 0; q < CTC_C / 4; ++q) {
+      const float4 x = row4[q];
+      v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+    }
+    float mx[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) mx[q] = fmaxf(fmaxf(v[4 * q], v[4 * q + 1]), fmaxf(v[4 * q + 2], v[4 * q + 3]));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) mx[q] = fmaxf(fmaxf(mx[4 * q], mx[4 * q + 1]), fmaxf(mx[4 * q + 2], mx[4 * q + 3]));
+    const float mm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * LOG2E;
+    float sum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < CTC_C; ++j) {
+      v[j] = ptx::ex2(fmaf(v[j], LOG2E, -mm));
+      sum[j & 3] += v[j];
+    }
+    const float tot = (sum[0] + sum[1]) + (sum[2] + sum[3]);
+    const float lse2 = mm + ptx::lg2(tot);
+    // emission scores come from the raw logits still in shared memory
+    s_eb[t] = fmaf(row[blank], LOG2E, -lse2);
+    for (int k = 0; k < L; ++k) s_el[(size_t)t * ES + k] = fmaf(row[s_ext[2 * k + 1]], LOG2E, -lse2);
+    s_k[t] = __fdividef(grad_scale, tot);
+#pragma unroll
+    for (int q = 0; q < CTC_C / 4; ++q) row4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+  __syncthreads();
+
+  // ---------------- phase 1: alpha and reversed beta, one instruction stream ----------------
+  {
+    const bool packed = (S <= 16);
+    if (warp < (packed ? 1 : 2)) {
+      const int W = packed ? 16 : 32;
+      const int half = packed ? (lane >> 4) : warp;            // 0 = alpha, 1 = beta (state order reversed)
+      const int j = packed ? (lane & 15) : lane;
+      const bool valid = j < S;
+      const int s = valid ? (half ? S - 1 - j : j) : 0;
+      bool ok2;
+      if (half == 0) ok2 = valid && (s >= 2) && (s_ext[s] != blank) && (s_ext[s] != s_ext[s - 2]);
+      else           ok2 = valid && (s + 2 < S) && (s_ext[s + 2] != blank) && (s_ext[s + 2] != s_ext[s]);
+      const float k1 = (valid && j >= 1) ? 0.f : NEG_INF;
+      const float k2 = ok2 ? 0.f : NEG_INF;
+      // The transition masks are added by the SENDING lane (k?n = the receiver's mask), so that the three sums leaving the
+      // log come out of one FADD level: per step the dependency chain is SHFL, FMNMX3, FADD, EX2, FADD, FADD, LG2, FADD.
+      // The shuffles rotate within the W-lane segment; the wrapped-around values carry the masks of lanes 0/1 (= -inf).
+      const int seg = lane & ~(W - 1);
+      const int src1 = seg | ((j - 1) & (W - 1)), src2 = seg | ((j - 2) & (W - 1));
+      const float k1n = __shfl_sync(0xffffffffu, k1, seg | ((j + 1) & (W - 1)));
+      const float k2n = __shfl_sync(0xffffffffu, k2, seg | ((j + 2) & (W - 1)));
+      float* buf = (half ? s_beta : s_alpha) + s;
+      const float* ep = (s & 1) ? (s_el + (s >> 1)) : s_eb;
+      const int estride = (s & 1) ? ES : 1;
+      const int dt = half ? -1 : 1;
+      int t = half ? Tn - 1 : 0;
+      float a = (valid && j < 2) ? ep[(size_t)t * estride] : NEG_INF;
+      float a1 = a + k1n, a2 = a + k2n;
+      if (valid) buf[(size_t)t * AS] = a;
+      float e_next = (Tn > 1) ? ep[(size_t)(t + dt) * estride] : 0.f;
+      for (int step = 1; step < Tn; ++step) {
+        t += dt;
+        const float e = e_next;
+        if (step + 1 < Tn) e_next = ep[(size_t)(t + dt) * estride];
+        const float c = fmaxf(a, -1e30f);                                // clamp keeps (-inf) - (-inf) out of the exponent
+        const float u1 = __shfl_sync(0xffffffffu, a1, src1);
+        const float u2 = __shfl_sync(0xffffffffu, a2, src2);
+        const float m = max3(c, u1, u2);                                 // one FMNMX3 behind the shuffles (c is ready earlier)
+        const float sum = ptx::ex2(a - m) + (ptx::ex2(u1 - m) + ptx::ex2(u2 - m));
+        const float lg = ptx::lg2(sum), me = m + e;
+        a = lg + me;
+        a1 = lg + (me + k1n);
+        a2 = lg + (me + k2n);
+        if (valid) buf[(size_t)t * AS] = a;
+      }
+    }
+  }
+  __syncthreads();
+
+  const float aS1 = s_alpha[(size_t)(Tn - 1) * AS + (S - 1)];
+  const float aS2 = (S >= 2) ? s_alpha[(size_t)(Tn - 1) * AS + (S - 2)] : NEG_INF;
+  const float ll2 = lse3(aS1, aS2, NEG_INF);
+  if (tid == 0) costs[n] = -ll2 * LN2;
+  if (grad == nullptr) return;
+
+  // ---------------- phase 2: thread = frame, gradient row built in place and bulk-stored ----------------
+  for (int t = tid; t < T; t += FAST_THREADS) {
+    float4* row4 = reinterpret_cast<float4*>(s_x + (size_t)t * FAST_XS);
+    float* row = s_x + (size_t)t * FAST_XS;
+    if (t >= Tn || ll2 == NEG_INF) {
+#pragma unroll
+      for (int q = 0; q < CTC_C / 4; ++q) row4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      const float k = s_k[t];
+#pragma unroll
+      for (int q = 0; q < CTC_C / 4; ++q) {
+        float4 x = row4[q];
+        x.x *= k; x.y *= k; x.z *= k; x.w *= k;
+        row4[q] = x;
+      }
+      const float* al = s_alpha + (size_t)t * AS;
+      const float* be = s_beta + (size_t)t * AS;
+      const float eb = s_eb[t] + ll2;
+      float wb = ptx::ex2(al[0] + be[0] - eb);                       // blank states: one accumulated update
+      for (int kk = 0; kk < L; ++kk) {
+        const float el = s_el[(size_t)t * ES + kk] + ll2;
+        const float w = ptx::ex2(al[2 * kk + 1] + be[2 * kk + 1] - el);   // alpha*beta / y / p(l|x)
+        wb += ptx::ex2(al[2 * kk + 2] + be[2 * kk + 2] - eb);
+        const int c = s_ext[2 * kk + 1];
+        row[c] = fmaf(-grad_scale, w, row[c]);
+      }
+      row[blank] = fmaf(-grad_scale, wb, row[blank]);
+    }
+    ptx::fence_proxy_async_smem();
+    ptx::bulk_store_1d(grad + ((size_t)t * N + n) * CTC_C, row, CTC_C * sizeof(float));
+  }
+  ptx::bulk_commit();
+  ptx::bulk_wait_read_all();
+}
+
+size_t ctc_fast_smem_bytes(int T, int max_label_len) {
+  return sizeof(float) * (size_t)T * (FAST_XS + 2 * fast_alpha_stride(max_label_len) + fast_label_stride(max_label_len) + 2);
+}
+
 // Greedy decode: one warp per utterance, lane = frame (chunks of 32 frames).
 __global__ void __launch_bounds__(128) ctc_greedy_kernel(const float* __restrict__ logits,
                                                          const int* __restrict__ input_len, int T, int N,
@@ -355,6 +577,12 @@ int launch_ctc(const float* logits, float* grad, const int* flat_labels, const i
   return CRNN_OK;
 }
 
+// CRNN_CTC_KERNEL=generic routes S <= 32 to ctc_loss_kernel<1> as well (the parity tests run both kernels on the same inputs).
+bool ctc_force_generic() {
+  const char* e = getenv("CRNN_CTC_KERNEL");
+  return e != nullptr && strcmp(e, "generic") == 0;
+}
+
 }  // namespace
 
 extern "C" int crnn_ctc_workspace_size(int T, int N, int C, int max_label_len, size_t* bytes) {
@@ -374,6 +602,15 @@ extern "C" int crnn_ctc_loss(const float* logits, float* grad, const int* flat_l
   if (C != CTC_C) return crnn_fail(CRNN_UNSUPPORTED, "ctc: C must be 64");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int S = 2 * max_label_len + 1;
+  const bool aligned = (reinterpret_cast<uintptr_t>(logits) % 16 == 0) && (grad == nullptr || reinterpret_cast<uintptr_t>(grad) % 16 == 0);
+  if (S <= 32 && aligned && ctc_fast_smem_bytes(T, max_label_len) <= 200 * 1024 && !ctc_force_generic()) {
+    const size_t smem = ctc_fast_smem_bytes(T, max_label_len);
+    CUDA_TRY(cudaFuncSetAttribute(ctc_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctc_fast_kernel<<<N, FAST_THREADS, smem, st>>>(logits, grad, flat_labels, label_len, input_len, T, N, blank, max_label_len,
+                                                   grad_scale, costs);
+    CUDA_TRY(cudaGetLastError());
+    return CRNN_OK;
+  }
   if (S <= 32) return launch_ctc<1>(logits, grad, flat_labels, label_len, input_len, T, N, blank, grad_scale, costs, st);
   if (S <= 64) return launch_ctc<2>(logits, grad, flat_labels, label_len, input_len, T, N, blank, grad_scale, costs, st);
   if (S <= 128) return launch_ctc<4>(logits, grad, flat_labels, label_len, input_len, T, N, blank, grad_scale, costs, st);
