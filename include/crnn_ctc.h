@@ -99,6 +99,16 @@ int     crnn_forward(crnn_model* m, const float* data, const int* time_step_len,
                      float* logits_out, void* workspace, size_t workspace_bytes,
                      crnn_stream_t stream);
 
+/* Same forward, fed from PAGE-LOCKED HOST memory (the reference feeds host numpy arrays through feed_dict every iteration,
+ * lib/lstm/train.py:121-130).  The batch is copied in `chunks` image ranges on `copy_stream` into the caller-owned device
+ * tensor `data_staging` [N,W,32] while the batch-independent front end (conv1 .. conv3_2) of the previous range runs on
+ * `stream`; from the first batch-statistics BatchNorm on the batch is processed whole.  chunks <= 1 (or a batch that does not
+ * split on tile boundaries) degenerates to copy-then-compute.  `data_staging` holds the whole batch on return order of
+ * `stream` (crnn_backward reads it). */
+int     crnn_forward_host(crnn_model* m, const float* host_data, float* data_staging, const int* time_step_len,
+                          int N, int W, float* logits_out, void* workspace, size_t workspace_bytes, int chunks,
+                          crnn_stream_t stream, crnn_stream_t copy_stream);
+
 /* loss = mean_n(costs) + weight_decay * 0.5 * sum(w^2) over conv kernels + logits matrix
  * (lib/networks/network.py:655,660-662).  loss_out: 1 f32 on device. */
 int     crnn_total_loss(crnn_model* m, const float* costs, int N, float* loss_out,

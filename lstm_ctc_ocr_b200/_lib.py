@@ -34,6 +34,8 @@ SIGNATURES = {
     "crnn_model_params_changed": (c_int, [c_void_p]),
     "crnn_model_workspace_size": (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
     "crnn_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "crnn_forward_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_int,
+                                  c_void_p, c_void_p]),
     "crnn_total_loss": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "crnn_debug_tap": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "crnn_profile_begin": (c_int, [c_void_p, c_int]),

@@ -50,6 +50,7 @@ enum Epi {
 
 struct Params {
   int num_m_tiles, num_n_tiles, num_k_blocks;
+  int m_tile0;           // first M tile of this launch (batch-chunked launches of the conv front end); tiles m_tile0 .. m_tile0+num_m_tiles-1
   int kb_per_shift;      // A_PLAIN: K-block kb reads A columns (kb % kb_per_shift)*64 of row (m + kb / kb_per_shift);
                          // == num_k_blocks for an ordinary GEMM; conv5 (2x2 VALID) uses 16 -> rows t and t+1
   int merged;            // conv: the tile's 4 sub-boxes are contiguous H rows of one image -> one 128-position TMA box
@@ -175,8 +176,8 @@ __device__ __forceinline__ void run_epilogue(const Params& p, const uint32_t tba
       }
       if (grow < p.M) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4)
-          *reinterpret_cast<uint4*>(out + c0 + 2 * i) = make_uint4(pk[i], pk[i + 1], pk[i + 2], pk[i + 3]);
+        for (int i = 0; i < 16; i += 8)
+          ptx::st_global_v8(out + c0 + 2 * i, pk[i], pk[i + 1], pk[i + 2], pk[i + 3], pk[i + 4], pk[i + 5], pk[i + 6], pk[i + 7]);
       }
     }
   } else if (EPI == EPI_LOGITS) {
@@ -221,8 +222,8 @@ __device__ __forceinline__ void run_epilogue(const Params& p, const uint32_t tba
       if (EPI == EPI_RELU) {
         if (valid) {
 #pragma unroll
-          for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<uint4*>(out + c0 + 2 * i) = make_uint4(pk[i], pk[i + 1], pk[i + 2], pk[i + 3]);
+          for (int i = 0; i < 16; i += 8)
+            ptx::st_global_v8(out + c0 + 2 * i, pk[i], pk[i + 1], pk[i + 2], pk[i + 3], pk[i + 4], pk[i + 5], pk[i + 6], pk[i + 7]);
         }
       } else if (EPI == EPI_RELU_POOL22) {
         // lane = hl*16 + w : partners lane^1 (w pair) and lane^16 (h pair); rounding to bf16 is monotonic,
@@ -261,12 +262,16 @@ __device__ __forceinline__ void run_epilogue(const Params& p, const uint32_t tba
       ptx::tmem_ld_wait();
       if (valid) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8)
-          *reinterpret_cast<uint4*>(out + c0 + i) =
-              make_uint4(ptx::pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
-                         ptx::pack_bf16x2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])),
-                         ptx::pack_bf16x2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])),
-                         ptx::pack_bf16x2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
+        for (int i = 0; i < 32; i += 16)
+          ptx::st_global_v8(out + c0 + i,
+                            ptx::pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
+                            ptx::pack_bf16x2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])),
+                            ptx::pack_bf16x2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])),
+                            ptx::pack_bf16x2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])),
+                            ptx::pack_bf16x2(__uint_as_float(v[i + 8]), __uint_as_float(v[i + 9])),
+                            ptx::pack_bf16x2(__uint_as_float(v[i + 10]), __uint_as_float(v[i + 11])),
+                            ptx::pack_bf16x2(__uint_as_float(v[i + 12]), __uint_as_float(v[i + 13])),
+                            ptx::pack_bf16x2(__uint_as_float(v[i + 14]), __uint_as_float(v[i + 15])));
       }
     }
   } else if (EPI == EPI_RELU_POOL22_T || EPI == EPI_RELU_POOL12_T) {
@@ -351,8 +356,8 @@ __device__ __forceinline__ void run_epilogue(const Params& p, const uint32_t tba
       }
       if (valid) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4)
-          *reinterpret_cast<uint4*>(out + c0 + 2 * i) = make_uint4(pk[i], pk[i + 1], pk[i + 2], pk[i + 3]);
+        for (int i = 0; i < 16; i += 8)
+          ptx::st_global_v8(out + c0 + 2 * i, pk[i], pk[i + 1], pk[i + 2], pk[i + 3], pk[i + 4], pk[i + 5], pk[i + 6], pk[i + 7]);
       }
       // statistics of the values the next layer will actually read (bf16-rounded), masked to valid rows
 #pragma unroll
@@ -492,7 +497,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+        const int m_blk = p.m_tile0 + tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
         int b_row = n_blk * BLOCK_N;
         if (EPI == EPI_LSTM) b_row += (m_blk >= p.m_tiles_per_dir) ? 1024 : 0;
         // per-tile coordinates of this lane's A box (conv): image n, first H row h0
@@ -562,7 +567,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int q = warp_idx & 3;                      // TMEM lane quadrant accessible to this warp
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
+      const int m_blk = p.m_tile0 + tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);

@@ -68,7 +68,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (lane <= nA) {
       int stage = 0; uint32_t phase = 0;
       for (int pr = cluster_id; pr < num_pairs; pr += num_clusters) {
-        const int m_blk = (pr / p.num_n_tiles) * 2 + (int)rank, n_blk = pr % p.num_n_tiles;
+        const int m_blk = p.m_tile0 + (pr / p.num_n_tiles) * 2 + (int)rank, n_blk = pr % p.num_n_tiles;
         const int b_row = n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2);
         int cn = 0, ch0 = 0;
         if (AMODE == A_CONV3 && lane < nA) {
@@ -132,14 +132,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int q = warp_idx & 3;
     int it = 0;
     for (int pr = cluster_id; pr < num_pairs; pr += num_clusters, ++it) {
-      const int m_blk = (pr / p.num_n_tiles) * 2 + (int)rank, n_blk = pr % p.num_n_tiles;
+      const int m_blk = p.m_tile0 + (pr / p.num_n_tiles) * 2 + (int)rank, n_blk = pr % p.num_n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
       const int chalf = (warp_idx - 2) >> 2;
-      if (m_blk < p.num_m_tiles)
+      if (m_blk < p.m_tile0 + p.num_m_tiles)
         run_epilogue<BLOCK_N, EPI>(p, tbase, m_blk, n_blk, q, lane, chalf * (BLOCK_N / 2), (chalf + 1) * (BLOCK_N / 2));
       ptx::tc_fence_before();
       __syncwarp();

@@ -34,11 +34,14 @@ __global__ void __launch_bounds__(256) conv1_pool_kernel(const float* __restrict
   const int cg = lane & 7;                          // channel group: channels cg*8 .. cg*8+7
   const int slot = warp * 4 + (lane >> 3);          // 0..31
 
-  float wr[9][8], br[8];
+  // taps as f32x2 pairs of adjacent channels: the 288 FMAs per pooled position issue as 144 FFMA2 (the 3-register FFMA
+  // issues every other cycle per scheduler on sm_100, so the scalar loop sat at its ~37 TFLOP/s ceiling)
+  uint64_t wr[9][4];
+  float br[8];
 #pragma unroll
   for (int k = 0; k < 9; ++k)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) wr[k][j] = __ldg(wgt + k * 64 + cg * 8 + j);
+    for (int j = 0; j < 4; ++j) wr[k][j] = ptx::pack_f32x2(__ldg(wgt + k * 64 + cg * 8 + 2 * j), __ldg(wgt + k * 64 + cg * 8 + 2 * j + 1));
 #pragma unroll
   for (int j = 0; j < 8; ++j) br[j] = __ldg(bias + cg * 8 + j);
 
@@ -83,17 +86,20 @@ __global__ void __launch_bounds__(256) conv1_pool_kernel(const float* __restrict
       for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
-          float acc[8];
+          uint64_t acc2[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+          for (int j = 0; j < 4; ++j) acc2[j] = 0ull;
 #pragma unroll
           for (int r = 0; r < 3; ++r)
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
-              const float x = patch[dy + r][dx + s];
+              const uint64_t x2 = ptx::pack_f32x2(patch[dy + r][dx + s], patch[dy + r][dx + s]);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) acc[j] = fmaf(x, wr[r * 3 + s][j], acc[j]);
+              for (int j = 0; j < 4; ++j) acc2[j] = ptx::ffma2(x2, wr[r * 3 + s][j], acc2[j]);
             }
+          float acc[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ptx::unpack_f32x2(acc2[j], acc[2 * j], acc[2 * j + 1]);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             if (TRAIN) {

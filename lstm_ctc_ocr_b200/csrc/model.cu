@@ -9,6 +9,7 @@
 
 #include "gemm_launch.h"
 #include "lstm.cuh"
+#include "conv_swap.cuh"
 #include "kernels.cuh"
 #include "model_internal.h"
 
@@ -143,7 +144,11 @@ extern "C" int crnn_model_create(const crnn_config* cfg, crnn_model** out) {
   }
   m->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("CRNN_GEMM2")) m->use_2cta = std::string(e) != "0";
-  if (const char* e = getenv("CRNN_LSTM_IMPL")) m->lstm_upc = (std::string(e) == "step") ? 64 : 32;   // debug A/B switch
+  if (const char* e = getenv("CRNN_CONV2")) m->conv2_swap = std::string(e) != "pos";    // debug A/B switch: "pos" = position-major gemm.cuh kernel
+  if (const char* e = getenv("CRNN_LSTM_IMPL")) {                                                      // debug A/B switch
+    m->lstm_upc = (std::string(e) == "step") ? 64 : 32;
+    m->lstm_mc = std::string(e) == "ds" ? 2 : (std::string(e) == "persistent" || std::string(e) == "step") ? 0 : 1;
+  }
 
   // one allocation for all derived operand copies
   const size_t nB[9] = {128 * 576, 256 * 1152, 256 * 2304, 512 * 2304, 512 * 4608, 512 * 2048, 2048 * 512, 2048 * 256, 64 * 512};
@@ -185,6 +190,7 @@ extern "C" int crnn_model_destroy(crnn_model* m) {
   if (m->wblock_bwd) cudaFree(m->wblock_bwd);
   for (auto e : m->prof_events) cudaEventDestroy(e);
   for (auto e : m->prof_events_bwd) cudaEventDestroy(e);
+  for (auto e : m->chunk_events) cudaEventDestroy(e);
   delete m;
   return CRNN_OK;
 }
@@ -309,6 +315,7 @@ static int build_plan(crnn_model* m, int N, int W, void* ws, cudaStream_t st) {
   pl.mg2 = (pl.H1 % 8) == 0; pl.mg3 = (pl.H2 % 16) == 0; pl.mg4 = (pl.H2 % 32) == 0;
   pl.wm2 = (pl.H1 % 4) == 0; pl.wm3 = (pl.H2 % 8) == 0; pl.wm4 = (pl.H2 % 16) == 0;
   CRNN_TRY(make_tmap_nhwc(&pl.tA_c2, pl.a1, N, pl.H1, 16, 64, pl.mg2 ? 8 : 2));
+  CRNN_TRY(make_tmap_nhwc(&pl.tA_c2s, pl.a1, N, pl.H1, 16, 64, 8));
   CRNN_TRY(make_tmap_nhwc(&pl.tA_c31, pl.a2, N, pl.H2, 8, 128, pl.mg3 ? 16 : 4));
   CRNN_TRY(make_tmap_nhwc(&pl.tA_c32, pl.a3, N, pl.H2, 8, 256, pl.mg3 ? 16 : 4));
   CRNN_TRY(make_tmap_nhwc(&pl.tA_c41, pl.a3p, N, pl.H2, 4, 256, pl.mg4 ? 32 : 8));
@@ -368,8 +375,12 @@ int ensure_plan(crnn_model* m, int N, int W, void* ws, cudaStream_t st) {
   return CRNN_OK;
 }
 
-extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_step_len, int N, int W, float* logits_out,
-                            void* workspace, size_t workspace_bytes, crnn_stream_t stream) {
+// Forward pass.  `host_data` != nullptr (crnn_forward_host): the batch is still in page-locked HOST memory; it is cut into
+// `chunks` image ranges whose H2D copies run on `copy_st` while the batch-independent front end (conv1 .. conv3_2 + pools) of
+// the previous range runs on `st` -- the copy (33.6 MB at batch 1024 x 32x256, ~0.65 ms over PCIe 5) hides behind ~0.9 ms of
+// compute instead of preceding it.  From conv4_1 on (batch-statistics BatchNorm) the batch is processed whole.
+static int forward_impl(crnn_model* m, const float* data, const float* host_data, const int* time_step_len, int N, int W,
+                        float* logits_out, void* workspace, size_t workspace_bytes, int chunks, cudaStream_t st, cudaStream_t copy_st) {
   if (!m || !data || !time_step_len || !logits_out || !workspace) return crnn_fail(CRNN_INVALID_VALUE, "forward: null pointer");
   if (!m->params) return crnn_fail(CRNN_NOT_BOUND, "forward: call crnn_model_bind first");
   if (N <= 0 || W < 8 || (W % 4) != 0) return crnn_fail(CRNN_INVALID_VALUE, "forward: need N>0, W>=8, W%%4==0");
@@ -377,7 +388,6 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
   CRNN_TRY(crnn_model_workspace_size(m, N, W, m->training ? 1 : 0, &need));
   if (workspace_bytes < need) return crnn_fail(CRNN_WORKSPACE_TOO_SMALL, "forward: workspace %zu < %zu", workspace_bytes, need);
   if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return crnn_fail(CRNN_INVALID_VALUE, "forward: workspace must be 1024-byte aligned");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (m->dirty) CRNN_TRY(prepare_weights(m, st));
   Plan& pl = m->plan;
   CRNN_TRY(ensure_plan(m, N, W, workspace, st));
@@ -388,42 +398,83 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
 #define STAGE_MARK() do { if (ev) CUDA_TRY(cudaEventRecord(ev[evi++], st)); } while (0)
   STAGE_MARK();
 
-  // conv1 + pool1 (SIMT, HBM/FMA-bound: K = 9)
-  CRNN_TRY(launch_conv1_pool(data, m->P("conv1/weights"), m->P("conv1/biases"), pl.a1, pl.train ? pl.am1 : nullptr, N, W, sms, st));
-  STAGE_MARK();
-  // conv2 + ReLU + pool2
-  {
-    gemm::Params p = conv_params(N, H1, 16, 64, 128, 128, m->P("conv2/biases"), pl.a2, pl.mg2);
-    if (pl.train) {
-      p.argmax = pl.am2;
-      // (CTA pairs with a 128-column N tile were measured slower here: 0.371 vs 0.348 ms -- conv2 is bound by the MMA rate at
-      //  N = 128 and its 2x2-pool epilogue, not by the operand feed)
-      CRNN_TRY((launch_gemm<128, gemm::A_CONV3, gemm::EPI_RELU_POOL22_T, 6>(pl.tA_c2, m->tB_c2, p, sms, st)));
-    } else {
-      CRNN_TRY((launch_gemm<128, gemm::A_CONV3, gemm::EPI_RELU_POOL22, 6>(pl.tA_c2, m->tB_c2, p, sms, st)));
+  // ---- front end, per image range [n0, n0 + nc): conv1+pool1, conv2+pool2, conv3_1, conv3_2+pool (all batch-independent)
+  const int sb3 = (H2 + 3) / 4;                      // 32-position sub-boxes per image of the conv3 layers (Wd = 8 -> 4 H rows)
+  const int sb2 = (H1 + 1) / 2;                      // conv2 through gemm.cuh (Wd = 16 -> 2 H rows)
+  if (chunks < 1) chunks = 1;
+  if (chunks > kMaxChunks) chunks = kMaxChunks;
+  int nc = (N + chunks - 1) / chunks;
+  // a range must start on a tile-PAIR boundary of every layer (128-position tiles = 4 sub-boxes, pairs = 8)
+  if (chunks > 1 && ((nc * sb3) % 8 != 0 || (nc * sb2) % 8 != 0)) { chunks = 1; nc = N; }
+  if (host_data != nullptr) {
+    if (m->chunk_events.empty()) {
+      m->chunk_events.resize(kMaxChunks + 1);
+      for (auto& e : m->chunk_events) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    // the staging tensor may still be read by work queued earlier on `st` (previous forward / backward)
+    CUDA_TRY(cudaEventRecord(m->chunk_events[kMaxChunks], st));
+    CUDA_TRY(cudaStreamWaitEvent(copy_st, m->chunk_events[kMaxChunks], 0));
+    for (int c = 0; c * nc < N; ++c) {
+      const int n0 = c * nc, n1 = (n0 + nc < N) ? n0 + nc : N;
+      const size_t off = (size_t)n0 * W * 32;
+      CUDA_TRY(cudaMemcpyAsync(const_cast<float*>(data) + off, host_data + off, (size_t)(n1 - n0) * W * 32 * sizeof(float),
+                               cudaMemcpyHostToDevice, copy_st));
+      CUDA_TRY(cudaEventRecord(m->chunk_events[c], copy_st));
     }
   }
-  STAGE_MARK();
-  // conv3_1 + ReLU
-  {
-    gemm::Params p = conv_params(N, H2, 8, 128, 256, 256, m->P("conv3_1/biases"), pl.a3, pl.mg3);
-    if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_RELU, 6>(pl.tA_c31, m->tBh_c31, p, sms, st)));
-    else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_RELU, 4>(pl.tA_c31, m->tB_c31, p, sms, st)));
-  }
-  STAGE_MARK();
-  // conv3_2 + ReLU + height pool
-  {
-    gemm::Params p = conv_params(N, H2, 8, 256, 256, 256, m->P("conv3_2/biases"), pl.a3p, pl.mg3);
-    if (pl.train) {
-      p.argmax = pl.am3;
-      if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_RELU_POOL12_T, 6>(pl.tA_c32, m->tBh_c32, p, sms, st)));
-      else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_RELU_POOL12_T, 4>(pl.tA_c32, m->tB_c32, p, sms, st)));
-    } else {
-      if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_RELU_POOL12, 6>(pl.tA_c32, m->tBh_c32, p, sms, st)));
-      else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_RELU_POOL12, 4>(pl.tA_c32, m->tB_c32, p, sms, st)));
+  for (int c = 0; c * nc < N; ++c) {
+    const int n0 = c * nc, n1 = (n0 + nc < N) ? n0 + nc : N, cn = n1 - n0;
+    const bool mark = (n1 == N) && chunks == 1;      // per-stage events only make sense for an unchunked front end
+    if (host_data != nullptr) CUDA_TRY(cudaStreamWaitEvent(st, m->chunk_events[c], 0));
+    // conv1 + pool1 (SIMT: K = 9)
+    {
+      const size_t o1 = (size_t)n0 * H1 * 16 * 64;
+      CRNN_TRY(launch_conv1_pool(data + (size_t)n0 * W * 32, m->P("conv1/weights"), m->P("conv1/biases"), pl.a1 + o1,
+                                 pl.train ? pl.am1 + o1 : nullptr, cn, W, sms, st));
     }
+    if (mark) STAGE_MARK();
+    // conv2 + ReLU + pool2
+    if (m->conv2_swap) {
+      convsw::Params p;
+      p.Nimg = cn; p.img0 = n0; p.H = H1; p.tiles_per_img = (H1 + 15) / 16; p.bias = m->P("conv2/biases"); p.out = pl.a2;
+      p.argmax = pl.train ? pl.am2 : nullptr;
+      if (pl.train) CRNN_TRY(launch_conv2_swap<true>(pl.tA_c2s, m->tB_c2, p, sms, st));
+      else CRNN_TRY(launch_conv2_swap<false>(pl.tA_c2s, m->tB_c2, p, sms, st));
+    } else {
+      gemm::Params p = conv_params(N, H1, 16, 64, 128, 128, m->P("conv2/biases"), pl.a2, pl.mg2);
+      if (chunks > 1) { p.m_tile0 = n0 * sb2 / 4; p.num_m_tiles = cn * sb2 / 4; }
+      if (pl.train) {
+        p.argmax = pl.am2;
+        CRNN_TRY((launch_gemm<128, gemm::A_CONV3, gemm::EPI_RELU_POOL22_T, 6>(pl.tA_c2, m->tB_c2, p, sms, st)));
+      } else {
+        CRNN_TRY((launch_gemm<128, gemm::A_CONV3, gemm::EPI_RELU_POOL22, 6>(pl.tA_c2, m->tB_c2, p, sms, st)));
+      }
+    }
+    if (mark) STAGE_MARK();
+    // conv3_1 + ReLU
+    {
+      gemm::Params p = conv_params(N, H2, 8, 128, 256, 256, m->P("conv3_1/biases"), pl.a3, pl.mg3);
+      if (chunks > 1) { p.m_tile0 = n0 * sb3 / 4; p.num_m_tiles = cn * sb3 / 4; }
+      if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_RELU, 6>(pl.tA_c31, m->tBh_c31, p, sms, st)));
+      else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_RELU, 4>(pl.tA_c31, m->tB_c31, p, sms, st)));
+    }
+    if (mark) STAGE_MARK();
+    // conv3_2 + ReLU + height pool
+    {
+      gemm::Params p = conv_params(N, H2, 8, 256, 256, 256, m->P("conv3_2/biases"), pl.a3p, pl.mg3);
+      if (chunks > 1) { p.m_tile0 = n0 * sb3 / 4; p.num_m_tiles = cn * sb3 / 4; }
+      if (pl.train) {
+        p.argmax = pl.am3;
+        if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_RELU_POOL12_T, 6>(pl.tA_c32, m->tBh_c32, p, sms, st)));
+        else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_RELU_POOL12_T, 4>(pl.tA_c32, m->tB_c32, p, sms, st)));
+      } else {
+        if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_RELU_POOL12, 6>(pl.tA_c32, m->tBh_c32, p, sms, st)));
+        else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_RELU_POOL12, 4>(pl.tA_c32, m->tB_c32, p, sms, st)));
+      }
+    }
+    if (mark) STAGE_MARK();
   }
-  STAGE_MARK();
+  if (chunks > 1) for (int i = 0; i < 4; ++i) STAGE_MARK();     // keep the event layout (front-end stages read as ~0)
   CUDA_TRY(cudaMemsetAsync(pl.stats, 0, 2 * 2 * 512 * sizeof(double), st));
   const double bn_count = (double)N * H2 * 4;
   // conv4_1 + bias -> batch statistics -> BN + ReLU
@@ -483,23 +534,46 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
     lp.xproj = pl.xproj; lp.h_state = pl.h_state; lp.lstm_out = pl.lstm_out; lp.seq_len = time_step_len;
     lp.Nimg = N; lp.Npad = pl.Npad; lp.H = H2; lp.T = T; lp.tiles_per_dir = pl.Npad / 128;
     lp.gates = pl.train ? pl.gates : nullptr; lp.csave = pl.train ? pl.csave : nullptr;
+    static long long* d_trace = nullptr;          // debug timeline (CRNN_LSTM_TRACE=1), printed to stderr after every launch
+    const bool want_trace = getenv("CRNN_LSTM_TRACE") != nullptr;
+    if (want_trace && d_trace == nullptr) CUDA_TRY(cudaMalloc(&d_trace, 2 * 4 * 16 * sizeof(long long)));
+    if (want_trace) CUDA_TRY(cudaMemsetAsync(d_trace, 0, 2 * 4 * 16 * sizeof(long long), st));
+    lp.trace = want_trace ? d_trace : nullptr;
+    lp.swap_ls = getenv("CRNN_LSTM_SWAPLS") != nullptr;
     auto kern = lstm::lstm_persistent_kernel<CS>;
+    auto kern_mc = lstm::lstm_mc_kernel<CS, false>;
+    auto kern_ds = lstm::lstm_mc_kernel<CS, true>;
     static bool attr = false;
     if (!attr) {
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::Cfg<CS>::SMEM_BYTES));
+      CUDA_TRY(cudaFuncSetAttribute(kern_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::CfgMc<CS>::SMEM_BYTES));
+      CUDA_TRY(cudaFuncSetAttribute(kern_ds, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::CfgMc<CS>::SMEM_BYTES));
       attr = true;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(CS * 2 * lp.tiles_per_dir);
-    cfg.blockDim = dim3(lstm::NUM_THREADS);
-    cfg.dynamicSmemBytes = lstm::Cfg<CS>::SMEM_BYTES;
+    cfg.blockDim = dim3(m->lstm_mc ? lstm::MC_THREADS : lstm::NUM_THREADS);
+    cfg.dynamicSmemBytes = m->lstm_mc ? lstm::CfgMc<CS>::SMEM_BYTES : lstm::Cfg<CS>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, pl.tA_hall, m->tB_h128, lp));
+    if (m->lstm_mc == 2) CUDA_TRY(cudaLaunchKernelEx(&cfg, kern_ds, m->tB_h128, lp));
+    else if (m->lstm_mc == 1) CUDA_TRY(cudaLaunchKernelEx(&cfg, kern_mc, m->tB_h128, lp));
+    else CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, pl.tA_hall, m->tB_h128, lp));
+    if (want_trace) {
+      long long h[2 * 4 * 16];
+      CUDA_TRY(cudaStreamSynchronize(st));
+      CUDA_TRY(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
+      for (int c = 0; c < 2; ++c)
+        for (int s = 0; s < 4; ++s) {
+          fprintf(stderr, "lstm_trace cta%d step%d:", c ? 5 : 0, 8 + s);
+          for (int e = 0; e < 12; ++e) fprintf(stderr, " %lld", h[(c * 4 + s) * 16 + e] ? h[(c * 4 + s) * 16 + e] - h[(c * 4) * 16] : -1);
+          fprintf(stderr, "\n");
+        }
+    }
   } else {
     // per-step launches (debug fallback, CRNN_LSTM_IMPL=step): both directions stacked along M
     CUDA_TRY(cudaMemsetAsync(pl.h_state, 0, (size_t)2 * pl.Npad * 256 * 2, st));
@@ -528,6 +602,20 @@ extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_st
   STAGE_MARK();
 #undef STAGE_MARK
   return CRNN_OK;
+}
+
+extern "C" int crnn_forward(crnn_model* m, const float* data, const int* time_step_len, int N, int W, float* logits_out,
+                            void* workspace, size_t workspace_bytes, crnn_stream_t stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return forward_impl(m, data, nullptr, time_step_len, N, W, logits_out, workspace, workspace_bytes, 1, st, st);
+}
+
+extern "C" int crnn_forward_host(crnn_model* m, const float* host_data, float* data_staging, const int* time_step_len, int N, int W,
+                                 float* logits_out, void* workspace, size_t workspace_bytes, int chunks, crnn_stream_t stream,
+                                 crnn_stream_t copy_stream) {
+  if (!host_data || !data_staging) return crnn_fail(CRNN_INVALID_VALUE, "forward_host: null pointer");
+  return forward_impl(m, data_staging, host_data, time_step_len, N, W, logits_out, workspace, workspace_bytes, chunks,
+                      reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<cudaStream_t>(copy_stream));
 }
 
 // ------------------------------------------------------------------------------------------------ profiling

@@ -37,6 +37,8 @@ static const char* kBwdStageNames[] = {"zero+logits_bwd", "lstm_bptt", "lstm_wgr
                                        "conv2_dgrad", "conv1_wgrad"};
 static const int kNumBwdStages = 20;
 
+static const int kMaxChunks = 16;
+
 struct Plan {
   int N = 0, W = 0, H1 = 0, H2 = 0, T = 0, Npad = 0;
   void* ws = nullptr;
@@ -44,6 +46,7 @@ struct Plan {
   float* c_state;
   double* stats;        // [2 layers][2][512]
   float* bn;            // [2 layers][4][512]: scale, shift, mean, invstd
+  CUtensorMap tA_c2s;   // conv2 input through 128-position boxes regardless of H (swapped-operand kernel, conv_swap.cuh)
   CUtensorMap tA_c2, tA_c31, tA_c32, tA_c41, tA_c42, tA_c5, tA_x, tA_h[2], tA_l, tA_hall;
   // conv A maps use 128-position boxes (`mg*` = 1) when a tile's 4 sub-boxes are contiguous rows of one image;
   // the weight-gradient GEMMs read the same tensors through 64- or 32-position boxes (tW_*)
@@ -87,8 +90,12 @@ struct crnn_model {
   double* grad_sumsq = nullptr;
   CUtensorMap tBh_c2, tBh_c31, tBh_c32, tBh_c41, tBh_c42, tBh_c5, tBh_x;   // same weights, box = 128 rows: per-CTA half of a 256-row N tile
   bool use_2cta = true;      // cta_group::2 GEMM pairs for the Nc % 256 == 0 layers (CRNN_GEMM2=0 disables; debug A/B switch)
+  bool conv2_swap = true;    // conv2 with channels on the MMA M side and 256 positions on N (conv_swap.cuh); CRNN_CONV2=pos -> gemm.cuh
+  int lstm_mc = 1;           // recurrence through lstm::lstm_mc_kernel (no per-step cluster barrier): 1 = global slice + multicast bulk copy
+                             // (CRNN_LSTM_IMPL=mc), 2 = slices pushed smem -> peer smem (CRNN_LSTM_IMPL=ds)
   int lstm_upc = 32;         // hidden units per gate tile: 32 = persistent cluster kernel (default), 64 = per-step launches
   Plan plan;
+  std::vector<cudaEvent_t> chunk_events;   // crnn_forward_host: one per H2D chunk + one "staging free" event
   // per-stage CUDA-event profiling (crnn_profile_*): events are recorded on the caller's stream between stages
   std::vector<cudaEvent_t> prof_events;   // [slots][kNumStages + 1]
   int prof_slots = 0, prof_used = 0;

@@ -69,6 +69,23 @@ __device__ __forceinline__ void bulk_store_1d(void* dst_gmem, const void* src_sm
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+// 1-D bulk copy global -> the SAME smem offset of every CTA in `cta_mask`; each destination's mbarrier (same offset) gets the bytes
+__device__ __forceinline__ void bulk_load_1d_mc(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(src_gmem)), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+// Shared-memory matrix descriptor, K-major operand, NO swizzle: 8-row x 16-B core matrices (128 B contiguous);
+// `lbo` = byte distance between the two core matrices of one K=16 step, `sbo` = byte distance between 8-row groups.
+__device__ __forceinline__ uint64_t make_desc_k_nosw(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(lbo >> 4) << 16;
+  d |= static_cast<uint64_t>(sbo >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+
 // ------------------------------------------------------------------ TMA loads (tile mode, OOB -> 0)
 __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
@@ -252,6 +269,31 @@ __device__ __forceinline__ uint32_t hmax2_bf16(uint32_t a, uint32_t b) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+// ------------------------------------------------------------------ 256-bit global store (sm_100 STG.256; 32-B aligned address)
+// A row-per-thread epilogue store touches 32 different lines per instruction; with 16-B stores every instruction fills half a
+// 32-B sector per lane, with 32-B stores a whole one -- half the store wavefronts for the same bytes.
+__device__ __forceinline__ void st_global_v8(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                             uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f),
+               "r"(g), "r"(h)
+               : "memory");
+}
+
+// ------------------------------------------------------------------ packed f32x2 FMA (sm_100 FFMA2: two IEEE fma.rn per lane)
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
 
 __device__ __forceinline__ float ex2(float x) {
   float y;

@@ -138,6 +138,25 @@ class CrnnModel:
                                     nbytes, _stream()))
         return out
 
+    def forward_host(self, host_data, time_step_len, chunks=4, out=None):
+        """host_data: C-contiguous f32 numpy array [N,W,32] in PAGE-LOCKED memory.  The H2D copy is cut into `chunks` image
+        ranges on a side stream and overlapped with the conv front end (crnn_forward_host).  Returns (logits, device data)."""
+        N, W, Hh = host_data.shape
+        if Hh != 32:
+            raise CrnnError("data must be [N, W, 32] (cfg.NUM_FEATURES = 32)")
+        assert host_data.dtype == np.float32 and host_data.flags.c_contiguous
+        T = W // 4 - 1
+        if out is None:
+            out = torch.empty((T, N, NCLASSES), dtype=torch.float32, device=self.device)
+        if getattr(self, "_stage", None) is None or self._stage.shape != (N, W, 32):
+            self._stage = torch.empty((N, W, 32), dtype=torch.float32, device=self.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        ws, nbytes = self._workspace(N, W)
+        check(self.lib.crnn_forward_host(self.handle, host_data.ctypes.data, self._stage.data_ptr(), time_step_len.data_ptr(), N, W,
+                                         out.data_ptr(), ws, nbytes, int(chunks), _stream(), self._copy_stream.cuda_stream))
+        return out, self._stage
+
     def tap(self, name, N, W):
         """Intermediate of the last forward as f32 NHWC (tests only)."""
         H1, H2 = W // 2, W // 4

@@ -198,10 +198,14 @@ def test_forward_loss_decode_vs_committed_golden():
         assert np.array_equal(logits[int(tsl[n]):, n].cpu().numpy(), np.broadcast_to(b, (T - int(tsl[n]), 64)))
 
 
+@pytest.mark.parametrize("conv2", ["swap", "pos"])
 @pytest.mark.parametrize("N,W,widths", [(3, 100, None), (5, 24, [24, 20, 9, 24, 16]), (2, 160, [160, 131]), (130, 40, None)])
-def test_forward_layers_vs_oracle(N, W, widths):
+def test_forward_layers_vs_oracle(N, W, widths, conv2, monkeypatch):
+    """Every layer against the fp64 oracle; conv2 through both kernels (conv_swap.cuh: channels on the MMA M side, default;
+    gemm.cuh: positions on M, CRNN_CONV2=pos)."""
     from lstm_ctc_ocr_b200 import engine
     from oracle import crnn_oracle as O
+    monkeypatch.setenv("CRNN_CONV2", conv2)
     pn = O.randomize_params(O.init_params(3, dtype=np.float32, logits_scale=10.0))
     data, lab, ll, tsl = O.synth_batch(N, W, seed=5, widths=widths, min_len=1, max_len=3)
     m = engine.CrnnModel(device=DEV)
@@ -220,6 +224,26 @@ def test_forward_layers_vs_oracle(N, W, widths):
     co, _ = O.ctc_loss_np(lo.numpy(), lab, ll, tsl)
     loss_o = co.mean() + float(O.l2_reg(O.to_torch(pn), 1e-5))
     assert abs(float(m.total_loss(costs).item()) - loss_o) / loss_o < 5e-3
+
+
+@pytest.mark.parametrize("chunks", [1, 3, 4])
+def test_forward_from_page_locked_host_memory_matches_device_forward(chunks):
+    """crnn_forward_host (chunked H2D on a side stream overlapped with the conv front end) == crnn_forward on the same batch;
+    chunks=3 does not split 64 images on tile-pair boundaries and must degenerate to one range."""
+    from lstm_ctc_ocr_b200 import engine, synthetic
+    N, W = 64, 64
+    params = synthetic.init_params(3, logits_scale=10.0)
+    data, _, _, tsl = synthetic.synth_batch(N, W, seed=21, widths=np.random.default_rng(3).integers(8, 65, size=N))
+    m = engine.CrnnModel(device=DEV)
+    m.load_params(params)
+    d_tsl = torch.tensor(tsl, device=DEV)
+    ref = m.forward(torch.tensor(data, device=DEV), d_tsl).clone()
+    host = torch.from_numpy(data.copy()).pin_memory()
+    for _ in range(2):                                   # second call re-uses the staging tensor while the first may be in flight
+        logits, staged = m.forward_host(host.numpy(), d_tsl, chunks=chunks)
+    torch.cuda.synchronize()
+    assert torch.equal(staged.cpu(), torch.from_numpy(data))
+    assert rel(logits.cpu().numpy(), ref.cpu().numpy()) < 2e-3      # BN-statistic atomics order is the only difference
 
 
 def test_session_run_reads_like_the_reference_solver():
@@ -307,8 +331,10 @@ def test_full_size_c3_properties():
     assert int(out.max()) <= 62 and int(out.min()) >= 0
 
 
-def test_persistent_cluster_lstm_matches_per_step_kernel():
-    """csrc/lstm.cuh (one persistent cluster launch) vs the per-step GEMM+cell launches (CRNN_LSTM_IMPL=step)."""
+@pytest.mark.parametrize("impl", ["persistent", "mc", "ds"])
+def test_cluster_lstm_kernels_match_per_step_kernel(impl):
+    """csrc/lstm.cuh -- v1 (`persistent`: cluster barrier per step), v2 (`mc`: global slice + multicast bulk copy, `ds`: slices
+    pushed smem -> peer smem) -- vs the per-step GEMM+cell launches (CRNN_LSTM_IMPL=step)."""
     from lstm_ctc_ocr_b200 import engine, synthetic
     N, W = 200, 100
     params = synthetic.init_params(3, logits_scale=10.0)
@@ -316,14 +342,16 @@ def test_persistent_cluster_lstm_matches_per_step_kernel():
     data, _, _, tsl = synthetic.synth_batch(N, W, seed=12, widths=widths)
     t = lambda a: torch.tensor(a, device=DEV)
     outs = []
-    for impl in ("persistent", "step"):
-        os.environ["CRNN_LSTM_IMPL"] = impl
+    for which in (impl, "step"):
+        os.environ["CRNN_LSTM_IMPL"] = which
         try:
             m = engine.CrnnModel(device=DEV)
         finally:
             os.environ.pop("CRNN_LSTM_IMPL", None)
         m.load_params(params)
         logits = m.forward(t(data), t(tsl)).clone()
+        logits_again = m.forward(t(data), t(tsl)).clone()           # the exchange buffers are reused across launches
+        assert rel(logits_again.cpu().numpy(), logits.cpu().numpy()) < 5e-3
         outs.append((logits.cpu().numpy(), m.tap("lstm_out", N, W).cpu().numpy()))
         del m
     assert np.abs(outs[0][1] - outs[1][1]).max() <= 1e-2        # bf16 h, identical math up to MMA tile order
