@@ -238,7 +238,8 @@ def main():
         data, lab, ll, tsl = batches[i % nrot][5]
         return sess.run(loss_h, feed_dict={net.data: data, net.labels: lab, net.time_step_len: tsl, net.labels_len: ll,
                                            net.keep_prob: 0.5})
-    for i in range(max(3, 2 * nrot)):      # every rotating host buffer is fed twice (page-locked in place on its second sighting)
+    for i in range(max(3, 3 * nrot)):      # every rotating host buffer is fed three times: page-locked in place on its second
+                                           # sighting, fed through the chunked crnn_forward_host path from the third on
         e2e_step(i)
     sync_all()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -297,7 +297,9 @@ __device__ __forceinline__ void bulk_copy_s2s_cluster(uint32_t dst_cluster_addr,
                : "memory");
 }
 
-template <int CS, bool DS>
+// MODE: 0 = global slice + multicast ("mc"), 1 = smem -> peer smem pushes ("ds"), 2 = smem slice -> bulk store to global ->
+// multicast to the 7 peers ("ms": no generic-proxy global stores, hence no full fence.proxy.async on the critical path)
+template <int CS, int MODE>
 __global__ void __launch_bounds__(MC_THREADS, 1)
 lstm_mc_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
   static_assert(CS == 8, "8 CTAs x 32 units");
@@ -305,7 +307,8 @@ lstm_mc_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
   constexpr int UPC = C::UPC, NCOLS = C::NCOLS;
   constexpr uint32_t IDESC = ptx::make_idesc_bf16(BLOCK_M, NCOLS);
   constexpr int HALF = UPC / 2;                             // units per epilogue warp
-  constexpr uint32_t FILL_TX = DS ? (CS - 1) * C::SLICE_BYTES : C::A_BYTES;   // DS: the local slice is written in place
+  constexpr bool DS = (MODE == 1), MS = (MODE == 2), LOCAL = DS || MS;            // LOCAL: own slice written in place
+  constexpr uint32_t FILL_TX = LOCAL ? (CS - 1) * C::SLICE_BYTES : C::A_BYTES;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -325,8 +328,8 @@ lstm_mc_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
   if (warp_idx == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmW);
     // DS: one arrival arms the byte count (MMA thread), the other says "the local slice is in place" (epilogue)
-    ptx::mbar_init(&a_full[0], DS ? 2 : 1);
-    ptx::mbar_init(&a_full[1], DS ? 2 : 1);
+    ptx::mbar_init(&a_full[0], LOCAL ? 2 : 1);
+    ptx::mbar_init(&a_full[1], LOCAL ? 2 : 1);
     ptx::mbar_init(b_full, 1);
     ptx::mbar_init(acc_full, 1);
     ptx::fence_barrier_init();
@@ -449,7 +452,7 @@ lstm_mc_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
       // ---- h_t slice first (it is on the critical path), bookkeeping stores afterwards
       if (s + 1 < p.T) {
         const int nb = (s + 1) & 1;
-        if (DS) {
+        if (LOCAL) {
           uint8_t* dst = smem_a + nb * C::A_BYTES + slice_off;
           *reinterpret_cast<uint4*>(dst) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
           *reinterpret_cast<uint4*>(dst + 2048) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
@@ -464,19 +467,28 @@ lstm_mc_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
         ptx::tc_fence_before();
         asm volatile("bar.sync 1, %0;" ::"n"(MC_EPI_THREADS) : "memory");
         if (warp_idx == 2) {
+          uint8_t* my_slice = smem_a + nb * C::A_BYTES + rank * C::SLICE_BYTES;
           if (DS) {
             if (lane < CS) {
               if (lane == rank) {
                 ptx::mbar_arrive(&a_full[nb]);
               } else {
-                const uint32_t dst = ptx::mapa(ptx::smem_u32(smem_a + nb * C::A_BYTES + rank * C::SLICE_BYTES), (uint32_t)lane);
+                const uint32_t dst = ptx::mapa(ptx::smem_u32(my_slice), (uint32_t)lane);
                 const uint32_t bar = ptx::mapa(ptx::smem_u32(&a_full[nb]), (uint32_t)lane);
-                bulk_copy_s2s_cluster(dst, smem_a + nb * C::A_BYTES + rank * C::SLICE_BYTES, C::SLICE_BYTES, bar);
+                bulk_copy_s2s_cluster(dst, my_slice, C::SLICE_BYTES, bar);
               }
             }
+          } else if (MS) {
+            if (lane == 0) {
+              uint8_t* g = hx0 + (size_t)nb * hx_buf_stride;
+              ptx::bulk_store_1d(g, my_slice, C::SLICE_BYTES);                // async proxy: smem -> global (L2)
+              ptx::bulk_commit();
+              asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // writes performed, not just the smem reads
+              ptx::bulk_load_1d_mc(my_slice, g, C::SLICE_BYTES, &a_full[nb], (uint16_t)(((1u << CS) - 1) & ~(1u << rank)));
+              ptx::mbar_arrive(&a_full[nb]);                                  // the local slice is already in place
+            }
           } else if (lane == 0) {
-            ptx::bulk_load_1d_mc(smem_a + nb * C::A_BYTES + rank * C::SLICE_BYTES, hx0 + (size_t)nb * hx_buf_stride, C::SLICE_BYTES,
-                                 &a_full[nb], (uint16_t)((1u << CS) - 1));
+            ptx::bulk_load_1d_mc(my_slice, hx0 + (size_t)nb * hx_buf_stride, C::SLICE_BYTES, &a_full[nb], (uint16_t)((1u << CS) - 1));
           }
           __syncwarp();
           LSTM_TRACE(9);

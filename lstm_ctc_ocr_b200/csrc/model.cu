@@ -10,6 +10,7 @@
 #include "gemm_launch.h"
 #include "lstm.cuh"
 #include "conv_swap.cuh"
+#include "conv1_tc.cuh"
 #include "kernels.cuh"
 #include "model_internal.h"
 
@@ -144,10 +145,11 @@ extern "C" int crnn_model_create(const crnn_config* cfg, crnn_model** out) {
   }
   m->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("CRNN_GEMM2")) m->use_2cta = std::string(e) != "0";
+  if (const char* e = getenv("CRNN_CONV1")) m->conv1_tc = std::string(e) != "simt";    // debug A/B switch
   if (const char* e = getenv("CRNN_CONV2")) m->conv2_swap = std::string(e) != "pos";    // debug A/B switch: "pos" = position-major gemm.cuh kernel
   if (const char* e = getenv("CRNN_LSTM_IMPL")) {                                                      // debug A/B switch
     m->lstm_upc = (std::string(e) == "step") ? 64 : 32;
-    m->lstm_mc = std::string(e) == "ds" ? 2 : (std::string(e) == "persistent" || std::string(e) == "step") ? 0 : 1;
+    m->lstm_mc = std::string(e) == "ds" ? 2 : std::string(e) == "mc" ? 1 : (std::string(e) == "persistent" || std::string(e) == "step") ? 0 : 3;
   }
 
   // one allocation for all derived operand copies
@@ -429,8 +431,12 @@ static int forward_impl(crnn_model* m, const float* data, const float* host_data
     // conv1 + pool1 (SIMT: K = 9)
     {
       const size_t o1 = (size_t)n0 * H1 * 16 * 64;
-      CRNN_TRY(launch_conv1_pool(data + (size_t)n0 * W * 32, m->P("conv1/weights"), m->P("conv1/biases"), pl.a1 + o1,
+      if (m->conv1_tc)
+        CRNN_TRY(launch_conv1_tc(data + (size_t)n0 * W * 32, m->P("conv1/weights"), m->P("conv1/biases"), pl.a1 + o1,
                                  pl.train ? pl.am1 + o1 : nullptr, cn, W, sms, st));
+      else
+        CRNN_TRY(launch_conv1_pool(data + (size_t)n0 * W * 32, m->P("conv1/weights"), m->P("conv1/biases"), pl.a1 + o1,
+                                   pl.train ? pl.am1 + o1 : nullptr, cn, W, sms, st));
     }
     if (mark) STAGE_MARK();
     // conv2 + ReLU + pool2
@@ -541,13 +547,15 @@ static int forward_impl(crnn_model* m, const float* data, const float* host_data
     lp.trace = want_trace ? d_trace : nullptr;
     lp.swap_ls = getenv("CRNN_LSTM_SWAPLS") != nullptr;
     auto kern = lstm::lstm_persistent_kernel<CS>;
-    auto kern_mc = lstm::lstm_mc_kernel<CS, false>;
-    auto kern_ds = lstm::lstm_mc_kernel<CS, true>;
+    auto kern_mc = lstm::lstm_mc_kernel<CS, 0>;
+    auto kern_ds = lstm::lstm_mc_kernel<CS, 1>;
+    auto kern_ms = lstm::lstm_mc_kernel<CS, 2>;
     static bool attr = false;
     if (!attr) {
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::Cfg<CS>::SMEM_BYTES));
       CUDA_TRY(cudaFuncSetAttribute(kern_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::CfgMc<CS>::SMEM_BYTES));
       CUDA_TRY(cudaFuncSetAttribute(kern_ds, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::CfgMc<CS>::SMEM_BYTES));
+      CUDA_TRY(cudaFuncSetAttribute(kern_ms, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::CfgMc<CS>::SMEM_BYTES));
       attr = true;
     }
     cudaLaunchConfig_t cfg;
@@ -560,7 +568,8 @@ static int forward_impl(crnn_model* m, const float* data, const float* host_data
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    if (m->lstm_mc == 2) CUDA_TRY(cudaLaunchKernelEx(&cfg, kern_ds, m->tB_h128, lp));
+    if (m->lstm_mc == 3) CUDA_TRY(cudaLaunchKernelEx(&cfg, kern_ms, m->tB_h128, lp));
+    else if (m->lstm_mc == 2) CUDA_TRY(cudaLaunchKernelEx(&cfg, kern_ds, m->tB_h128, lp));
     else if (m->lstm_mc == 1) CUDA_TRY(cudaLaunchKernelEx(&cfg, kern_mc, m->tB_h128, lp));
     else CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, pl.tA_hall, m->tB_h128, lp));
     if (want_trace) {

@@ -90,9 +90,11 @@ struct crnn_model {
   double* grad_sumsq = nullptr;
   CUtensorMap tBh_c2, tBh_c31, tBh_c32, tBh_c41, tBh_c42, tBh_c5, tBh_x;   // same weights, box = 128 rows: per-CTA half of a 256-row N tile
   bool use_2cta = true;      // cta_group::2 GEMM pairs for the Nc % 256 == 0 layers (CRNN_GEMM2=0 disables; debug A/B switch)
+  bool conv1_tc = true;      // conv1 + pool1 on the tensor cores (conv1_tc.cuh, split-bf16 operands); CRNN_CONV1=simt -> kernels.cu
   bool conv2_swap = true;    // conv2 with channels on the MMA M side and 256 positions on N (conv_swap.cuh); CRNN_CONV2=pos -> gemm.cuh
-  int lstm_mc = 1;           // recurrence through lstm::lstm_mc_kernel (no per-step cluster barrier): 1 = global slice + multicast bulk copy
-                             // (CRNN_LSTM_IMPL=mc), 2 = slices pushed smem -> peer smem (CRNN_LSTM_IMPL=ds)
+  int lstm_mc = 3;           // recurrence through lstm::lstm_mc_kernel (no per-step cluster barrier): 1 = global slice + multicast bulk copy
+                             // (CRNN_LSTM_IMPL=mc), 2 = slices pushed smem -> peer smem (CRNN_LSTM_IMPL=ds),
+                             // 3 = smem slice -> bulk store -> multicast (default, "ms"); 0 = v1 with a cluster barrier per step (persistent)
   int lstm_upc = 32;         // hidden units per gate tile: 32 = persistent cluster kernel (default), 64 = per-step launches
   Plan plan;
   std::vector<cudaEvent_t> chunk_events;   // crnn_forward_host: one per H2D chunk + one "staging free" event

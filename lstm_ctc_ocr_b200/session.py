@@ -80,7 +80,8 @@ class Session(object):
         self._pinned = _Pinned()
         self.h2d_bytes = 0
         self.d2h_bytes = 0
-        self.h2d_chunks = 4           # image ranges of the overlapped host->device feed (1 = copy, then compute)
+        import os
+        self.h2d_chunks = int(os.environ.get("CRNN_H2D_CHUNKS", "4"))   # image ranges of the overlapped host->device feed (1 = copy, then compute)
 
     def __enter__(self):
         return self

@@ -198,14 +198,16 @@ def test_forward_loss_decode_vs_committed_golden():
         assert np.array_equal(logits[int(tsl[n]):, n].cpu().numpy(), np.broadcast_to(b, (T - int(tsl[n]), 64)))
 
 
-@pytest.mark.parametrize("conv2", ["swap", "pos"])
+@pytest.mark.parametrize("front", ["tc+swap", "simt+pos"])
 @pytest.mark.parametrize("N,W,widths", [(3, 100, None), (5, 24, [24, 20, 9, 24, 16]), (2, 160, [160, 131]), (130, 40, None)])
-def test_forward_layers_vs_oracle(N, W, widths, conv2, monkeypatch):
-    """Every layer against the fp64 oracle; conv2 through both kernels (conv_swap.cuh: channels on the MMA M side, default;
-    gemm.cuh: positions on M, CRNN_CONV2=pos)."""
+def test_forward_layers_vs_oracle(N, W, widths, front, monkeypatch):
+    """Every layer against the fp64 oracle; conv1 and conv2 through both of their kernels: the defaults (conv1_tc.cuh: im2col +
+    split-bf16 tcgen05; conv_swap.cuh: channels on the MMA M side) and the first-generation ones (kernels.cu SIMT conv1,
+    CRNN_CONV1=simt; gemm.cuh positions-on-M conv2, CRNN_CONV2=pos)."""
     from lstm_ctc_ocr_b200 import engine
     from oracle import crnn_oracle as O
-    monkeypatch.setenv("CRNN_CONV2", conv2)
+    monkeypatch.setenv("CRNN_CONV1", "tc" if front == "tc+swap" else "simt")
+    monkeypatch.setenv("CRNN_CONV2", "swap" if front == "tc+swap" else "pos")
     pn = O.randomize_params(O.init_params(3, dtype=np.float32, logits_scale=10.0))
     data, lab, ll, tsl = O.synth_batch(N, W, seed=5, widths=widths, min_len=1, max_len=3)
     m = engine.CrnnModel(device=DEV)
@@ -331,7 +333,7 @@ def test_full_size_c3_properties():
     assert int(out.max()) <= 62 and int(out.min()) >= 0
 
 
-@pytest.mark.parametrize("impl", ["persistent", "mc", "ds"])
+@pytest.mark.parametrize("impl", ["persistent", "mc", "ds", "ms"])
 def test_cluster_lstm_kernels_match_per_step_kernel(impl):
     """csrc/lstm.cuh -- v1 (`persistent`: cluster barrier per step), v2 (`mc`: global slice + multicast bulk copy, `ds`: slices
     pushed smem -> peer smem) -- vs the per-step GEMM+cell launches (CRNN_LSTM_IMPL=step)."""
