@@ -14,7 +14,8 @@
 //   the 2x2 pool is register-local in the epilogue thread and a warp stores 32 consecutive channels (64 B).
 //
 // f32 fidelity on a bf16 pipe: pixels and taps are split x = xh + xl, w = wh + wl (bf16 high part + bf16 remainder) and the 32
-// K columns of a patch hold  [xh (9) | xl (9) | xh (9) | 0 (5)]  against  [wh | wh | wl | 0]:  xh*wh + xl*wh + xh*wl reproduces the
+// K columns of a patch hold  [xh (9) 0 | xl (9) 0 | xh (9) 0 | 0 0]  against  [wh 0 | wh 0 | wl 0 | 0 0]  (10 columns per part, so
+// every bf16x2 word is one F2FP of two neighbouring taps):  xh*wh + xl*wh + xh*wl reproduces the
 // f32 product to ~2^-17 (the dropped xl*wl term), so the layer keeps the numerics of the f32 SIMT kernel it replaces
 // (measured against the fp64 oracle: 2.5e-3 of max |out| either way, all of it the bf16 rounding of the OUTPUT; plain bf16
 // operands would have been 4.3e-3).
@@ -43,7 +44,7 @@ constexpr int OFF_IN = OFF_B + 2 * B_BYTES;
 constexpr int OFF_BAR = OFF_IN + 2 * IN_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
 
-// K column k (0..31) of a patch: part = k / 9 (x: hi, lo, hi | w: hi, hi, lo), tap = k % 9; k >= 27 is zero padding
+// K column k (0..31) of a patch: part = k / 10 (x: hi, lo, hi | w: hi, hi, lo), tap = k % 10; tap 9 and k >= 30 are zero padding
 __device__ __forceinline__ uint32_t bf16_bits(float v) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)); }
 __device__ __forceinline__ float bf16_back(uint32_t b) { return __uint_as_float(b << 16); }
 
@@ -60,7 +61,8 @@ template <bool TRAIN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv1_tc_kernel(const Params p) {
   constexpr uint32_t IDESC = ptx::make_idesc_bf16(128, 256);
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // aligned by OFFSET (not by casting through an integer): the pointers stay in the shared address space -> LDS/STS, not LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + OFF_B;
   float* s_in = reinterpret_cast<float*>(smem + OFF_IN);
@@ -96,8 +98,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv1_tc_kernel(const Params p
     if ((chunk >> 2) == set) {
       for (int i = 0; i < 8; ++i) {
         const int k = (chunk & 3) * 8 + i;
-        if (k < 27) {
-          const int part = k / 9, tap = k - part * 9;
+        const int part = k / 10, tap = k - part * 10;
+        if (part < 3 && tap < 9) {
           const float wv = __ldg(p.wgt + tap * 64 + ch);
           const uint32_t hi = bf16_bits(wv);
           hw[i] = (part == 2) ? bf16_bits(wv - bf16_back(hi)) : hi;
@@ -185,23 +187,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv1_tc_kernel(const Params p
 #pragma unroll
         for (int set = 0; set < 2; ++set) {
           const float* s0 = stg + (hl + set * 8) * IN_STRIDE + w;   // patch origin: image row h-1, column w-1
-          uint32_t xh[9], xl[9];
+          float x[10];
 #pragma unroll
           for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
-              const float x = s0[r * IN_STRIDE + s];
-              xh[r * 3 + s] = bf16_bits(x);
-              xl[r * 3 + s] = bf16_bits(x - bf16_back(xh[r * 3 + s]));
-            }
-          uint32_t wd[16];                                    // K pairs (2m, 2m+1) of the 32 K columns
+            for (int s = 0; s < 3; ++s) x[r * 3 + s] = s0[r * IN_STRIDE + s];
+          x[9] = 0.f;
+          uint32_t wd[16];                                    // K pairs: [hi x5 | lo x5 | hi x5 | 0]
 #pragma unroll
-          for (int m = 0; m < 16; ++m) {
-            const int k0 = 2 * m, k1 = 2 * m + 1;
-            const uint32_t a = k0 >= 27 ? 0u : (k0 / 9 == 1 ? xl[k0 % 9] : xh[k0 % 9]);
-            const uint32_t b = k1 >= 27 ? 0u : (k1 / 9 == 1 ? xl[k1 % 9] : xh[k1 % 9]);
-            wd[m] = a | (b << 16);
+          for (int m = 0; m < 5; ++m) {
+            const uint32_t h = ptx::pack_bf16x2(x[2 * m], x[2 * m + 1]);                         // one F2FP per two taps
+            wd[m] = h; wd[10 + m] = h;
+            wd[5 + m] = ptx::pack_bf16x2(x[2 * m] - ptx::bf16_lo(h), x[2 * m + 1] - ptx::bf16_hi(h));
           }
+          wd[15] = 0u;
 #pragma unroll
           for (int cq = 0; cq < 4; ++cq)
             *reinterpret_cast<uint4*>(sb + (set * 4 + cq) * 4096 + j * 16) = make_uint4(wd[4 * cq], wd[4 * cq + 1], wd[4 * cq + 2], wd[4 * cq + 3]);
@@ -217,7 +216,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv1_tc_kernel(const Params p
     const int half = (warp_idx - 2) >> 2;                    // columns half*128 ..: image rows half*4 .. half*4+3 of the set
     const int set = q >> 1;
     const int c = (q & 1) * 32 + lane;
-    const float bias = __ldg(p.bias + c);
+    const float bias = __ldg(p.bias + c), nbias = -bias;
     const int Hp = p.W >> 1;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -241,8 +240,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv1_tc_kernel(const Params p
             const float x00 = __uint_as_float(v0[2 * pw]), x01 = __uint_as_float(v0[2 * pw + 1]);
             const float x10 = __uint_as_float(v1[2 * pw]), x11 = __uint_as_float(v1[2 * pw + 1]);
             if (!TRAIN) {
-              const float mx = fmaxf(fmaxf(x00, x01), fmaxf(x10, x11));
-              p.out[off + (size_t)pw * 64] = __float2bfloat16_rn(fmaxf(mx + bias, 0.f));
+              // relu(max4 + b) == max(max4, -b) + b exactly (the same FADD on the same operand, or (-b) + b = 0): two 3-input
+              // maxima and one add instead of three maxima, an add and a max -- the kernel is ALU-issue bound (ncu: 52 %)
+              float m3, m4;
+              asm("max.f32 %0, %1, %2, %3;" : "=f"(m3) : "f"(x00), "f"(x01), "f"(x10));
+              asm("max.f32 %0, %1, %2, %3;" : "=f"(m4) : "f"(m3), "f"(x11), "f"(nbias));
+              const float o = m4 + bias;
+              reinterpret_cast<unsigned short*>(p.out)[off + (size_t)pw * 64] = (unsigned short)ptx::pack_bf16x2(o, o);   // F2FP (ALU), not F2F (XU)
             } else {
               // strict '>' in (dy, dx) row-major order keeps the FIRST maximum (tie-break of TF/torch max-pool gradients),
               // decided on the f32 accumulators like the SIMT kernel
@@ -251,7 +255,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv1_tc_kernel(const Params p
               if (x01 > best) { best = x01; bi = 1; }
               if (x10 > best) { best = x10; bi = 2; }
               if (x11 > best) { best = x11; bi = 3; }
-              p.out[off + (size_t)pw * 64] = __float2bfloat16_rn(fmaxf(best + bias, 0.f));
+              const float o = fmaxf(best + bias, 0.f);
+              reinterpret_cast<unsigned short*>(p.out)[off + (size_t)pw * 64] = (unsigned short)ptx::pack_bf16x2(o, o);
               p.argmax[off + (size_t)pw * 64] = (uint8_t)bi;
             }
           }

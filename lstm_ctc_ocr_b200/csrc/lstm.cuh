@@ -276,8 +276,14 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_con
 //     MMA of step t-1 (the last reader of that buffer) has completed -- causality replaces a "buffer free" handshake
 //   * the accumulator is single buffered for the same reason (MMA t+1 needs this CTA's own h_t, sent after its TMEM reads)
 // Global exchange buffer (DS = false): p.h_state viewed as [2 bufs][2*tiles_per_dir units][8 ranks][8 KB].
-constexpr int MC_THREADS = 320;              // warp 0 setup, warp 1 MMA, warps 2..9 epilogue
-constexpr int MC_EPI_THREADS = 256;
+// EW epilogue warps (8 or 16): EW/4 per TMEM lane quadrant, each owning 32/(EW/4) of the CTA's units.  The cell is a chain of
+// MUFU latencies (ncu: XU pipe 22 %, issue slots 22 % busy), but 16 warps x 8 units measured SLOWER than 8 x 16 on the B200
+// (0.422 vs 0.402 ms: the longer 512-thread barrier and 4 tcgen05.ld per 8 units eat the gain); model.cu instantiates EW = 8.
+template <int EW>
+struct McThreads {
+  static constexpr int EPI = EW * 32;
+  static constexpr int ALL = 64 + EPI;       // warp 0 setup, warp 1 MMA, warps 2.. epilogue
+};
 
 template <int CS>
 struct CfgMc {
@@ -299,19 +305,21 @@ __device__ __forceinline__ void bulk_copy_s2s_cluster(uint32_t dst_cluster_addr,
 
 // MODE: 0 = global slice + multicast ("mc"), 1 = smem -> peer smem pushes ("ds"), 2 = smem slice -> bulk store to global ->
 // multicast to the 7 peers ("ms": no generic-proxy global stores, hence no full fence.proxy.async on the critical path)
-template <int CS, int MODE>
-__global__ void __launch_bounds__(MC_THREADS, 1)
+template <int CS, int MODE, int EW>
+__global__ void __launch_bounds__(McThreads<EW>::ALL, 1)
 lstm_mc_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
   static_assert(CS == 8, "8 CTAs x 32 units");
   using C = CfgMc<CS>;
   constexpr int UPC = C::UPC, NCOLS = C::NCOLS;
   constexpr uint32_t IDESC = ptx::make_idesc_bf16(BLOCK_M, NCOLS);
-  constexpr int HALF = UPC / 2;                             // units per epilogue warp
+  constexpr int HALF = UPC / (EW / 4);                      // units per epilogue warp (16 or 8)
+  constexpr int MC_EPI_THREADS = McThreads<EW>::EPI;
+  static_assert(EW == 8 || EW == 16, "epilogue warps");
   constexpr bool DS = (MODE == 1), MS = (MODE == 2), LOCAL = DS || MS;            // LOCAL: own slice written in place
   constexpr uint32_t FILL_TX = LOCAL ? (CS - 1) * C::SLICE_BYTES : C::A_BYTES;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space (STS)
   uint8_t* smem_a = smem;                                   // [2][A_BYTES]
   uint8_t* smem_b = smem + 2 * C::A_BYTES;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + C::BAR_OFFSET);   // [2] one per A buffer
@@ -378,7 +386,7 @@ lstm_mc_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
   } else if (warp_idx >= 2) {
     // ===================== epilogue: thread = (sample row, 16 of the CTA's 32 units); cell state in registers =====================
     const int q = warp_idx & 3;
-    const int hh = (warp_idx - 2) >> 2;               // which half of the CTA's units
+    const int hh = (warp_idx - 2) >> 2;               // which HALF-unit group of the CTA's units
     const int u0 = hh * HALF;
     const int row = q * 32 + lane;
     const int n = tile * BLOCK_M + row;
@@ -388,8 +396,8 @@ lstm_mc_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
 #pragma unroll
     for (int i = 0; i < HALF; ++i) cst[i] = 0.f;
     const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    // this thread's 2 x 16 B of the h slice: K-chunks hh*2, hh*2+1 at chunk*2048 + row*16 inside the CTA's 8 KB slice
-    const uint32_t slice_off = rank * C::SLICE_BYTES + (hh * 2) * 2048 + row * 16;
+    // this thread's HALF/8 x 16 B of the h slice: K-chunks u0/8 .. at chunk*2048 + row*16 inside the CTA's 8 KB slice
+    const uint32_t slice_off = rank * C::SLICE_BYTES + (u0 / 8) * 2048 + row * 16;
     uint8_t* hx0 = reinterpret_cast<uint8_t*>(p.h_state) + ((size_t)unit * CS + rank) * C::SLICE_BYTES;
     const size_t hx_buf_stride = (size_t)2 * p.tiles_per_dir * CS * C::SLICE_BYTES;
 
@@ -397,14 +405,13 @@ lstm_mc_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
       const bool active = s < len;
       const int t = active ? (dir ? (len - 1 - s) : s) : s;
       // this step's input projection (row n, step s; bw rows were stored reversed by the projection GEMM): 4 gates x 16 units
-      uint4 xp[4][2];
+      uint4 xp[4][HALF / 8];
       if (active) {
         const __nv_bfloat16* src = p.xproj + ((size_t)n * p.H + s) * 2048 + dir * 1024 + rank * NCOLS + u0;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          xp[g][0] = __ldg(reinterpret_cast<const uint4*>(src + g * UPC));
-          xp[g][1] = __ldg(reinterpret_cast<const uint4*>(src + g * UPC) + 1);
-        }
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int v = 0; v < HALF / 8; ++v) xp[g][v] = __ldg(reinterpret_cast<const uint4*>(src + g * UPC) + v);
       }
       if (warp_idx == 2) LSTM_TRACE(5);
       uint32_t gi[HALF], gj[HALF], gf[HALF], go[HALF];
@@ -412,10 +419,17 @@ lstm_mc_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
         ptx::mbar_wait(acc_full, (s - 1) & 1);
         ptx::tc_fence_after();
         if (warp_idx == 2) LSTM_TRACE(6);
-        ptx::tmem_ld_32x32b_x16(tbase + 0 * UPC + u0, gi);
-        ptx::tmem_ld_32x32b_x16(tbase + 1 * UPC + u0, gj);
-        ptx::tmem_ld_32x32b_x16(tbase + 2 * UPC + u0, gf);
-        ptx::tmem_ld_32x32b_x16(tbase + 3 * UPC + u0, go);
+        if constexpr (HALF == 16) {
+          ptx::tmem_ld_32x32b_x16(tbase + 0 * UPC + u0, gi);
+          ptx::tmem_ld_32x32b_x16(tbase + 1 * UPC + u0, gj);
+          ptx::tmem_ld_32x32b_x16(tbase + 2 * UPC + u0, gf);
+          ptx::tmem_ld_32x32b_x16(tbase + 3 * UPC + u0, go);
+        } else {
+          ptx::tmem_ld_32x32b_x8(tbase + 0 * UPC + u0, gi);
+          ptx::tmem_ld_32x32b_x8(tbase + 1 * UPC + u0, gj);
+          ptx::tmem_ld_32x32b_x8(tbase + 2 * UPC + u0, gf);
+          ptx::tmem_ld_32x32b_x8(tbase + 3 * UPC + u0, go);
+        }
         ptx::tmem_ld_wait();
         if (warp_idx == 2) LSTM_TRACE(7);
       } else {
@@ -454,13 +468,15 @@ lstm_mc_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
         const int nb = (s + 1) & 1;
         if (LOCAL) {
           uint8_t* dst = smem_a + nb * C::A_BYTES + slice_off;
-          *reinterpret_cast<uint4*>(dst) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-          *reinterpret_cast<uint4*>(dst + 2048) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+#pragma unroll
+          for (int v = 0; v < HALF / 8; ++v)
+            *reinterpret_cast<uint4*>(dst + v * 2048) = make_uint4(hp[4 * v], hp[4 * v + 1], hp[4 * v + 2], hp[4 * v + 3]);
           ptx::fence_proxy_async_smem();                    // generic-proxy smem writes -> async proxy (bulk copies, tcgen05.mma)
         } else {
-          uint8_t* dst = hx0 + (size_t)nb * hx_buf_stride + (hh * 2) * 2048 + row * 16;
-          *reinterpret_cast<uint4*>(dst) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-          *reinterpret_cast<uint4*>(dst + 2048) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+          uint8_t* dst = hx0 + (size_t)nb * hx_buf_stride + (u0 / 8) * 2048 + row * 16;
+#pragma unroll
+          for (int v = 0; v < HALF / 8; ++v)
+            *reinterpret_cast<uint4*>(dst + v * 2048) = make_uint4(hp[4 * v], hp[4 * v + 1], hp[4 * v + 2], hp[4 * v + 3]);
           fence_proxy_async_all();                          // generic-proxy global writes -> async proxy (bulk copy)
         }
         if (warp_idx == 2) LSTM_TRACE(8);
@@ -496,7 +512,8 @@ lstm_mc_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
       }
       if (okn) {
         __nv_bfloat16* lo = p.lstm_out + ((size_t)n * p.H + t) * 512 + dir * 256 + rank * UPC + u0;
-        ptx::st_global_v8(lo, hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6], hp[7]);
+        if constexpr (HALF == 16) ptx::st_global_v8(lo, hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6], hp[7]);
+        else *reinterpret_cast<uint4*>(lo) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
       }
       if (active && p.gates != nullptr) {
         const size_t srow = ((size_t)dir * p.Nimg + n) * p.T + s;

@@ -547,9 +547,9 @@ static int forward_impl(crnn_model* m, const float* data, const float* host_data
     lp.trace = want_trace ? d_trace : nullptr;
     lp.swap_ls = getenv("CRNN_LSTM_SWAPLS") != nullptr;
     auto kern = lstm::lstm_persistent_kernel<CS>;
-    auto kern_mc = lstm::lstm_mc_kernel<CS, 0>;
-    auto kern_ds = lstm::lstm_mc_kernel<CS, 1>;
-    auto kern_ms = lstm::lstm_mc_kernel<CS, 2>;
+    auto kern_mc = lstm::lstm_mc_kernel<CS, 0, 8>;
+    auto kern_ds = lstm::lstm_mc_kernel<CS, 1, 8>;
+    auto kern_ms = lstm::lstm_mc_kernel<CS, 2, 8>;
     static bool attr = false;
     if (!attr) {
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::Cfg<CS>::SMEM_BYTES));
@@ -561,7 +561,7 @@ static int forward_impl(crnn_model* m, const float* data, const float* host_data
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(CS * 2 * lp.tiles_per_dir);
-    cfg.blockDim = dim3(m->lstm_mc ? lstm::MC_THREADS : lstm::NUM_THREADS);
+    cfg.blockDim = dim3(m->lstm_mc ? lstm::McThreads<8>::ALL : lstm::NUM_THREADS);
     cfg.dynamicSmemBytes = m->lstm_mc ? lstm::CfgMc<CS>::SMEM_BYTES : lstm::Cfg<CS>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
