@@ -33,6 +33,7 @@ extern "C" int crnn_model_set_training(crnn_model* m, int flag) {
     CRNN_TRY(make_tmap_2d(&m->tD_l, m->Bld, 512, 64, 64, 256));
     CRNN_TRY(make_tmap_2d(&m->tD_x, m->Bxb, 512, 2048, 2048, 256));
     CRNN_TRY(make_tmap_2d(&m->tD_h, m->Bhb, 512, 1024, 1024, 32));
+    CRNN_TRY(make_tmap_2d(&m->tD_h256, m->Bhb, 512, 1024, 1024, 256));
     CRNN_TRY(make_tmap_2d(&m->tDh_c42, m->Bd_c42, 512, 4608, 4608, 128));
     CRNN_TRY(make_tmap_2d(&m->tDh_c41, m->Bd_c41, 256, 4608, 4608, 128));
     CRNN_TRY(make_tmap_2d(&m->tDh_c32, m->Bd_c32, 256, 2304, 2304, 128));
@@ -129,19 +130,21 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
     static bool attr = false;
     if (!attr) {
       CUDA_TRY(cudaFuncSetAttribute(lstm_bwd::lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_bwd::SMEM_BYTES));
+      CUDA_TRY(cudaFuncSetAttribute(lstm_bwd::lstm_bwd_ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm_bwd::ks::SMEM_BYTES));
       attr = true;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(lstm_bwd::CS * 2 * lp.tiles_per_dir);
-    cfg.blockDim = dim3(lstm_bwd::NUM_THREADS);
-    cfg.dynamicSmemBytes = lstm_bwd::SMEM_BYTES;
+    cfg.blockDim = dim3(m->bptt_ks ? lstm_bwd::ks::NUM_THREADS : lstm_bwd::NUM_THREADS);
+    cfg.dynamicSmemBytes = m->bptt_ks ? lstm_bwd::ks::SMEM_BYTES : lstm_bwd::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = lstm_bwd::CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, lstm_bwd::lstm_bwd_kernel, pl.tG_dzstate, m->tD_h, lp));
+    if (m->bptt_ks) CUDA_TRY(cudaLaunchKernelEx(&cfg, lstm_bwd::lstm_bwd_ks_kernel, m->tD_h256, lp, pl.bptt_x));
+    else CUDA_TRY(cudaLaunchKernelEx(&cfg, lstm_bwd::lstm_bwd_kernel, pl.tG_dzstate, m->tD_h, lp));
   }
   BMARK();
   {

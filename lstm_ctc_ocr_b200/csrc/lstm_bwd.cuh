@@ -238,4 +238,237 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
   if (warp_idx == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 32); }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// v2 ("ks"): the same recurrence with the product split along K and NOTHING but generic-proxy traffic between CTAs.
+//
+// v1 above moves the whole dz_{s+1} tile (128 x 1024, 256 KB) into every CTA each step (multicast ring with cluster-wide slot
+// hand-shakes), issues 64 tcgen05.mma of N = 32 (an MMA instruction costs >= ~128 cycles whatever its N) and pays two
+// fence.proxy.async and a cluster barrier per step: 26 us per step.  Here CTA `rank` multiplies ONLY ITS OWN dz slice
+// (128 x 128 gate columns, written by its own epilogue straight into shared memory as the no-swizzle A operand) with the
+// resident W_h[all 256 units, its 128 gate columns]: 8 tcgen05.mma of 128 x 256 x 16 give its partial dh for ALL units.  The
+// partials are exchanged all-to-all through L2 as bf16 (8 KB per (source, destination) pair): plain st.global, one
+// release.cluster arrive on every peer's mbarrier, acquire.cluster wait, ld.global.cg of the 8 partial rows, f32 sum --
+// no async proxy, no proxy fences, no cluster barrier on the critical path.
+//   X[buf = s & 1][unit][dst][src][128 rows][32 units] bf16 is the exchange buffer (double buffered: a source can only reach
+//   step s-2 after every peer finished reading step s, because its own step s-1 needs all peers' step s-1 partials).
+namespace ks {
+constexpr int NUM_THREADS = 320;                 // warp 0 setup, warp 1 MMA, warps 2..9 epilogue
+constexpr int EPI_THREADS = 256;
+constexpr int B_BYTES = 2 * 256 * 128;           // 2 K-blocks x [256 unit rows x 128 B] (SW128) = 64 KB
+constexpr int A_BYTES = 16 * BLOCK_M * 16;       // [16 K-chunks][128 rows][16 B] = 32 KB, no swizzle
+constexpr int BAR_OFFSET = B_BYTES + A_BYTES;
+constexpr int SMEM_BYTES = BAR_OFFSET + 128 + 1024;
+constexpr int PAIR_BYTES = BLOCK_M * UPC * 2;    // one (source, destination) block of partial sums: 8 KB
+}  // namespace ks
+
+__global__ void __launch_bounds__(ks::NUM_THREADS, 1)
+lstm_bwd_ks_kernel(const __grid_constant__ CUtensorMap tmW, const Params p, uint8_t* __restrict__ xbuf) {
+  constexpr uint32_t IDESC = ptx::make_idesc_bf16(BLOCK_M, 256);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_b = smem;
+  uint8_t* smem_a = smem + ks::B_BYTES;
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(smem + ks::BAR_OFFSET);
+  uint64_t* acc_full = b_full + 1;
+  uint64_t* a_ready = acc_full + 1;
+  uint64_t* part_ready = a_ready + 1;            // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(part_ready + 2);
+
+  const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)lstm::cluster_ctarank();
+  const int unit = blockIdx.x / CS;
+  const int dir = unit / p.tiles_per_dir;
+  const int tile = unit - dir * p.tiles_per_dir;
+  const int num_units = 2 * p.tiles_per_dir;
+
+  if (warp_idx == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmW);
+    ptx::mbar_init(b_full, 1);
+    ptx::mbar_init(acc_full, 1);
+    ptx::mbar_init(a_ready, ks::EPI_THREADS);
+    ptx::mbar_init(&part_ready[0], CS);
+    ptx::mbar_init(&part_ready[1], CS);
+    ptx::fence_barrier_init();
+    // resident W_h[dir: all 256 units][gate columns rank*128 .. +128)
+    ptx::mbar_arrive_expect_tx(b_full, ks::B_BYTES);
+    for (int kb = 0; kb < 2; ++kb) ptx::tma_load_2d(&tmW, b_full, smem_b + kb * 256 * 128, rank * 128 + kb * 64, dir * 256);
+  }
+  if (warp_idx == 1) { ptx::tmem_alloc(tmem_ptr, 256); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  lstm::cluster_arrive_release();                  // peers arrive on this CTA's part_ready barriers
+  lstm::cluster_wait_acquire();
+
+  if (warp_idx == 1) {
+    // ===================== MMA issuer: partial dh[128 x 256] = dz_{s+1}[128 x own 128 gate columns] * W_h^T =====================
+    if (lane == 0) {
+      ptx::mbar_wait(b_full, 0);
+      for (int s = p.T - 2; s >= 0; --s) {
+        const uint32_t ph = (uint32_t)(p.T - 2 - s) & 1u;
+        ptx::mbar_wait(a_ready, ph);
+        ptx::tc_fence_after();
+        const uint32_t a_base = ptx::smem_u32(smem_a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t a_desc = ptx::make_desc_k_nosw(a_base + k * 4096, 2048, 128);
+          const uint64_t b_desc = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b + (k >> 2) * 256 * 128)) + 2 * (k & 3);
+          ptx::mma_f16_ss(tmem_base, a_desc, b_desc, IDESC, k != 0);
+        }
+        ptx::tc_commit(acc_full);
+      }
+    }
+    __syncwarp();
+  } else if (warp_idx >= 2) {
+    // ===================== epilogue: thread = (sample row, half) =====================
+    const int q = warp_idx & 3;
+    const int hh = (warp_idx - 2) >> 2;            // exchange: destination CTAs hh*4 .. hh*4+3; cell: units hh*16 .. +16 of this CTA
+    const int u0 = hh * 16;
+    const int row = q * 32 + lane;
+    const int n = tile * BLOCK_M + row;
+    const bool okn = n < p.Nimg;
+    const int len = okn ? min(max(__ldg(p.seq_len + n), 0), p.T) : 0;
+    const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + hh * 128;
+    float dcr[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dcr[i] = 0.f;
+    const size_t buf_stride = (size_t)num_units * CS * CS * ks::PAIR_BYTES;
+    uint8_t* x_unit = xbuf + (size_t)unit * CS * CS * ks::PAIR_BYTES;
+
+    for (int s = p.T - 1; s >= 0; --s) {
+      const bool has_rec = (s < p.T - 1);
+      const bool active = s < len;
+      const int t = active ? (dir ? (len - 1 - s) : s) : s;
+      const size_t srow = ((size_t)dir * p.Nimg + n) * p.T + s;
+      // pull the next step's saved state into L2 one step ahead (it was evicted long ago)
+      if (s >= 1 && (s - 1) < len) {
+        const size_t prow = srow - 1;
+        const int tp = dir ? (len - s) : (s - 1);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.gates + prow * 1024 + g * 256 + rank * UPC + u0));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.csave + prow * 256 + rank * UPC + u0));
+        if (s >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.csave + (prow - 1) * 256 + rank * UPC + u0));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.d_out + ((size_t)n * p.H + tp) * 512 + dir * 256 + rank * UPC + u0));
+      }
+
+      float rec[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) rec[i] = 0.f;
+      if (has_rec) {
+        const int b = s & 1;
+        uint8_t* xb = x_unit + (size_t)b * buf_stride;
+        ptx::mbar_wait(acc_full, (uint32_t)(p.T - 2 - s) & 1u);
+        ptx::tc_fence_after();
+        // ---- this CTA's partial sums for destinations hh*4 .. hh*4+3 -> X[dst][src = rank][row]
+#pragma unroll 1
+        for (int jj = 0; jj < 4; ++jj) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(tbase + jj * 32, v);
+          ptx::tmem_ld_wait();
+          uint32_t w[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) w[i] = ptx::pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+          uint8_t* dst = xb + ((size_t)((hh * 4 + jj) * CS + rank) * BLOCK_M + row) * 64;
+          ptx::st_global_v8(dst, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+          ptx::st_global_v8(dst + 32, w[8], w[9], w[10], w[11], w[12], w[13], w[14], w[15]);
+        }
+        ptx::tc_fence_before();
+        asm volatile("bar.sync 1, %0;" ::"n"(ks::EPI_THREADS) : "memory");
+        // one release.cluster arrive per peer (cumulative over the barrier above: covers every thread's stores)
+        if (warp_idx == 2 && lane < CS) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&part_ready[b]), (uint32_t)lane));
+      }
+      // saved forward state of this step: issued before the exchange wait so that its latency hides behind it
+      uint4 qg[4][2], qd[2];
+      float4 qc[4], qp[4];
+      if (active) {
+        const __nv_bfloat16* gs = p.gates + srow * 1024 + rank * UPC + u0;
+        const float* cs = p.csave + srow * 256 + rank * UPC + u0;
+        const __nv_bfloat16* dout = p.d_out + ((size_t)n * p.H + t) * 512 + dir * 256 + rank * UPC + u0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          qg[g][0] = __ldg(reinterpret_cast<const uint4*>(gs + g * 256));
+          qg[g][1] = __ldg(reinterpret_cast<const uint4*>(gs + g * 256) + 1);
+        }
+        qd[0] = __ldg(reinterpret_cast<const uint4*>(dout));
+        qd[1] = __ldg(reinterpret_cast<const uint4*>(dout) + 1);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          qc[v] = __ldg(reinterpret_cast<const float4*>(cs) + v);
+          qp[v] = (s > 0) ? __ldg(reinterpret_cast<const float4*>(cs - 256) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      if (has_rec) {
+        const int b = s & 1;
+        uint8_t* xb = x_unit + (size_t)b * buf_stride;
+        // ---- all 8 partial rows for this thread's 16 units
+        ptx::mbar_wait_cluster(&part_ready[b], (uint32_t)((p.T - 2 - s) >> 1) & 1u);
+        const uint8_t* src = xb + ((size_t)(rank * CS) * BLOCK_M + row) * 64 + hh * 32;
+#pragma unroll
+        for (int r = 0; r < CS; ++r) {
+          const uint4 a = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)r * BLOCK_M * 64));
+          const uint4 c = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)r * BLOCK_M * 64) + 1);
+          float f[16];
+          unpack8(a, f);
+          unpack8(c, f + 8);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) rec[i] += f[i];
+        }
+      }
+
+      float dzi[16], dzj[16], dzf[16], dzo[16];
+      if (active) {
+        float gi[16], gj[16], gf[16], go[16], dh[16];
+        unpack8(qg[0][0], gi); unpack8(qg[0][1], gi + 8);
+        unpack8(qg[1][0], gj); unpack8(qg[1][1], gj + 8);
+        unpack8(qg[2][0], gf); unpack8(qg[2][1], gf + 8);
+        unpack8(qg[3][0], go); unpack8(qg[3][1], go + 8);
+        unpack8(qd[0], dh); unpack8(qd[1], dh + 8);
+        const float* cc = reinterpret_cast<const float*>(qc);
+        const float* cp = reinterpret_cast<const float*>(qp);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float dht = dh[i] + rec[i];
+          const float tc = ptx::fast_tanh(cc[i]);
+          const float dc = dcr[i] + dht * go[i] * (1.f - tc * tc);
+          dzo[i] = dht * tc * go[i] * (1.f - go[i]);
+          dzi[i] = dc * gj[i] * gi[i] * (1.f - gi[i]);
+          dzj[i] = dc * gi[i] * (1.f - gj[i] * gj[i]);
+          dzf[i] = dc * cp[i] * gf[i] * (1.f - gf[i]);
+          dcr[i] = dc * gf[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { dzi[i] = 0.f; dzj[i] = 0.f; dzf[i] = 0.f; dzo[i] = 0.f; }
+      }
+      const uint4 zi0 = pack8(dzi), zi1 = pack8(dzi + 8), zj0 = pack8(dzj), zj1 = pack8(dzj + 8);
+      const uint4 zf0 = pack8(dzf), zf1 = pack8(dzf + 8), zo0 = pack8(dzo), zo1 = pack8(dzo + 8);
+      if (s > 0) {
+        // A operand of the next step's product: K index = gate*32 + unit -> chunks gate*4 + hh*2 + {0, 1}
+        uint8_t* a = smem_a + (size_t)(hh * 2) * 2048 + row * 16;
+        *reinterpret_cast<uint4*>(a + 0 * 8192) = zi0; *reinterpret_cast<uint4*>(a + 0 * 8192 + 2048) = zi1;
+        *reinterpret_cast<uint4*>(a + 1 * 8192) = zj0; *reinterpret_cast<uint4*>(a + 1 * 8192 + 2048) = zj1;
+        *reinterpret_cast<uint4*>(a + 2 * 8192) = zf0; *reinterpret_cast<uint4*>(a + 2 * 8192 + 2048) = zf1;
+        *reinterpret_cast<uint4*>(a + 3 * 8192) = zo0; *reinterpret_cast<uint4*>(a + 3 * 8192 + 2048) = zo1;
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(a_ready);
+      }
+      if (okn) {
+        __nv_bfloat16* za = p.dz_all + ((size_t)n * p.H + t) * 2048 + dir * 1024 + rank * 128 + u0;
+        ptx::st_global_v8(za + 0 * 32, zi0.x, zi0.y, zi0.z, zi0.w, zi1.x, zi1.y, zi1.z, zi1.w);
+        ptx::st_global_v8(za + 1 * 32, zj0.x, zj0.y, zj0.z, zj0.w, zj1.x, zj1.y, zj1.z, zj1.w);
+        ptx::st_global_v8(za + 2 * 32, zf0.x, zf0.y, zf0.z, zf0.w, zf1.x, zf1.y, zf1.z, zf1.w);
+        ptx::st_global_v8(za + 3 * 32, zo0.x, zo0.y, zo0.z, zo0.w, zo1.x, zo1.y, zo1.z, zo1.w);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  lstm::cluster_arrive_release();                  // no CTA leaves while a peer may still arrive on its barriers
+  lstm::cluster_wait_acquire();
+  if (warp_idx == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 256); }
+}
+
 }  // namespace lstm_bwd

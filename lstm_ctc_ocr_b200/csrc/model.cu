@@ -145,6 +145,7 @@ extern "C" int crnn_model_create(const crnn_config* cfg, crnn_model** out) {
   }
   m->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("CRNN_GEMM2")) m->use_2cta = std::string(e) != "0";
+  if (const char* e = getenv("CRNN_BPTT")) m->bptt_ks = std::string(e) != "ring";        // debug A/B switch
   if (const char* e = getenv("CRNN_CONV1")) m->conv1_tc = std::string(e) != "simt";    // debug A/B switch
   if (const char* e = getenv("CRNN_CONV2")) m->conv2_swap = std::string(e) != "pos";    // debug A/B switch: "pos" = position-major gemm.cuh kernel
   if (const char* e = getenv("CRNN_LSTM_IMPL")) {                                                      // debug A/B switch
@@ -286,6 +287,7 @@ size_t layout_plan(Plan& pl, int N, int W, uint8_t* base, bool train) {
     pl.d_lstm_out = (__nv_bfloat16*)take(n * h2 * 512 * 2);
     pl.dz_all = (__nv_bfloat16*)take(n * h2 * 2048 * 2);
     pl.dz_state = (__nv_bfloat16*)take((size_t)2 * 2 * pl.Npad * 1024 * 2);
+    pl.bptt_x = (uint8_t*)take((size_t)2 * (2 * pl.Npad / 128) * 64 * 8192);
     pl.d_a5 = (__nv_bfloat16*)take(n * h2 * 512 * 2);
     pl.d_a4b = (__nv_bfloat16*)take(n * h2 * 2 * 512 * 2);
     pl.d_pre4b = (__nv_bfloat16*)take(n * h2 * 4 * 512 * 2);

@@ -59,6 +59,7 @@ struct Plan {
   float* csave;                                   // [2][N][T][256]
   __nv_bfloat16 *dl_rows, *d_lstm_out, *dz_all, *dz_state, *d_a5, *d_a4b, *d_pre4b, *d_pre4a, *d_a3p, *d_pre32, *d_pre31, *d_a2,
       *d_pre2, *d_a1;
+  uint8_t* bptt_x;                                // lstm_bwd_ks_kernel exchange buffer [2][units][8 dst][8 src][8 KB]
   double* bn_bwd_sums;                            // [2 layers][2][512]
   float* bn_bwd_coef;                             // [3][512] scratch
   // K-major A maps of gradient buffers (data-gradient GEMMs)
@@ -86,6 +87,8 @@ struct crnn_model {
   void* wblock_bwd = nullptr;
   __nv_bfloat16 *Bd_c42 = nullptr, *Bd_c41, *Bd_c32, *Bd_c31, *Bd_c2, *Bd_c5, *Bld, *Bxb, *Bhb;
   CUtensorMap tD_c42, tD_c41, tD_c32, tD_c31, tD_c2, tD_c5, tD_l, tD_x, tD_h;
+  CUtensorMap tD_h256;       // same W_h^T operand, box = 256 unit rows (K-split BPTT)
+  bool bptt_ks = true;       // BPTT through lstm_bwd::lstm_bwd_ks_kernel (K-split, generic-proxy exchange); CRNN_BPTT=ring -> v1
   CUtensorMap tDh_c42, tDh_c41, tDh_c32, tDh_c5, tDh_x;     // box = 128 rows (2-CTA pairs)
   double* grad_sumsq = nullptr;
   CUtensorMap tBh_c2, tBh_c31, tBh_c32, tBh_c41, tBh_c42, tBh_c5, tBh_x;   // same weights, box = 128 rows: per-CTA half of a 256-row N tile
