@@ -304,7 +304,9 @@ __device__ __forceinline__ void bulk_copy_s2s_cluster(uint32_t dst_cluster_addr,
 }
 
 // MODE: 0 = global slice + multicast ("mc"), 1 = smem -> peer smem pushes ("ds"), 2 = smem slice -> bulk store to global ->
-// multicast to the 7 peers ("ms": no generic-proxy global stores, hence no full fence.proxy.async on the critical path)
+// multicast to the 7 peers ("ms": no generic-proxy global stores, hence no full fence.proxy.async on the critical path),
+// 3 = generic proxy only ("gx"): st.global slice -> release.cluster arrive on every peer's mbarrier -> acquire.cluster wait ->
+// the 8 epilogue warps copy the 64 KB h tile L2 -> smem with ld.global.cg / st.shared (the exchange the K-split BPTT uses)
 template <int CS, int MODE, int EW>
 __global__ void __launch_bounds__(McThreads<EW>::ALL, 1)
 lstm_mc_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
@@ -315,7 +317,7 @@ lstm_mc_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
   constexpr int HALF = UPC / (EW / 4);                      // units per epilogue warp (16 or 8)
   constexpr int MC_EPI_THREADS = McThreads<EW>::EPI;
   static_assert(EW == 8 || EW == 16, "epilogue warps");
-  constexpr bool DS = (MODE == 1), MS = (MODE == 2), LOCAL = DS || MS;            // LOCAL: own slice written in place
+  constexpr bool DS = (MODE == 1), MS = (MODE == 2), GX = (MODE == 3), LOCAL = DS || MS;   // LOCAL: own slice written in place
   constexpr uint32_t FILL_TX = LOCAL ? (CS - 1) * C::SLICE_BYTES : C::A_BYTES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -325,7 +327,8 @@ lstm_mc_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + C::BAR_OFFSET);   // [2] one per A buffer
   uint64_t* b_full = a_full + 2;
   uint64_t* acc_full = b_full + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* part_ready = acc_full + 1;                      // [2] GX: the 8 CTAs' slices of one h buffer are in L2
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(part_ready + 2);
 
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
@@ -335,15 +338,17 @@ lstm_mc_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
 
   if (warp_idx == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmW);
+    ptx::mbar_init(&part_ready[0], CS);
+    ptx::mbar_init(&part_ready[1], CS);
     // DS: one arrival arms the byte count (MMA thread), the other says "the local slice is in place" (epilogue)
-    ptx::mbar_init(&a_full[0], LOCAL ? 2 : 1);
-    ptx::mbar_init(&a_full[1], LOCAL ? 2 : 1);
+    ptx::mbar_init(&a_full[0], GX ? MC_EPI_THREADS : LOCAL ? 2 : 1);      // GX: every epilogue thread copied its part of the tile
+    ptx::mbar_init(&a_full[1], GX ? MC_EPI_THREADS : LOCAL ? 2 : 1);
     ptx::mbar_init(b_full, 1);
     ptx::mbar_init(acc_full, 1);
     ptx::fence_barrier_init();
     // first fills: buffer 1 receives h_0 (consumed at step 1), buffer 0 receives h_1 (consumed at step 2)
-    if (p.T > 1) ptx::mbar_arrive_expect_tx(&a_full[1], FILL_TX);
-    if (p.T > 2) ptx::mbar_arrive_expect_tx(&a_full[0], FILL_TX);
+    if (!GX && p.T > 1) ptx::mbar_arrive_expect_tx(&a_full[1], FILL_TX);
+    if (!GX && p.T > 2) ptx::mbar_arrive_expect_tx(&a_full[0], FILL_TX);
     ptx::mbar_arrive_expect_tx(b_full, C::B_BYTES);
     for (int kb = 0; kb < 4; ++kb)
       ptx::tma_load_2d(&tmW, b_full, smem_b + kb * NCOLS * 128, kb * 64, dir * 1024 + rank * NCOLS);
@@ -370,7 +375,7 @@ lstm_mc_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
         LSTM_TRACE(3);
         ptx::tc_fence_after();
         // next fill of this buffer is h_{s+1}, consumed at step s+2; its senders are all behind this wait (see header)
-        if (s + 2 < p.T) ptx::mbar_arrive_expect_tx(&a_full[b], FILL_TX);
+        if (!GX && s + 2 < p.T) ptx::mbar_arrive_expect_tx(&a_full[b], FILL_TX);
         const uint32_t a_base = ptx::smem_u32(smem_a + b * C::A_BYTES);
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
@@ -477,7 +482,7 @@ lstm_mc_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
 #pragma unroll
           for (int v = 0; v < HALF / 8; ++v)
             *reinterpret_cast<uint4*>(dst + v * 2048) = make_uint4(hp[4 * v], hp[4 * v + 1], hp[4 * v + 2], hp[4 * v + 3]);
-          fence_proxy_async_all();                          // generic-proxy global writes -> async proxy (bulk copy)
+          if (!GX) fence_proxy_async_all();                 // generic-proxy global writes -> async proxy (bulk copy)
         }
         if (warp_idx == 2) LSTM_TRACE(8);
         ptx::tc_fence_before();
@@ -503,11 +508,28 @@ lstm_mc_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
               ptx::bulk_load_1d_mc(my_slice, g, C::SLICE_BYTES, &a_full[nb], (uint16_t)(((1u << CS) - 1) & ~(1u << rank)));
               ptx::mbar_arrive(&a_full[nb]);                                  // the local slice is already in place
             }
+          } else if (GX) {
+            // cumulative over the barrier above: the release covers every epilogue thread's slice stores
+            if (lane < CS) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&part_ready[nb]), (uint32_t)lane));
           } else if (lane == 0) {
             ptx::bulk_load_1d_mc(my_slice, hx0 + (size_t)nb * hx_buf_stride, C::SLICE_BYTES, &a_full[nb], (uint16_t)((1u << CS) - 1));
           }
           __syncwarp();
           LSTM_TRACE(9);
+        }
+        if (GX) {
+          // h_t of the whole tile = the cluster's 8 contiguous slices = exactly the A operand image: 64 KB, 16 B per thread per pass
+          ptx::mbar_wait_cluster(&part_ready[nb], (uint32_t)(s >> 1) & 1u);
+          const uint8_t* g = reinterpret_cast<const uint8_t*>(p.h_state) + (size_t)nb * hx_buf_stride + (size_t)unit * CS * C::SLICE_BYTES;
+          uint8_t* d = smem_a + nb * C::A_BYTES;
+          const int et = threadIdx.x - 64;                       // 0 .. MC_EPI_THREADS-1
+          uint4 v[C::A_BYTES / 16 / MC_EPI_THREADS];
+#pragma unroll
+          for (int k = 0; k < C::A_BYTES / 16 / MC_EPI_THREADS; ++k) v[k] = __ldcg(reinterpret_cast<const uint4*>(g) + k * MC_EPI_THREADS + et);
+#pragma unroll
+          for (int k = 0; k < C::A_BYTES / 16 / MC_EPI_THREADS; ++k) *(reinterpret_cast<uint4*>(d) + k * MC_EPI_THREADS + et) = v[k];
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(&a_full[nb]);
         }
       }
       if (okn) {

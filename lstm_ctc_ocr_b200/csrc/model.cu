@@ -150,7 +150,7 @@ extern "C" int crnn_model_create(const crnn_config* cfg, crnn_model** out) {
   if (const char* e = getenv("CRNN_CONV2")) m->conv2_swap = std::string(e) != "pos";    // debug A/B switch: "pos" = position-major gemm.cuh kernel
   if (const char* e = getenv("CRNN_LSTM_IMPL")) {                                                      // debug A/B switch
     m->lstm_upc = (std::string(e) == "step") ? 64 : 32;
-    m->lstm_mc = std::string(e) == "ds" ? 2 : std::string(e) == "mc" ? 1 : (std::string(e) == "persistent" || std::string(e) == "step") ? 0 : 3;
+    m->lstm_mc = std::string(e) == "ds" ? 2 : std::string(e) == "mc" ? 1 : std::string(e) == "gx" ? 4 : (std::string(e) == "persistent" || std::string(e) == "step") ? 0 : 3;
   }
 
   // one allocation for all derived operand copies
@@ -552,12 +552,14 @@ static int forward_impl(crnn_model* m, const float* data, const float* host_data
     auto kern_mc = lstm::lstm_mc_kernel<CS, 0, 8>;
     auto kern_ds = lstm::lstm_mc_kernel<CS, 1, 8>;
     auto kern_ms = lstm::lstm_mc_kernel<CS, 2, 8>;
+    auto kern_gx = lstm::lstm_mc_kernel<CS, 3, 8>;
     static bool attr = false;
     if (!attr) {
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::Cfg<CS>::SMEM_BYTES));
       CUDA_TRY(cudaFuncSetAttribute(kern_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::CfgMc<CS>::SMEM_BYTES));
       CUDA_TRY(cudaFuncSetAttribute(kern_ds, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::CfgMc<CS>::SMEM_BYTES));
       CUDA_TRY(cudaFuncSetAttribute(kern_ms, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::CfgMc<CS>::SMEM_BYTES));
+      CUDA_TRY(cudaFuncSetAttribute(kern_gx, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::CfgMc<CS>::SMEM_BYTES));
       attr = true;
     }
     cudaLaunchConfig_t cfg;
@@ -570,7 +572,8 @@ static int forward_impl(crnn_model* m, const float* data, const float* host_data
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    if (m->lstm_mc == 3) CUDA_TRY(cudaLaunchKernelEx(&cfg, kern_ms, m->tB_h128, lp));
+    if (m->lstm_mc == 4) CUDA_TRY(cudaLaunchKernelEx(&cfg, kern_gx, m->tB_h128, lp));
+    else if (m->lstm_mc == 3) CUDA_TRY(cudaLaunchKernelEx(&cfg, kern_ms, m->tB_h128, lp));
     else if (m->lstm_mc == 2) CUDA_TRY(cudaLaunchKernelEx(&cfg, kern_ds, m->tB_h128, lp));
     else if (m->lstm_mc == 1) CUDA_TRY(cudaLaunchKernelEx(&cfg, kern_mc, m->tB_h128, lp));
     else CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, pl.tA_hall, m->tB_h128, lp));

@@ -333,7 +333,7 @@ def test_full_size_c3_properties():
     assert int(out.max()) <= 62 and int(out.min()) >= 0
 
 
-@pytest.mark.parametrize("impl", ["persistent", "mc", "ds", "ms"])
+@pytest.mark.parametrize("impl", ["persistent", "mc", "ds", "ms", "gx"])
 def test_cluster_lstm_kernels_match_per_step_kernel(impl):
     """csrc/lstm.cuh -- v1 (`persistent`: cluster barrier per step), v2 (`mc`: global slice + multicast bulk copy, `ds`: slices
     pushed smem -> peer smem) -- vs the per-step GEMM+cell launches (CRNN_LSTM_IMPL=step)."""

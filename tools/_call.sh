@@ -1,13 +1,14 @@
 mkdir -p gpurun_out
-echo "== training tests with K-split BPTT"
-CRNN_BPTT=ks timeout 400 python -m pytest tests/test_gpu_training.py -q 2>&1 | tail -5
-for v in ring ks; do
-  echo "== bench train step bptt=$v"
-  CRNN_BPTT=$v timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/bench_bptt_$v.json 2>gpurun_out/bench_bptt_$v.err
-  python - "$v" <<'PY'
+q() { python - "$1" <<'PY'
 import json,sys
-d=json.load(open(f'gpurun_out/bench_bptt_{sys.argv[1]}.json'))
-t=d['train_step']; print(round(d['value']), t['ms_per_step'], round(t['images_per_s']), {k:v for k,v in t['stages_ms'].items() if 'lstm' in k or 'forward' in k})
+d=json.load(open(sys.argv[1]))
+print(round(d['value']), d['ms_per_step'], 'e2e', round(d['e2e']['value']), 'lstm', d['stages']['lstm_recurrence']['ms'])
 PY
+}
+echo "== gx tests"
+timeout 200 python -m pytest tests/test_gpu_parity.py -q -k "cluster_lstm" 2>&1 | tail -3
+CRNN_LSTM_IMPL=gx timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_training.py -q -k "golden or full_size_c3 or (gradients_vs_oracle and ks) or three_training" 2>&1 | tail -3
+for impl in ms gx; do
+  echo "== quick bench lstm=$impl"; CRNN_LSTM_IMPL=$impl timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-train > gpurun_out/bench_q_$impl.json 2>gpurun_out/bench_q_$impl.err; q gpurun_out/bench_q_$impl.json
 done
-tail -2 gpurun_out/bench_bptt_ks.err
+echo "== trace gx"; CRNN_LSTM_IMPL=gx timeout 100 python tools/lstm_trace.py 2>&1 | grep lstm_trace | head -3
