@@ -4,6 +4,14 @@
 // (lib/networks/network.py:104-107): per step  z = x_t W_x + b (precomputed, `xproj`) + h_{t-1} W_h ;
 // i,j,f,o = split(z); c = sigma(f+1) c + sigma(i) tanh(j); h = sigma(o) tanh(c); zero output past sequence_length.
 //
+// Two generations live in this file:
+//   lstm_mc_kernel<CS, MODE, EW>   (further down; the default, MODE 2 = "ms") -- h exchanged as 8 KB slices that land directly in
+//                                  every CTA's no-swizzle A operand, signalled through mbarriers; no cluster barrier per step
+//   lstm_persistent_kernel<CS>     (first, below; CRNN_LSTM_IMPL=persistent) -- h through global memory, a 64 KB TMA fetch per CTA,
+//                                  fence.proxy.async and one barrier.cluster per step; its measured step timeline is the
+//                                  reason the second generation exists (see the comment above lstm_mc_kernel)
+//
+// First generation:
 // Cluster of CS CTAs; CTA `rank` owns UPC = 256/CS hidden units (4*UPC gate columns, ordered [i|j|f|o]):
 //   * its W_h slice [4*UPC x 256] bf16 stays resident in shared memory for all T steps (loaded once by TMA)
 //   * per step: TMA loads h_{t-1} [128 x 256] (written to global/L2 by the whole cluster in the previous step),

@@ -356,6 +356,98 @@ def greedy_decode(logits, input_len, tf_blank=TF_BLANK, strip=0):
     return out
 
 
+class _Beam(object):
+    """One prefix of TF's CTC beam search tree (ctc_beam_entry.h [upstream-memory]): log-probabilities of the prefix ending
+    in blank / in its last label at the previous (`old`) and the current (`new`) frame."""
+    __slots__ = ("parent", "label", "children", "old", "new")
+
+    def __init__(self, parent, label):
+        self.parent, self.label, self.children = parent, label, None
+        self.old = [-np.inf, -np.inf, -np.inf]     # total, blank, label
+        self.new = [-np.inf, -np.inf, -np.inf]
+
+    def active(self):
+        return self.new[0] > -np.inf
+
+    def label_seq(self, merge_repeated):
+        out, c, prev = [], self, -1
+        seq = []
+        while c.parent is not None:
+            seq.append(c.label)
+            c = c.parent
+        for l in reversed(seq):
+            if not merge_repeated or l != prev:
+                out.append(l)
+            prev = l
+        return out
+
+
+def beam_search_decode(logits, input_len, beam_width=100, merge_repeated=True, strip=0):
+    """What the reference actually calls at network.py:656-657 / test.py:30:
+    ``tf.nn.ctc_beam_search_decoder(logits, seq_len, merge_repeated=True)`` (beam_width 100, top_paths 1, blank = C-1)
+    followed by the zero stripping of training.py:32.  [upstream-memory] restatement of TensorFlow 1.0's
+    ``CTCBeamSearchDecoder::Step`` / ``TopPaths`` (core/util/ctc/ctc_beam_search.h): prefix beam search over log-softmax
+    frames with per-prefix (blank, label) probabilities, candidates grown branch by branch in descending order against the
+    running bottom of a beam_width-bounded top-N list, and -- the part that differs from greedy decoding even on peaked
+    outputs -- ``merge_repeated=True`` collapsing consecutive equal labels of the DECODED sequence.  Test infrastructure
+    only: it quantifies the defined deviation of the product's greedy decode; nothing is pinned against TF."""
+    x = np.asarray(logits, dtype=np.float64)
+    T, N, C = x.shape
+    blank = C - 1
+    lse = lambda a, b: (max(a, b) + np.log1p(np.exp(-abs(a - b)))) if max(a, b) > -np.inf else -np.inf
+    out = []
+    for n in range(N):
+        root = _Beam(None, -1)
+        root.new = [0.0, 0.0, -np.inf]
+        leaves = [root]
+        for t in range(int(input_len[n])):
+            row = x[t, n]
+            lp = row - (row.max() + np.log(np.exp(row - row.max()).sum()))
+            branches = sorted(leaves, key=lambda b: -b.new[0])
+            leaves = []
+            for b in branches:
+                b.old = list(b.new)
+            for b in branches:
+                if b.parent is not None:
+                    if b.parent.active():
+                        prev = b.parent.old[1] if b.label == b.parent.label else b.parent.old[0]
+                        b.new[2] = lse(b.new[2], prev)
+                    b.new[2] += lp[b.label]
+                b.new[1] = b.old[0] + lp[blank]
+                b.new[0] = lse(b.new[1], b.new[2])
+                leaves.append(b)
+            bottom = lambda: min(leaves, key=lambda e: e.new[0])
+            for b in branches:
+                def is_candidate(total):
+                    return total > -np.inf and (len(leaves) < beam_width or total > bottom().new[0])
+                if not is_candidate(b.old[0]):
+                    continue
+                if b.children is None:
+                    b.children = [_Beam(b, c) for c in range(C - 1)]
+                base = np.full(C - 1, b.old[0])
+                if 0 <= b.label < C - 1:
+                    base[b.label] = b.old[1]
+                cand = base + lp[:C - 1]
+                thr = -np.inf if len(leaves) < beam_width else bottom().new[0]
+                for c in np.nonzero(cand > thr)[0] if len(leaves) >= beam_width else range(C - 1):
+                    ch = b.children[int(c)]
+                    if ch.active():
+                        continue
+                    ch.new = [cand[c], -np.inf, cand[c]]
+                    if is_candidate(ch.new[0]):
+                        if len(leaves) == beam_width:
+                            bt = bottom()
+                            bt.new = [-np.inf, -np.inf, -np.inf]
+                            leaves.remove(bt)
+                        leaves.append(ch)
+                    else:
+                        ch.old = [-np.inf, -np.inf, -np.inf]
+                        ch.new = [-np.inf, -np.inf, -np.inf]
+        best = max(leaves, key=lambda e: e.new[0])
+        out.append([v for v in best.label_seq(merge_repeated) if v != strip])
+    return out
+
+
 def dense_decoded(seqs, pad=0):
     """sparse_tensor_to_dense(default 0) (network.py:657) -> [N, maxlen] int32."""
     m = max([len(s) for s in seqs] + [0])

@@ -127,6 +127,64 @@ def test_greedy_rule_table():
     x = np.zeros((1, 1, C)); assert O.greedy_decode(x, [1])[0] == []   # tie -> lowest index 0 -> stripped
 
 
+def _peaked_lines(n, T, seed, margin=6.0):
+    """Frames like the 10k-line GPU decode test: peaked at a path with CTC blanks (0), decoder blanks (63) and repeats."""
+    rng = np.random.default_rng(seed)
+    path = rng.choice(64, size=(T, n), p=np.r_[0.25, np.full(62, 0.65 / 62), 0.10])
+    rep = rng.random((T, n)) < 0.3
+    for t in range(1, T):
+        path[t] = np.where(rep[t], path[t - 1], path[t])
+    x = rng.standard_normal((T, n, 64))
+    x[np.arange(T)[:, None], np.arange(n)[None, :], path] += margin
+    return x
+
+
+def test_beam_search_restatement_rule_table_and_defined_deviation():
+    """What the reference calls (beam search, width 100, merge_repeated=True) vs the greedy rule the product implements:
+    identical on peaked frames EXCEPT that the beam decoder also collapses consecutive equal labels of the decoded sequence
+    (a genuine double letter 5,<63>,5 comes out as a single 5) -- the defined deviation recorded in DESIGN.md section 2."""
+    C = 64
+    def onehot(seq):
+        x = np.zeros((len(seq), 1, C))
+        for t, a in enumerate(seq): x[t, 0, a] = 8.0
+        return x
+    beam = lambda seq, **kw: O.beam_search_decode(onehot(seq), [len(seq)], **kw)[0]
+    assert beam([1, 2, 3, 4]) == [1, 2, 3, 4]
+    assert beam([63, 63, 63]) == []
+    assert beam([5, 5, 63, 5, 0, 7], merge_repeated=False) == [5, 5, 7] == O.greedy_decode(onehot([5, 5, 63, 5, 0, 7]), [6])[0]
+    assert beam([5, 5, 63, 5, 0, 7]) == [5, 7]                       # the double 5 is merged away by merge_repeated=True
+    assert beam([3, 63, 3, 63, 4]) == [3, 4]
+    # peaked random lines: beam without the output merge == greedy; with it == greedy followed by the same collapse
+    x = _peaked_lines(12, 19, seed=2)
+    il = [19] * 12
+    g = O.greedy_decode(x, il, strip=-1)                             # keep class 0: it is an ordinary label to TF's decoder
+    b_plain = O.beam_search_decode(x, il, merge_repeated=False, strip=-1)
+    b_merge = O.beam_search_decode(x, il, merge_repeated=True, strip=-1)
+    collapse = lambda s: [v for i, v in enumerate(s) if i == 0 or v != s[i - 1]]
+    assert b_plain == g
+    assert b_merge == [collapse(s) for s in g]
+
+
+def test_split_bf16_products_reproduce_the_f32_conv1():
+    """The arithmetic csrc/conv1_tc.cuh puts on the bf16 tensor pipe -- x = xh + xl, w = wh + wl (bf16 high part + bf16
+    remainder), products xh*wh + xl*wh + xh*wl accumulated in f32 -- emulated on the CPU: it reproduces the f32 conv1 to ~2^-16
+    of max |out|, while plain bf16 operands are ~50x worse (which is why the kernel splits)."""
+    import torch.nn.functional as F
+    pn = O.randomize_params(O.init_params(3, dtype=np.float32))
+    data, _, _, _ = O.synth_batch(3, 100, seed=5)
+    x = torch.tensor(data, dtype=torch.float64)[:, None]
+    w = torch.tensor(pn["conv1/weights"], dtype=torch.float64).permute(3, 2, 0, 1)
+    bf = lambda t: t.float().bfloat16().double()
+    ref = F.conv2d(x, w, None, padding=1)
+    xh, wh = bf(x), bf(w)
+    xl, wl = bf(x - xh), bf(w - wh)
+    split = F.conv2d(xh, wh, None, padding=1) + F.conv2d(xl, wh, None, padding=1) + F.conv2d(xh, wl, None, padding=1)
+    plain = F.conv2d(xh, wh, None, padding=1)
+    rel = lambda a: float((a - ref).abs().max() / ref.abs().max())
+    assert rel(split) < 3e-5
+    assert rel(plain) > 20 * rel(split)
+
+
 def test_accuracy_calculation():
     assert O.accuracy_calculation([[1, 2, 0], [3]], [[1, 2], [3, 0, 0]]) == 1.0
     assert O.accuracy_calculation([[1, 2], [3]], [[1, 2], [4]]) == 0.5
