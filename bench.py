@@ -349,6 +349,19 @@ def main():
             r = cpu_reference(sn, W, steps=8, warmup=2)
             line["cpu_baseline"] = {"value": round(r["value"], 2), "unit": "images/s", "cores": r["cores"], "kind": "port",
                                     "sample": f"{sn} lines of 32x{W} per step (same shapes, fp32 torch-CPU restatement), median of 8"}
+            # BASELINE metric, second half ("CTC-loss delta vs ref"): the same sample (same seeds, same initialisers) through the GPU path
+            try:
+                sd, slab, sll, stsl = synthetic.synth_batch(sn, W, seed=3)
+                t_ = lambda a: torch.tensor(a, device=dev)
+                lg = model.forward(t_(sd), t_(stsl))
+                cs, _ = engine.ctc_loss(lg, t_(slab), t_(sll), t_(stsl), max_label_len=int(sll.max()))
+                gpu_loss = float(model.total_loss(cs).item())
+                cpu_loss = float(r["loss"])
+                line["ctc_loss_delta"] = {"gpu": round(gpu_loss, 5), "cpu_port_fp32": round(cpu_loss, 5),
+                                          "rel": round(abs(gpu_loss - cpu_loss) / abs(cpu_loss), 6),
+                                          "sample": f"{sn} lines of 32x{W}, seed 3, reference initialisers (mean CTC NLL + L2 term)"}
+            except Exception as e:      # never lose the bench line over the side statistic
+                line["ctc_loss_delta"] = {"error": repr(e)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
