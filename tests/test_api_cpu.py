@@ -165,3 +165,31 @@ def test_eval_line_preparation_and_cli_flags():
     assert a.network_name == "LSTM_train" and a.restore == 0 and a.set_cfgs == ["TRAIN.BATCH_SIZE", "32"] and a.max_iters == 1000000
     b = test_net.parse_args(["--network=LSTM_test", "--testDir", "x"])
     assert b.test_dir == "x" and b.restore == 1
+
+
+def test_data_layer_batch_contract():
+    """lib/lstm/utils/gen.py: groupBatch restates gen.py:41-67 -- resize to height 32 keeping aspect (nw = int(32/h*w)),
+    time_step = nw//4 - 1, right-pad with 0.0 to a multiple of 4, /255, transpose to [W, 32]; get_batch yields the 4-tuple."""
+    from lstm_ctc_ocr_b200.lib.lstm.utils import gen
+    from lstm_ctc_ocr_b200.lib.lstm.config import cfg
+    rng = np.random.default_rng(0)
+    imgs = [rng.integers(1, 256, size=(60, 160), dtype=np.uint8), rng.integers(1, 256, size=(60, 100), dtype=np.uint8),
+            rng.integers(1, 256, size=(32, 57), dtype=np.uint8)]
+    batch, lab, ll, ts = gen.groupBatch(imgs, ["ab1", "Zz", "0"])
+    nws = [int(32 / 60 * 160), int(32 / 60 * 100), 57]                       # 85, 53, 57
+    W = int(np.ceil(max(nws) / 4) * 4)                                        # 88 (the stock captcha case, SURVEY section 2 #7)
+    assert W == 88 and all(b.shape == (W, cfg.NUM_FEATURES) and b.dtype == np.float32 for b in batch)
+    assert ts == [nw // 4 - 1 for nw in nws] == [20, 12, 13]
+    assert ll == [3, 2, 1] and lab == [gen.encode_maps[c] for c in "ab1Zz0"] and min(lab) >= 1 and max(lab) <= 62
+    for b, nw in zip(batch, nws):
+        assert float(b.max()) <= 1.0 and float(b.min()) >= 0.0
+        assert not b[nw:].any() and b[:nw].any()                              # exact zeros right of the resized image
+    # the unresized third image: [W,32] is the transpose of the [32,W] pixel grid / 255
+    assert np.allclose(batch[2][:57], imgs[2].astype(np.float32).T / 255.0)
+    # generator contract (render or contract-identical fallback): N arrays [W,32], flat labels, lengths, time steps <= W/4-1
+    for render in (False, True):
+        img_list, flat, lens, steps = next(gen.get_batch(num_workers=2, batch_size=5, render=render))
+        assert len(img_list) == 5 and len(lens) == 5 and len(steps) == 5 and len(flat) == sum(lens)
+        Wb = img_list[0].shape[0]
+        assert Wb % 4 == 0 and all(a.shape == (Wb, 32) for a in img_list) and max(steps) <= Wb // 4 - 1
+        assert all(cfg.MIN_LEN <= l <= cfg.MAX_LEN for l in lens) and 1 <= min(flat) and max(flat) <= 62
