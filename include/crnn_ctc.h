@@ -48,6 +48,10 @@ const char* crnn_last_error(void);           /* host string, valid until the nex
  *   costs       [N] f32
  * max_label_len is a host-side upper bound on label_len[] (chooses the states-per-lane
  * variant; labels longer than it make that sample's cost NaN).  C must be 64.
+ * Validation: a sample whose labels contain an id outside [0,C) or equal to `blank`, or whose label_len is
+ * negative or above max_label_len, gets cost NaN and an all-zero gradient -- the kernels never index with such an id.
+ * input_len is clamped to [0,T].  flat_labels MUST hold sum(label_len) entries (its length is not passed and cannot be
+ * checked on the device; the Python wrappers check it).
  * ---------------------------------------------------------------------------------------- */
 int crnn_ctc_workspace_size(int T, int N, int C, int max_label_len, size_t* bytes);
 int crnn_ctc_loss(const float* logits, float* grad, const int* flat_labels, const int* label_len,
@@ -61,6 +65,20 @@ int crnn_ctc_loss(const float* logits, float* grad, const int* flat_labels, cons
  * previous raw argmax; drop `strip`.  out [N,T] i32 zero padded, out_len [N] i32. */
 int crnn_ctc_greedy(const float* logits, const int* input_len, int T, int N, int C, int tf_blank,
                     int strip, int* out, int* out_len, crnn_stream_t stream);
+
+/* Beam-search decode on the HOST.  Replaces tf.nn.ctc_beam_search_decoder(logits, seq_len, merge_repeated=True)
+ * (beam_width 100, top_paths 1, blank = C-1) + sparse_tensor_to_dense(default 0) at lib/networks/network.py:656-657 and
+ * lib/lstm/test.py:30-31.  The reference's op is a CPU-only TensorFlow kernel used at validation / evaluation time; so is
+ * this one: ALL pointers are HOST pointers (copy the logits back once), utterances are spread over `num_threads` host
+ * threads (0 = hardware concurrency).  logits [T,N,C] f32 unnormalised; out [N,T] i32 zero padded (labels equal to `strip`
+ * dropped, lib/lstm/utils/training.py:32); out_len [N]; neg_log_prob [N] or NULL (-log P of the best prefix). */
+int crnn_ctc_beam_search(const float* logits_host, const int* input_len_host, int T, int N, int C, int beam_width,
+                         int merge_repeated, int strip, int* out_host, int* out_len_host, float* neg_log_prob_host,
+                         int num_threads);
+
+/* 1 when `host_ptr` lies in page-locked (cudaHostAlloc / cudaHostRegister) memory, else 0.  The Python feed path uses it to
+ * decide whether a fed numpy batch can be DMA'd in place (crnn_forward_host) or has to be staged. */
+int crnn_host_is_pinned(const void* host_ptr);
 
 /* ------------------------------------------------------------------------------------------
  * Model boundary.  Replaces the graph built by lib/networks/LSTM_train.py:22-38 through

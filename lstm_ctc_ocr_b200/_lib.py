@@ -24,6 +24,8 @@ SIGNATURES = {
     "crnn_ctc_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                               c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     "crnn_ctc_greedy": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "crnn_ctc_beam_search": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int]),
+    "crnn_host_is_pinned": (c_int, [c_void_p]),
     "crnn_model_create": (c_int, [ctypes.POINTER(CrnnConfig), ctypes.POINTER(c_void_p)]),
     "crnn_model_destroy": (c_int, [c_void_p]),
     "crnn_num_tensors": (c_int, [c_void_p]),

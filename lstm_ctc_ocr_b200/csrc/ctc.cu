@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(CTC_THREADS, 8) ctc_loss_kernel(const float* _
   __shared__ int s_off;
   __shared__ int s_ext[SP];
   __shared__ int s_repeats;
+  __shared__ int s_bad;
 
   const int n = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -94,23 +95,27 @@ __global__ void __launch_bounds__(CTC_THREADS, 8) ctc_loss_kernel(const float* _
     if (lane == 0) s_off = acc;
   }
   __syncthreads();
-  const bool too_long = (S > SP) || (L < 0);
+  bool too_long = (S > SP) || (L < 0);
+  if (threadIdx.x == 0) { s_repeats = 0; s_bad = 0; }
+  __syncthreads();
   if (!too_long) {
-    int rep = 0;
+    int rep = 0, bad = 0;
     for (int s = threadIdx.x; s < SP; s += CTC_THREADS) {
       int v = blank;
       if (s < S && (s & 1)) {
         v = flat_labels[s_off + (s >> 1)];
+        // a label id outside [0,C) or equal to the blank would index the 64-class rows out of bounds / alias the blank
+        // states: the sample is rejected (cost NaN, zero gradient) and the id is never used as an index
+        if (v < 0 || v >= CTC_C || v == blank) { bad = 1; v = blank; }
         if (s >= 3 && v == flat_labels[s_off + (s >> 1) - 1]) rep++;
       }
       s_ext[s] = v;
     }
-    // count repeats (tiny): block reduce through smem atomics
-    if (threadIdx.x == 0) s_repeats = 0;
-    __syncthreads();
     if (rep) atomicAdd(&s_repeats, rep);
+    if (bad) atomicOr(&s_bad, 1);
   }
   __syncthreads();
+  too_long = too_long || (s_bad != 0);
 
   const bool feasible = !too_long && Tn > 0 && (L + s_repeats <= Tn);
   if (!feasible) {
@@ -344,7 +349,7 @@ ctc_fast_kernel(const float* __restrict__ logits, float* __restrict__ grad, cons
   float* s_k = s_eb + T;                           // [T]      grad_scale / sum_c 2^(x-m)
   __shared__ uint64_t s_bar;
   __shared__ int s_ext[32];
-  __shared__ int s_off, s_repeats;
+  __shared__ int s_off, s_repeats, s_bad;
 
   const int n = blockIdx.x, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -356,6 +361,7 @@ ctc_fast_kernel(const float* __restrict__ logits, float* __restrict__ grad, cons
     ptx::mbar_init(&s_bar, FAST_THREADS);
     ptx::fence_barrier_init();
     s_repeats = 0;
+    s_bad = 0;
   }
   __syncthreads();
   {   // every thread fetches its own frames; rows past input_len are never read
@@ -373,18 +379,22 @@ ctc_fast_kernel(const float* __restrict__ logits, float* __restrict__ grad, cons
     if (lane == 0) s_off = acc;
   }
   __syncthreads();
-  const bool too_long = (L < 0) || (L > max_label_len) || (S > 32);
+  bool too_long = (L < 0) || (L > max_label_len) || (S > 32);
   if (!too_long && tid < 32) {
-    int v = blank, rep = 0;
+    int v = blank, rep = 0, bad = 0;
     if (tid < S && (tid & 1)) {
       v = flat_labels[s_off + (tid >> 1)];
+      // ids outside [0,C) or equal to the blank are never used as row indices: the sample is rejected (cost NaN, zero gradient)
+      if (v < 0 || v >= CTC_C || v == blank) { bad = 1; v = blank; }
       if (tid >= 3 && v == flat_labels[s_off + (tid >> 1) - 1]) rep = 1;
     }
     s_ext[tid] = v;
     rep = __popc(__ballot_sync(0xffffffffu, rep));
-    if (tid == 0) s_repeats = rep;
+    bad = __any_sync(0xffffffffu, bad);
+    if (tid == 0) { s_repeats = rep; s_bad = bad; }
   }
   __syncthreads();
+  too_long = too_long || (s_bad != 0);
   ptx::mbar_wait(&s_bar, 0);                        // also required before an early exit: the copies target this CTA's smem
 
   const bool feasible = !too_long && Tn > 0 && (L + s_repeats <= Tn);

@@ -37,6 +37,13 @@ extern "C" const char* crnn_status_string(int s) {
   return "CRNN_UNKNOWN";
 }
 
+extern "C" int crnn_host_is_pinned(const void* host_ptr) {
+  if (!host_ptr) return 0;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host_ptr) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return a.type == cudaMemoryTypeHost ? 1 : 0;
+}
+
 // ------------------------------------------------------------------------------------------------ TMA maps
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

@@ -138,7 +138,7 @@ class CrnnModel:
                                     nbytes, _stream()))
         return out
 
-    def forward_host(self, host_data, time_step_len, chunks=4, out=None):
+    def forward_host(self, host_data, time_step_len, chunks=4, out=None, wait_copy=True):
         """host_data: C-contiguous f32 numpy array [N,W,32] in PAGE-LOCKED memory.  The H2D copy is cut into `chunks` image
         ranges on a side stream and overlapped with the conv front end (crnn_forward_host).  Returns (logits, device data)."""
         N, W, Hh = host_data.shape
@@ -155,6 +155,10 @@ class CrnnModel:
         ws, nbytes = self._workspace(N, W)
         check(self.lib.crnn_forward_host(self.handle, host_data.ctypes.data, self._stage.data_ptr(), time_step_len.data_ptr(), N, W,
                                          out.data_ptr(), ws, nbytes, int(chunks), _stream(), self._copy_stream.cuda_stream))
+        if wait_copy:
+            # the caller may rewrite `host_data` as soon as this returns (a feeder recycling its ring slot): wait for the DMA --
+            # not for the compute, which keeps running on the main stream
+            self._copy_stream.synchronize()
         return out, self._stage
 
     def tap(self, name, N, W):
@@ -177,11 +181,19 @@ class CrnnModel:
 
 
 def ctc_loss(logits, flat_labels, label_len, input_len, blank=0, want_grad=False, grad_scale=1.0, max_label_len=None,
-             costs=None, grad=None):
+             costs=None, grad=None, validate=False):
     """logits [T,N,64] f32 cuda; integer tensors i32 cuda.  Returns (costs [N], grad [T,N,64] | None)."""
     lib = _lib.load()
     assert logits.is_cuda and logits.dtype == torch.float32 and logits.is_contiguous()
     T, N, C = logits.shape
+    if label_len.numel() != N or input_len.numel() != N:
+        raise CrnnError("ctc_loss: label_len and input_len must hold one entry per utterance")
+    if validate:         # host-synchronising checks (the kernel itself rejects bad ids per sample: cost NaN, zero gradient)
+        ll = label_len.cpu()
+        if int(ll.min()) < 0 or int(ll.sum()) != flat_labels.numel():
+            raise CrnnError("ctc_loss: label_len must be non-negative and sum to len(flat_labels)")
+        if flat_labels.numel() and (int(flat_labels.min()) < 0 or int(flat_labels.max()) >= C or bool((flat_labels == blank).any())):
+            raise CrnnError(f"ctc_loss: label ids must lie in [0, {C}) and differ from the blank ({blank})")
     if max_label_len is None:
         max_label_len = int(label_len.max().item()) if label_len.numel() else 0      # host sync; pass it to avoid
     if costs is None:
@@ -203,6 +215,22 @@ def ctc_greedy(logits, input_len, tf_blank=TF_BLANK, strip=0):
     check(lib.crnn_ctc_greedy(logits.data_ptr(), input_len.data_ptr(), T, N, C, tf_blank, strip, out.data_ptr(),
                               out_len.data_ptr(), _stream()))
     return out, out_len
+
+
+def ctc_beam_search(logits, input_len, beam_width=100, merge_repeated=True, strip=0, num_threads=0):
+    """The reference's decoder (network.py:656: ctc_beam_search_decoder, width 100, blank C-1, merge_repeated) on the HOST, as
+    the TF op is.  logits: [T,N,C] f32 (cuda tensor -> copied back once, or numpy); returns (out [N,T] i32, out_len [N] i32,
+    neg_log_prob [N] f32) as numpy arrays."""
+    lib = _lib.load()
+    x = logits.detach().float().cpu().numpy() if torch.is_tensor(logits) else np.asarray(logits, dtype=np.float32)
+    x = np.ascontiguousarray(x)
+    il = input_len.detach().cpu().numpy() if torch.is_tensor(input_len) else np.asarray(input_len)
+    il = np.ascontiguousarray(il, dtype=np.int32)
+    T, N, C = x.shape
+    out = np.zeros((N, T), np.int32); out_len = np.zeros(N, np.int32); nlp = np.zeros(N, np.float32)
+    check(lib.crnn_ctc_beam_search(x.ctypes.data, il.ctypes.data, T, N, C, int(beam_width), 1 if merge_repeated else 0, int(strip),
+                                   out.ctypes.data, out_len.ctypes.data, nlp.ctypes.data, int(num_threads)))
+    return out, out_len, nlp
 
 
 def dense_decoded(out, out_len):

@@ -33,6 +33,9 @@ _DEFAULTS = {
     "BLANK_TOKEN": 0, "SPACE_INDEX": 0, "SPACE_TOKEN": "",
     "CHARSET": _CHARSET, "NCLASSES": len(_CHARSET) + 2,        # + CTC blank (0) + decoder blank (63)
     "FONT": "fonts/Ubuntu-M.ttf",
+    # not in the reference: which decoder `dense_decoded` runs -- "greedy" (GPU kernel, the hot path) or "beam" (the reference's
+    # ctc_beam_search_decoder semantics, host side, network.py:656)
+    "DECODER": "greedy", "BEAM_WIDTH": 100,
     "NET_NAME": "lstm", "EXP_DIR": "default", "LOG_DIR": "default", "RNG_SEED": 3,
     "TRAIN": {
         "SOLVER": "Adam", "TXT": "annotation_train.txt",

@@ -110,7 +110,9 @@ class SolverWrapper(object):
         """feed_dict for one data-layer tuple (train.py:119-127)."""
         imgs, flat_labels, label_len, time_steps = batch
         net = self.net
-        return {net.data: np.array(imgs), net.labels: np.array(flat_labels), net.time_step_len: np.array(time_steps),
+        # a PrefetchFeeder hands out an ndarray view of a page-locked ring slot: keep it (np.array would copy it to pageable memory)
+        data = imgs if isinstance(imgs, np.ndarray) and imgs.ndim == 3 else np.array(imgs)
+        return {net.data: data, net.labels: np.array(flat_labels), net.time_step_len: np.array(time_steps),
                 net.labels_len: np.array(label_len), net.keep_prob: keep_prob}
 
     def _prepare(self, sess, restore, lr, global_step):

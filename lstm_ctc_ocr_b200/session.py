@@ -24,8 +24,12 @@ class _Pinned(object):
 
     def __init__(self):
         self.bufs = {}
+        self.events = {}              # staging buffer name -> event recorded after its last H2D copy
+        self.pending = []             # events of copies that read the CALLER's memory in place
         self.registered = {}          # (ptr, nbytes) -> array (keeps the memory alive), insertion-ordered
         self.seen_once = {}           # (ptr, nbytes) -> True, bounded
+        from . import _lib
+        self._is_pinned = _lib.load().crnn_host_is_pinned
 
     def _registered(self, arr):
         key = (arr.ctypes.data, arr.nbytes)
@@ -48,8 +52,14 @@ class _Pinned(object):
         return True
 
     def is_page_locked(self, arr):
-        """True when `arr` has already been registered with the driver by stage() (pure lookup, no side effects)."""
-        return (arr.ctypes.data, arr.nbytes) in self.registered
+        """True when `arr` lives in page-locked memory: registered in place by stage(), or allocated pinned by the caller
+        (e.g. a PrefetchFeeder ring slot) -- asked of the driver through crnn_host_is_pinned."""
+        return (arr.ctypes.data, arr.nbytes) in self.registered or bool(self._is_pinned(arr.ctypes.data))
+
+    def wait_pending(self):
+        for ev in self.pending:
+            ev.synchronize()
+        self.pending = []
 
     def close(self):
         rt = torch.cuda.cudart()
@@ -61,14 +71,26 @@ class _Pinned(object):
         arr = np.ascontiguousarray(arr)
         tdt = _NP2T[arr.dtype]
         if arr.nbytes >= self.REGISTER_MIN_BYTES and arr.flags.owndata and self._registered(arr):
-            return torch.from_numpy(arr).to(device, non_blocking=True)
+            d = torch.from_numpy(arr).to(device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self.pending.append(ev)   # DMA straight out of the caller's array: run() waits for it before returning
+            return d
         t = self.bufs.get(name)
         if t is None or t.numel() < arr.size or t.dtype != tdt:
             t = torch.empty(max(arr.size, 1), dtype=tdt).pin_memory()
             self.bufs[name] = t
+            self.events.pop(name, None)
+        ev = self.events.get(name)
+        if ev is not None:
+            ev.synchronize()          # the previous run's DMA out of this staging buffer must be done before it is rewritten
         v = t[:arr.size].view(arr.shape)
         v.copy_(torch.from_numpy(arr))
-        return v.to(device, non_blocking=True)
+        d = v.to(device, non_blocking=True)
+        if ev is None:
+            ev = self.events[name] = torch.cuda.Event()
+        ev.record()
+        return d
 
 
 class Session(object):
@@ -198,8 +220,15 @@ class Session(object):
             elif k == "logits":
                 v = logits.cpu().numpy()
             elif k == "dense_decoded":
-                o, ol = engine.ctc_greedy(logits, d_tsl)
-                v = engine.dense_decoded(o, ol).cpu().numpy()
+                from .lib.lstm.config import cfg
+                if str(cfg.get("DECODER", "greedy")) == "beam":
+                    # the reference's own decoder (network.py:656): host-side prefix beam search, width 100, blank 63
+                    o, ol, _ = engine.ctc_beam_search(logits, tsl, beam_width=int(cfg.get("BEAM_WIDTH", 100)), merge_repeated=True)
+                    m_ = int(ol.max()) if ol.size else 0
+                    v = np.ascontiguousarray(o[:, :m_])
+                else:
+                    o, ol = engine.ctc_greedy(logits, d_tsl)
+                    v = engine.dense_decoded(o, ol).cpu().numpy()
             elif k == "train_op":
                 v = f.step_fn(eng, logits, grad, d_data, d_tsl)
             elif k.startswith("layer:"):
@@ -213,4 +242,5 @@ class Session(object):
             elif isinstance(v, (np.floating, float)):
                 self.d2h_bytes += 4
             out.append(v)
+        self._pinned.wait_pending()
         return out[0] if single else out

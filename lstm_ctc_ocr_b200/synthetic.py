@@ -29,6 +29,16 @@ def synth_batch(N, W, seed=3, widths=None, min_len=4, max_len=6):
     return data, labels, label_len, time_step_len
 
 
+def synth_bucket_batch(N, W, seed=3, buckets=(80, 160, 256), min_len=4, max_len=6):
+    """One width-bucketed batch (BASELINE configs[3]): true widths uniform in (previous bucket, W], at least one
+    sample of width exactly W, everything else as ``synth_batch``."""
+    lo = max([b for b in buckets if b < W] or [0])
+    rng = np.random.Generator(np.random.PCG64(seed + 7919))
+    widths = rng.integers(max(lo + 1, 8), W + 1, size=N)
+    widths[rng.integers(0, N)] = W
+    return synth_batch(N, W, seed=seed, widths=widths, min_len=min_len, max_len=max_len)
+
+
 def init_params(seed=3, logits_scale=1.0):
     rng = np.random.Generator(np.random.PCG64(seed))
     p = OrderedDict()

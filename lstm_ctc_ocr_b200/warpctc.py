@@ -41,6 +41,17 @@ def ctc(activations, flat_labels, label_lengths, input_lengths, blank_label=0):
     dev = activations.device
     ll_host = label_lengths.cpu().numpy() if torch.is_tensor(label_lengths) else np.asarray(label_lengths)
     mll = int(ll_host.max()) if ll_host.size else 0
+    # host-side checks the kernel cannot make (it is not told the length of flat_labels): warp-ctc reads sum(label_lengths) ids
+    T, N, C = activations.shape
+    n_lab = int(flat_labels.numel()) if torch.is_tensor(flat_labels) else int(np.asarray(flat_labels).size)
+    if ll_host.shape != (N,) or (ll_host.size and int(ll_host.min()) < 0):
+        raise ValueError("ctc: label_lengths must be [N], non-negative")
+    if int(ll_host.sum()) != n_lab:
+        raise ValueError(f"ctc: sum(label_lengths) = {int(ll_host.sum())} but flat_labels holds {n_lab} ids")
+    if not torch.is_tensor(flat_labels) and n_lab:
+        fl_host = np.asarray(flat_labels)
+        if int(fl_host.min()) < 0 or int(fl_host.max()) >= C or bool((fl_host == int(blank_label)).any()):
+            raise ValueError(f"ctc: label ids must lie in [0, {C}) and differ from the blank ({int(blank_label)})")
     fl, ll, il = _dev_i32(flat_labels, dev), _dev_i32(label_lengths, dev), _dev_i32(input_lengths, dev)
     if activations.requires_grad:
         costs = _CTC.apply(activations, fl, ll, il, int(blank_label), mll)

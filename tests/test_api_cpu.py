@@ -193,3 +193,141 @@ def test_data_layer_batch_contract():
         Wb = img_list[0].shape[0]
         assert Wb % 4 == 0 and all(a.shape == (Wb, 32) for a in img_list) and max(steps) <= Wb // 4 - 1
         assert all(cfg.MIN_LEN <= l <= cfg.MAX_LEN for l in lens) and 1 <= min(flat) and max(flat) <= 62
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# beam-search decoder (host side of the C ABI: runs without a GPU) vs the oracle's restatement of TF's CTCBeamSearchDecoder
+# ---------------------------------------------------------------------------------------------------------------------------
+def _beam(x, il, **kw):
+    from lstm_ctc_ocr_b200 import engine
+    out, out_len, nlp = engine.ctc_beam_search(x, il, **kw)
+    return [out[i, :out_len[i]].tolist() for i in range(len(il))], nlp
+
+
+def test_beam_search_rule_table():
+    """Same rule table as tests/test_oracle.py::test_beam_search_restatement_rule_table_and_defined_deviation (network.py:656)."""
+    def onehot(seq):
+        x = np.zeros((len(seq), 1, 64), np.float32)
+        for t, a in enumerate(seq):
+            x[t, 0, a] = 8.0
+        return x
+    beam = lambda seq, **kw: _beam(onehot(seq), [len(seq)], **kw)[0][0]
+    assert beam([1, 2, 3, 4]) == [1, 2, 3, 4]
+    assert beam([63, 63, 63]) == []
+    assert beam([5, 5, 63, 5, 0, 7], merge_repeated=False) == [5, 5, 7]
+    assert beam([5, 5, 63, 5, 0, 7]) == [5, 7]                   # merge_repeated collapses the decoded double 5
+    assert beam([3, 63, 3, 63, 4]) == [3, 4]
+    assert beam([0, 1, 0, 2], strip=-1) == [0, 1, 0, 2]          # class 0 is an ordinary label to the decoder; the solver strips it
+
+
+@pytest.mark.parametrize("kind,seed", [("peaked", 2), ("soft", 5), ("flat", 7)])
+def test_beam_search_matches_oracle_restatement(kind, seed):
+    """crnn_ctc_beam_search == oracle.beam_search_decode (width 100, blank 63, merge_repeated) on peaked, soft and flat
+    frames with ragged lengths, including zero-length utterances; log-probability of the best prefix is finite."""
+    from oracle import crnn_oracle as O
+    def _peaked_lines(n, T, seed, margin=6.0):        # frames peaked at a path with CTC blanks (0), decoder blanks (63), repeats
+        r = np.random.default_rng(seed)
+        path = r.choice(64, size=(T, n), p=np.r_[0.25, np.full(62, 0.65 / 62), 0.10])
+        rep = r.random((T, n)) < 0.3
+        for t in range(1, T):
+            path[t] = np.where(rep[t], path[t - 1], path[t])
+        y = r.standard_normal((T, n, 64))
+        y[np.arange(T)[:, None], np.arange(n)[None, :], path] += margin
+        return y
+    rng = np.random.default_rng(seed)
+    T, N = 19, 10
+    if kind == "peaked":
+        x = _peaked_lines(N, T, seed=seed)
+    elif kind == "soft":
+        x = _peaked_lines(N, T, seed=seed, margin=2.0)
+    else:
+        x = rng.standard_normal((T, N, 64)) * 0.3
+    x = x.astype(np.float32)
+    il = rng.integers(0, T + 1, size=N).astype(np.int32)
+    il[0] = T; il[1] = 0
+    for merge in (True, False):
+        ref = O.beam_search_decode(x, il, beam_width=100, merge_repeated=merge)
+        got, nlp = _beam(x, il, beam_width=100, merge_repeated=merge)
+        assert got == ref, (kind, merge)
+        assert np.isfinite(nlp).all() and nlp[1] == 0.0
+    # a narrow beam still agrees with the oracle at the same width (exercises the full-list eviction path)
+    assert _beam(x, il, beam_width=3)[0] == O.beam_search_decode(x, il, beam_width=3)
+
+
+def test_beam_search_rejects_bad_lengths():
+    from lstm_ctc_ocr_b200 import engine
+    from lstm_ctc_ocr_b200._lib import CrnnError
+    x = np.zeros((4, 2, 64), np.float32)
+    with pytest.raises(CrnnError):
+        engine.ctc_beam_search(x, [5, 1])
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# data path, SURVEY 8(f)2: width-bucketing sampler, rank-distinct streams, prefetching feeder (gen.py:112-128 replacement)
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("render", [True, False])
+def test_bucket_sampler_contract(render):
+    """BASELINE configs[3]: every batch comes from ONE bucket of W in {80,160,256}, is padded to that width, and every line's
+    true width lies in (previous bucket, W] (rendered: resized width; synthetic: SURVEY 8(d), at least one line of width W)."""
+    from lstm_ctc_ocr_b200.lib.lstm.utils import gen
+    s = gen.BucketSampler(batch_size=12, render=render, seed=5, rank=0, world=1)
+    for k, W in zip(range(3), gen.BUCKETS):
+        assert s.bucket_of(k) == W and s.bucket_of(k + 3) == W
+        imgs, flat, lens, steps = s.batch(k)
+        lo = max([b for b in gen.BUCKETS if b < W] or [0])
+        assert len(imgs) == 12 and all(a.shape == (W, 32) and a.dtype == np.float32 for a in imgs)
+        assert len(flat) == sum(lens) and 1 <= min(flat) and max(flat) <= 62
+        assert max(steps) <= W // 4 - 1
+        widths = [int(np.nonzero(a.any(axis=1))[0].max()) + 1 for a in imgs]        # last non-zero column + 1
+        if render:
+            assert all(lo // 4 - 1 <= st <= W // 4 - 1 for st in steps)
+            assert all(w <= W for w in widths) and max(widths) > lo
+        else:
+            assert max(steps) == W // 4 - 1 and all(lo < w <= W for w in widths)
+    # deterministic: batch k is a pure function of (seed, k, rank, world)
+    a, b = s.batch(4), gen.BucketSampler(batch_size=12, render=render, seed=5, rank=0, world=1).batch(4)
+    assert all(np.array_equal(x, y) for x, y in zip(a[0], b[0])) and a[1:] == b[1:]
+
+
+def test_data_parallel_ranks_draw_different_batches():
+    """ADVICE r1 (gen.py:82): the synthetic fallback seeded every rank identically.  batch k of rank r now uses seed
+    base + k*world + r: ranks differ, and the union over ranks at step k never repeats a batch of another step."""
+    from lstm_ctc_ocr_b200.lib.lstm.utils import gen
+    for render in (False, True):
+        b0 = gen.make_batch(0, 6, render, seed=3, rank=0, world=2)
+        b1 = gen.make_batch(0, 6, render, seed=3, rank=1, world=2)
+        assert b0[1] != b1[1]
+    seeds = {gen.batch_seed(k, 3, r, 4) for k in range(50) for r in range(4)}
+    assert len(seeds) == 200
+    g0 = gen.generator(batch_size=4, render=False, seed=3, rank=0, world=2)
+    g1 = gen.generator(batch_size=4, render=False, seed=3, rank=1, world=2)
+    assert next(g0)[1] != next(g1)[1]
+
+
+def test_prefetch_feeder_delivers_the_stream_in_order():
+    """PrefetchFeeder (stands in for GeneratorEnqueuer + multiprocessing.Queue, gen.py:112-128): render processes, batches
+    delivered in order as views of a ring of slots; a view stays intact until `depth` further batches were taken."""
+    from lstm_ctc_ocr_b200.lib.lstm.utils import gen
+    arg_fn = lambda k: dict(k=k, batch_size=6, render=True, seed=11, rank=0, world=1, bucket=gen.BUCKETS[k % 3])
+    ref = [gen.make_batch(**arg_fn(k)) for k in range(7)]
+    for workers in (0, 2):
+        f = gen.PrefetchFeeder(arg_fn, num_workers=workers, depth=3, max_width=256, batch_size=6)
+        try:
+            held = []
+            for k in range(7):
+                view, lab, ll, tsl = next(f)
+                assert isinstance(view, np.ndarray) and view.shape == (6, gen.BUCKETS[k % 3], 32) and view.flags.c_contiguous
+                assert np.array_equal(view, np.stack(ref[k][0])) and (lab, ll, tsl) == tuple(ref[k][1:])
+                held.append((k, view))
+                for kk, v in held[-3:]:                                         # the last `depth` views are still valid
+                    assert np.array_equal(v, np.stack(ref[kk][0]))
+        finally:
+            f.close()
+    # the reference entry point: get_batch(num_workers=N, batch_size=B) -> iterator of data-layer tuples
+    it = gen.get_batch(num_workers=2, batch_size=5, render=True, seed=11)
+    try:
+        imgs, flat, lens, steps = next(it)
+        assert len(imgs) == 5 and len(flat) == sum(lens) and len(steps) == 5
+    finally:
+        if hasattr(it, "close"):
+            it.close()
