@@ -110,6 +110,35 @@ def cpu_reference(N, W, steps, warmup, seed=3):
     return dict(value=N / t, ms_per_step=t * 1e3, loss=loss, cores=torch.get_num_threads())
 
 
+def ctc_loss_delta(engine, synthetic, torch, dev, W, n_lines, seeds=(3, 4, 5)):
+    """GPU path vs the fp64 oracle: total loss (mean CTC NLL + L2) and logits on `n_lines` seeded lines of 32xW per seed."""
+    from oracle import crnn_oracle as O
+    rows, worst_rel, worst_logit = [], 0.0, 0.0
+    for seed in seeds:
+        params = synthetic.init_params(seed)
+        m = engine.CrnnModel(weight_decay=1e-5, device=dev)            # fresh handle: inference mode, untouched parameters
+        m.load_params(params)
+        data, lab, ll, tsl = synthetic.synth_batch(n_lines, W, seed=seed)
+        t_ = lambda a: torch.tensor(a, device=dev)
+        lg = m.forward(t_(data), t_(tsl))
+        cs, _ = engine.ctc_loss(lg, t_(lab), t_(ll), t_(tsl), max_label_len=int(ll.max()))
+        gpu_loss = float(m.total_loss(cs).item())
+        p64 = O.to_torch({k: v.astype(np.float64) for k, v in params.items()})
+        lo = O.forward(p64, data.astype(np.float64), tsl).numpy()
+        co, _ = O.ctc_loss_np(lo, lab, ll, tsl, want_grad=False)
+        ref_loss = float(co.mean() + float(O.l2_reg(p64, 1e-5)))
+        rel = abs(gpu_loss - ref_loss) / abs(ref_loss)
+        lerr = float(np.abs(lg.cpu().numpy() - lo).max() / np.abs(lo).max())
+        rows.append({"seed": seed, "gpu": round(gpu_loss, 5), "oracle_fp64": round(ref_loss, 5), "rel": round(rel, 7),
+                     "max_logit_err_rel": round(lerr, 6)})
+        worst_rel, worst_logit = max(worst_rel, rel), max(worst_logit, lerr)
+        del m
+    return {"rel": round(worst_rel, 7), "max_logit_err_rel": round(worst_logit, 6), "per_seed": rows, "tolerance": 5e-3,
+            "within_tolerance": bool(worst_rel <= 5e-3),
+            "sample": f"{n_lines} lines of 32x{W} per seed, reference initialisers, fresh inference-mode model vs the fp64 oracle "
+                      f"(mean CTC NLL + L2 term; max |logit error| / max |logit|)"}
+
+
 def run_reference_arm(args, rank):
     N_full, W, desc = WORKLOADS[args.workload]
     if rank != 0:
@@ -228,28 +257,60 @@ def main():
     stage_names = [model.lib.crnn_profile_stage_name(i).decode() for i in range(nst)]
     ctc_ms = float(np.mean([a.elapsed_time(b) for a, b in ctc_ev]))
 
-    # ---- e2e: the reference-facing call (Session.run on HOST numpy buffers; H2D + D2H inside the timed region)
+    # ---- e2e: the reference-facing call (Session.run on HOST numpy buffers; H2D + D2H inside the timed region), three feeds:
+    #   feeder          fresh batch every step, produced by the PrefetchFeeder's worker processes straight into page-locked ring
+    #                   slots (lib/lstm/utils/gen.py; replaces GeneratorEnqueuer + Queue, reference gen.py:112-128) -> DMA in place,
+    #                   chunked and overlapped with the conv front end (crnn_forward_host).  THE HEADLINE e2e.
+    #   fresh_pageable  a brand-new pageable numpy array every step, as the reference's solver builds it (train.py:119-125):
+    #                   host copy into pinned staging, then copy-then-compute
+    #   refed_buffers   round 1's best case: the same few host buffers fed again and again (page-locked in place on re-sighting)
+    from lstm_ctc_ocr_b200.lib.lstm.utils import gen as datagen
     net = get_network("LSTM_train")
     sess = Session(device=dev)
     sess._engines[id(net)] = model            # same weights / same engine instance
     loss_h, _ = net.build_loss()
-
-    def e2e_step(i):
-        data, lab, ll, tsl = batches[i % nrot][5]
-        return sess.run(loss_h, feed_dict={net.data: data, net.labels: lab, net.time_step_len: tsl, net.labels_len: ll,
-                                           net.keep_prob: 0.5})
-    for i in range(max(3, 3 * nrot)):      # every rotating host buffer is fed three times: page-locked in place on its second
-                                           # sighting, fed through the chunked crnn_forward_host path from the third on
-        e2e_step(i)
-    sync_all()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     Ke = max(3, min(K, 10))
-    f0.record()
-    for i in range(Ke):
-        e2e_loss = e2e_step(i)
-    f1.record()
-    sync_all()
-    ms_e2e = f0.elapsed_time(f1)
+
+    def run_on(data, lab, ll, tsl):
+        return sess.run(loss_h, feed_dict={net.data: data, net.labels: lab, net.time_step_len: tsl, net.labels_len: ll, net.keep_prob: 0.5})
+
+    def timed(fn, n):
+        sync_all()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(n):
+            out = fn(i)
+        f1.record()
+        sync_all()
+        return f0.elapsed_time(f1), out
+
+    e2e_var = {}
+    # (a) feeder
+    nwork = int(os.environ.get("CRNN_BENCH_FEED_WORKERS", "8"))
+    arg_fn = lambda k: dict(k=k, batch_size=N, render=False, seed=3 + 1000 * rank, rank=0, world=1, width=W, cache=4)
+    feeder = datagen.PrefetchFeeder(arg_fn, num_workers=nwork, depth=4, max_width=W, batch_size=N, keep=2)
+    try:
+        def feed_step(i):
+            view, lab, ll, tsl = next(feeder)
+            return run_on(view, np.asarray(lab, np.int32), np.asarray(ll, np.int32), np.asarray(tsl, np.int32))
+        for i in range(max(8, 6 * nwork)):    # producers come up and fill their batch caches
+            feed_step(i)
+        feed_path = sess.last_feed_path
+        ms_feed, e2e_loss = timed(feed_step, Ke)
+        h2d_b, d2h_b = int(sess.h2d_bytes), int(sess.d2h_bytes)
+    finally:
+        feeder.close()
+    # (b) fresh pageable array every step
+    fresh = [np.array(batches[i % nrot][5][0]) for i in range(Ke + 2)]
+    run_on(fresh[0], *batches[0][5][1:]); run_on(fresh[1], *batches[1 % nrot][5][1:])
+    ms_fresh, _ = timed(lambda i: run_on(fresh[i + 2], *batches[(i + 2) % nrot][5][1:]), Ke)
+    fresh_path = sess.last_feed_path
+    del fresh
+    # (c) the same host buffers re-fed
+    for i in range(max(3, 3 * nrot)):
+        run_on(*batches[i % nrot][5])
+    ms_refed, _ = timed(lambda i: run_on(*batches[i % nrot][5]), Ke)
+    ms_e2e = ms_feed
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- BASELINE configs[4] companion: full training step (fwd + CTC + backward + [NCCL grad all-reduce] + clip + Adam)
@@ -289,10 +350,11 @@ def main():
 
     # ---- max over ranks
     if world > 1:
-        t = torch.tensor([ms_total, ms_e2e, ms_train or 0.0], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_total, ms_e2e, ms_train or 0.0, ms_fresh, ms_refed], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, ms_e2e = float(t[0]), float(t[1])
         ms_train = float(t[2]) if ms_train is not None else None
+        ms_fresh, ms_refed = float(t[3]), float(t[4])
     ms_step = ms_total / K
     value = world * N / (ms_step / 1e3)
     e2e_value = world * N / (ms_e2e / Ke / 1e3)
@@ -333,9 +395,16 @@ def main():
                        "l2": f"rotating {nrot} distinct input batches ({nrot * N * W * 32 * 4 / 1e6:.0f} MB > 126 MB L2); "
                              f"per-step activation traffic ~2.5 GB"},
             "loss": round(loss_val, 5),
-            "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": int(sess.h2d_bytes),
-                    "d2h_bytes_per_step": int(sess.d2h_bytes), "steps": Ke, "api": "Session.run(loss, feed_dict=host numpy)",
-                    "loss": float(e2e_loss)},
+            "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": h2d_b,
+                    "d2h_bytes_per_step": d2h_b, "steps": Ke, "api": "Session.run(loss, feed_dict=host numpy)",
+                    "feed": f"PrefetchFeeder: a fresh batch every step, written by {nwork} producer processes into page-locked "
+                            f"shared-memory ring slots, DMA'd in place ({feed_path})",
+                    "loss": float(e2e_loss),
+                    "variants": {
+                        "fresh_pageable_array_every_step": {"value": round(world * N / (ms_fresh / Ke / 1e3), 1), "path": fresh_path,
+                                                            "what": "np.array(...) built per step as reference train.py:119-125 does; staged through pinned memory"},
+                        "refed_host_buffers": {"value": round(world * N / (ms_refed / Ke / 1e3), 1),
+                                               "what": "round-1 e2e: the same host buffers re-fed (page-locked in place on re-sighting)"}}},
             "gpu_launches": K * 16,      # per step: conv1, 8 tcgen05 GEMMs, 2x(bn finalize + apply), persistent LSTM, CTC, loss
             "roofline": roofline, "stages": stages, "clocks": clocks,
         }
@@ -349,19 +418,15 @@ def main():
             r = cpu_reference(sn, W, steps=8, warmup=2)
             line["cpu_baseline"] = {"value": round(r["value"], 2), "unit": "images/s", "cores": r["cores"], "kind": "port",
                                     "sample": f"{sn} lines of 32x{W} per step (same shapes, fp32 torch-CPU restatement), median of 8"}
-            # BASELINE metric, second half ("CTC-loss delta vs ref"): the same sample (same seeds, same initialisers) through the GPU path
+            line["cpu_baseline"]["host_cpus"] = os.cpu_count()
+            line["cpu_baseline"]["threads_note"] = "cores = torch threads that ran fastest on this host (ladder 8/16/32/64/all); host_cpus = os.cpu_count()"
+            # BASELINE metric, second half ("CTC-loss delta vs ref"): a FRESH inference-mode model with the reference initialisers
+            # (the round-1 figure was taken on a model that had already run 13 Adam steps) against the fp64
+            # oracle on the same seeded 32x256 samples, three seeds.
             try:
-                sd, slab, sll, stsl = synthetic.synth_batch(sn, W, seed=3)
-                t_ = lambda a: torch.tensor(a, device=dev)
-                lg = model.forward(t_(sd), t_(stsl))
-                cs, _ = engine.ctc_loss(lg, t_(slab), t_(sll), t_(stsl), max_label_len=int(sll.max()))
-                gpu_loss = float(model.total_loss(cs).item())
-                cpu_loss = float(r["loss"])
-                line["ctc_loss_delta"] = {"gpu": round(gpu_loss, 5), "cpu_port_fp32": round(cpu_loss, 5),
-                                          "rel": round(abs(gpu_loss - cpu_loss) / abs(cpu_loss), 6),
-                                          "sample": f"{sn} lines of 32x{W}, seed 3, reference initialisers (mean CTC NLL + L2 term)"}
+                line["ctc_loss_delta"] = ctc_loss_delta(engine, synthetic, torch, dev, W, sn)
             except Exception as e:      # never lose the bench line over the side statistic
-                line["ctc_loss_delta"] = {"error": repr(e)[:200]}
+                line["ctc_loss_delta"] = {"error": repr(e)[:300]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -102,6 +102,7 @@ class Session(object):
         self._pinned = _Pinned()
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.last_feed_path = None    # "page-locked in place" (chunked crnn_forward_host) | "staged" (copy into pinned staging first)
         import os
         self.h2d_chunks = int(os.environ.get("CRNN_H2D_CHUNKS", "4"))   # image ranges of the overlapped host->device feed (1 = copy, then compute)
 
@@ -194,9 +195,11 @@ class Session(object):
         if self.h2d_chunks > 1 and self._pinned.is_page_locked(data):
             # large re-fed batch buffer (page-locked in place): chunked H2D overlapped with the conv front end
             logits, d_data = eng.forward_host(data, d_tsl, chunks=self.h2d_chunks)
+            self.last_feed_path = "page-locked in place"
         else:
             d_data = self._pinned.stage("data", data, dev)
             logits = eng.forward(d_data, d_tsl)
+            self.last_feed_path = "staged"
         costs = grad = loss = None
         if need_labels:
             d_lab = self._pinned.stage("labels", labels, dev)
