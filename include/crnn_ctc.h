@@ -91,7 +91,10 @@ typedef struct crnn_config {
   int   num_hid;        /* cfg.TRAIN.NUM_HID = 512    (lib/lstm/config.py:48) */
   float bn_eps;         /* 1e-3  tf.contrib.layers.batch_norm default */
   float weight_decay;   /* cfg.TRAIN.WEIGHT_DECAY (lstm/lstm.yml:13 -> 1e-5) */
-  int   compute_dtype;  /* 1 = bf16 operands / f32 accumulate (tcgen05 kind::f16) */
+  int   compute_dtype;  /* 1 = bf16 operands / f32 accumulate (tcgen05 kind::f16): the throughput path, forward + backward.
+                         * 2 = f32-class: every operand split into bf16 hi + bf16 lo, three tcgen05 products per term, f32
+                         *     accumulate and f32 elementwise math (the reference computes in fp32, LSTM_train.py:10);
+                         *     forward + CTC only (BASELINE configs[1]) */
 } crnn_config;
 
 int     crnn_model_create(const crnn_config* cfg, crnn_model** out);
@@ -148,6 +151,36 @@ int     crnn_backward(crnn_model* m, const float* data, const int* time_step_len
 int     crnn_clip_adam_step(crnn_model* m, float lr, float clip, int step, float grad_mul, float wd_mul,
                             crnn_stream_t stream);
 int     crnn_last_grad_norm(crnn_model* m, float grad_mul, float* out_host, crnn_stream_t stream);   /* syncs */
+
+/* ------------------------------------------------------------------------------------------
+ * Data parallelism (one process per GPU).  The reference is single-device: its BatchNorm sees the whole batch
+ * (lib/networks/network.py:177-178) and its optimizer the whole-batch gradient (lib/lstm/train.py:81-83).  With the batch
+ * sharded over `world` ranks the same function needs (1) the BN sums of conv4_1 / conv4_2 -- forward [sum x, sum x^2] and
+ * backward [sum dy, sum dy*xhat], 2 x 512 f64 each -- summed over ranks, and (2) the SUM of the flat gradient buffers before
+ * crnn_clip_adam_step(grad_mul = 1/world, wd_mul = world).
+ *
+ * (1) crnn_model_set_data_parallel switches the BN layers to global-batch statistics.  The exchange runs INSIDE the BN
+ *     finalize kernel over NVLink peer memory when crnn_model_set_peers was called (every rank stores its 8 KB of sums into
+ *     every peer's inbox, release/acquire flags at system scope, fixed-order f64 summation: bit-identical on all ranks, no
+ *     NCCL launch on the forward path); otherwise through `allreduce` (e.g. an NCCL all-reduce issued by the caller).
+ * (2) crnn_model_set_grad_ready_callback: crnn_backward calls `fn(user, offset, count, stream)` as soon as the gradients of a
+ *     contiguous range [offset, offset+count) of the flat buffer are final (LSTM+logits first, conv1+conv2 last, 7 ranges
+ *     covering the buffer exactly once), so the caller can all-reduce each range on a side stream while the rest of the
+ *     backward pass still runs.
+ * ---------------------------------------------------------------------------------------- */
+typedef int  (*crnn_allreduce_fn)(void* user, void* dev_ptr, size_t count, int is_f64, crnn_stream_t stream);   /* in-place SUM */
+typedef void (*crnn_grad_ready_fn)(void* user, int64_t offset, int64_t count, crnn_stream_t stream);
+int     crnn_model_set_data_parallel(crnn_model* m, int rank, int world, crnn_allreduce_fn allreduce, void* user);
+int     crnn_model_set_grad_ready_callback(crnn_model* m, crnn_grad_ready_fn fn, void* user);
+/* Peer-memory inboxes (cudaMalloc + CUDA IPC): create one per rank, exchange the 64-byte handles through the host language
+ * (e.g. torch.distributed.all_gather_object), open the peers', hand all `world` pointers (own at [rank]) to the model. */
+size_t  crnn_peer_inbox_bytes(void);
+int     crnn_peer_inbox_create(void** dev_ptr, unsigned char handle[64]);
+int     crnn_peer_inbox_open(const unsigned char handle[64], void** dev_ptr);
+int     crnn_peer_inbox_close(void* dev_ptr);      /* a pointer obtained from crnn_peer_inbox_open */
+int     crnn_peer_inbox_destroy(void* dev_ptr);    /* a pointer obtained from crnn_peer_inbox_create */
+int     crnn_model_set_peers(crnn_model* m, int rank, int world, void* const* inbox_ptrs_host);
+int     crnn_peer_error(crnn_model* m, int* err_host);   /* 1 if an exchange timed out waiting for a peer (syncs the device) */
 
 /* Debug/parity taps: copy a named intermediate of the last crnn_forward() as f32 into dst.
  * names: "conv1" "conv2" "conv3_1" "conv3_2" "conv4_1" "conv4_2" "conv5" "lstm_out"

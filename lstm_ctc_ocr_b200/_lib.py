@@ -51,9 +51,21 @@ SIGNATURES = {
     "crnn_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "crnn_clip_adam_step": (c_int, [c_void_p, c_float, c_float, c_int, c_float, c_float, c_void_p]),
     "crnn_last_grad_norm": (c_int, [c_void_p, c_float, ctypes.POINTER(c_float), c_void_p]),
+    "crnn_model_set_data_parallel": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "crnn_model_set_grad_ready_callback": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "crnn_peer_inbox_bytes": (c_size_t, []),
+    "crnn_peer_inbox_create": (c_int, [ctypes.POINTER(c_void_p), c_void_p]),
+    "crnn_peer_inbox_open": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
+    "crnn_peer_inbox_close": (c_int, [c_void_p]),
+    "crnn_peer_inbox_destroy": (c_int, [c_void_p]),
+    "crnn_model_set_peers": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "crnn_peer_error": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
     "crnn_test_gemm_tn_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "crnn_test_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }
+
+ALLREDUCE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, c_size_t, c_int, c_void_p)
+GRAD_READY_FN = ctypes.CFUNCTYPE(None, c_void_p, c_int64, c_int64, c_void_p)
 
 _lib = None
 

@@ -15,6 +15,7 @@
 
 extern "C" int crnn_model_set_training(crnn_model* m, int flag) {
   if (!m) return crnn_fail(CRNN_INVALID_VALUE, "set_training: null model");
+  if (flag && m->cfg.compute_dtype == 2) return crnn_fail(CRNN_UNSUPPORTED, "set_training: the f32-class path (compute_dtype 2) is forward + CTC only");
   if (flag && !m->wblock_bwd) {
     const size_t nB[9] = {512 * 4608, 256 * 4608, 256 * 2304, 128 * 2304, 64 * 1152, 1024 * 1024, 512 * 64, 512 * 2048, 512 * 1024};
     size_t tot = 1024;
@@ -100,6 +101,12 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   const int H1 = pl.H1, H2 = pl.H2, T = pl.T, sms = m->num_sms;
   const long long R = (long long)N * H2;
   auto G = [&](const std::string& n) { return m->grads + m->find(n)->offset; };
+  auto notify = [&](const char* first, const char* next) {     // gradients of tensors [first, next) of the table are final
+    if (!m->grad_cb) return;
+    const long long o = m->find(first)->offset;
+    const long long e = next ? m->find(next)->offset : m->total;
+    m->grad_cb(m->grad_user, o, e - o, stream);
+  };
   cudaEvent_t* ev = nullptr;
   if (m->prof_on && m->prof_used_bwd < m->prof_slots) ev = &m->prof_events_bwd[(size_t)(m->prof_used_bwd++) * (kNumBwdStages + 1)];
   int evi = 0;
@@ -168,6 +175,11 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
       p.num_n_tiles = 4; p.lstm_cols = 1; p.out_row_offset = 512; p.a_row_shift = +1;
       CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_PLAIN, 4>(pl.tT_lstm_bw, pl.tT_dz_bw, p, sms, st)));
     }
+    // LSTM (both directions) and the 512 -> 64 projection are the tail of the flat buffer: their gradients are final here
+    if (m->grad_cb) {
+      const long long o = m->find(fw + "/weights")->offset;
+      m->grad_cb(m->grad_user, o, m->total - o, stream);
+    }
     {  // dx = dz W_x^T  ->  gradient w.r.t. the conv5 feature rows
       gemm::Params p;
       memset(&p, 0, sizeof(p));
@@ -186,6 +198,7 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
     if (m->use_2cta) { p.num_m_tiles = 4; CRNN_TRY((launch_gemm_tn2<gemm_tn::TN_PLAIN, 6>(pl.tT_a4b, pl.tT_da5, p, sms, st))); }
     else CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_PLAIN, 4>(pl.tT_a4b, pl.tT_da5, p, sms, st)));
   }
+  notify("conv5/weights", "logits/bidirectional_rnn/fw/lstm_cell/weights");
   {
     gemm::Params p;
     memset(&p, 0, sizeof(p));
@@ -198,8 +211,15 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   // ------------------------------------------------------------------ conv4_2: pool3 + ReLU + batch-stat BN backward
   CUDA_TRY(cudaMemsetAsync(pl.bn_bwd_sums, 0, 2 * 2 * 512 * sizeof(double), st));
   const size_t P4 = (size_t)N * H2 * 4;
-  CRNN_TRY(launch_bn_bwd_reduce(true, pl.d_a4b, pl.a4b_pre, pl.d_pre4b, pl.bn + 2048, pl.bn_bwd_sums + 1024, P4 / 2, 512, st));
-  CRNN_TRY(launch_bn_bwd_apply(pl.d_pre4b, pl.a4b_pre, pl.bn + 2048, m->P("conv4_2/conv4_2/gamma"), pl.bn_bwd_sums + 1024, (double)P4, P4,
+  const double P4g = (double)P4 * m->dp_world;         // positions of the batch the BN statistics were taken over
+  // data parallel: [sum dy, sum dy*xhat] over the GLOBAL batch (exchanged over peer memory / the callback), local sums kept for dgamma/dbeta
+  double* sums42 = pl.bn_bwd_sums + 1024;
+  double* sums41 = pl.bn_bwd_sums;
+  double* gsum42 = m->dp_world > 1 ? pl.bn_bwd_sums + 3072 : sums42;
+  double* gsum41 = m->dp_world > 1 ? pl.bn_bwd_sums + 2048 : sums41;
+  CRNN_TRY(launch_bn_bwd_reduce(true, pl.d_a4b, pl.a4b_pre, pl.d_pre4b, pl.bn + 2048, sums42, P4 / 2, 512, st));
+  if (m->dp_world > 1) CRNN_TRY(dp_allreduce_1024(m, sums42, gsum42, st));
+  CRNN_TRY(launch_bn_bwd_apply(pl.d_pre4b, pl.a4b_pre, pl.bn + 2048, m->P("conv4_2/conv4_2/gamma"), gsum42, sums42, P4g, P4,
                                512, pl.bn_bwd_coef, G("conv4_2/conv4_2/gamma"), G("conv4_2/conv4_2/beta"), st));
   CRNN_TRY(launch_colsum_bf16(pl.d_pre4b, (long long)P4, 512, G("conv4_2/biases"), 0, 0, st));
   BMARK();
@@ -209,6 +229,7 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
     if (m->use_2cta) { p.num_m_tiles = 2; CRNN_TRY((launch_gemm_tn2<gemm_tn::TN_CONV, 6>(pl.tW_a4a, pl.tW_p4b, p, sms, st))); }
     else CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tW_a4a, pl.tW_p4b, p, sms, st)));
   }
+  notify("conv4_2/weights", "conv5/weights");
   BMARK();
   {
     gemm::Params p = conv_params(N, H2, 4, 512, 512, 256, nullptr, pl.d_pre4a, pl.mg4);
@@ -217,8 +238,9 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   }
   BMARK();
   // ------------------------------------------------------------------ conv4_1: ReLU + BN backward
-  CRNN_TRY(launch_bn_bwd_reduce(false, pl.d_pre4a, pl.a4a_pre, pl.d_pre4a, pl.bn, pl.bn_bwd_sums, P4, 512, st));
-  CRNN_TRY(launch_bn_bwd_apply(pl.d_pre4a, pl.a4a_pre, pl.bn, m->P("conv4_1/conv4_1/gamma"), pl.bn_bwd_sums, (double)P4, P4, 512,
+  CRNN_TRY(launch_bn_bwd_reduce(false, pl.d_pre4a, pl.a4a_pre, pl.d_pre4a, pl.bn, sums41, P4, 512, st));
+  if (m->dp_world > 1) CRNN_TRY(dp_allreduce_1024(m, sums41, gsum41, st));
+  CRNN_TRY(launch_bn_bwd_apply(pl.d_pre4a, pl.a4a_pre, pl.bn, m->P("conv4_1/conv4_1/gamma"), gsum41, sums41, P4g, P4, 512,
                                pl.bn_bwd_coef, G("conv4_1/conv4_1/gamma"), G("conv4_1/conv4_1/beta"), st));
   CRNN_TRY(launch_colsum_bf16(pl.d_pre4a, (long long)P4, 512, G("conv4_1/biases"), 0, 0, st));
   BMARK();
@@ -228,6 +250,7 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
     if (m->use_2cta) { p.num_m_tiles = 1; CRNN_TRY((launch_gemm_tn2<gemm_tn::TN_CONV, 6>(pl.tW_a3p, pl.tW_p4a, p, sms, st))); }
     else CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tW_a3p, pl.tW_p4a, p, sms, st)));
   }
+  notify("conv4_1/weights", "conv4_2/weights");
   BMARK();
   {
     gemm::Params p = conv_params(N, H2, 4, 512, 256, 256, nullptr, pl.d_a3p, pl.mg4);
@@ -245,6 +268,7 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
     if (m->use_2cta) { p.num_m_tiles = 1; CRNN_TRY((launch_gemm_tn2<gemm_tn::TN_CONV, 6>(pl.tW_a3, pl.tW_p32, p, sms, st))); }
     else CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tW_a3, pl.tW_p32, p, sms, st)));
   }
+  notify("conv3_2/weights", "conv4_1/weights");
   BMARK();
   {
     gemm::Params p = conv_params(N, H2, 8, 256, 256, 256, nullptr, pl.d_pre31, pl.mg3);
@@ -261,6 +285,7 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
     p.num_n_tiles = 1;
     CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tW_a2, pl.tW_p31, p, sms, st)));
   }
+  notify("conv3_1/weights", "conv3_2/weights");
   BMARK();
   {
     gemm::Params p = conv_params(N, H2, 8, 256, 128, 128, nullptr, pl.d_a2, pl.mg3);
@@ -286,6 +311,7 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   BMARK();
   // ------------------------------------------------------------------ conv1 (K = 9, SIMT): pool1 + ReLU folded in
   CRNN_TRY(launch_conv1_wgrad(pl.d_a1, pl.a1, pl.am1, data, G("conv1/weights"), G("conv1/biases"), N, W, st));
+  notify("conv1/weights", "conv3_1/weights");
   BMARK();
 #undef BMARK
   return CRNN_OK;

@@ -168,9 +168,11 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
 
 // pass 2a: per-channel coefficients of  dx = A*dy + B + C*x   (from dx = gamma*invstd*(dy - mean(dy) - xhat*mean(dy*xhat))),
 // plus dgamma = sum(dy*xhat), dbeta = sum(dy)
+// `sums` / `count` describe the batch the statistics were taken over (the GLOBAL batch under data parallelism); the gamma / beta
+// gradients accumulate this rank's LOCAL sums (the flat gradient buffers are summed over ranks afterwards).
 __global__ void bn_bwd_coef_kernel(const float* __restrict__ bn, const float* __restrict__ gamma, const double* __restrict__ sums,
-                                   double count, int C, float* __restrict__ coef, float* __restrict__ dgamma,
-                                   float* __restrict__ dbeta) {
+                                   const double* __restrict__ sums_local, double count, int C, float* __restrict__ coef,
+                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mu = bn[2 * C + c], is = bn[3 * C + c], g = gamma[c];
@@ -178,8 +180,8 @@ __global__ void bn_bwd_coef_kernel(const float* __restrict__ bn, const float* __
   coef[c] = (float)(g * is);
   coef[C + c] = (float)(-g * is * m1 + g * is * is * m2 * mu);
   coef[2 * C + c] = (float)(-g * is * is * m2);
-  dbeta[c] += (float)sums[c];
-  dgamma[c] += (float)sums[C + c];
+  dbeta[c] += (float)sums_local[c];
+  dgamma[c] += (float)sums_local[C + c];
 }
 // pass 2b: elementwise, in place on dy
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(uint4* __restrict__ dy, const uint4* __restrict__ x_pre,
@@ -491,9 +493,10 @@ int launch_bn_bwd_reduce(bool pool, const __nv_bfloat16* dout, const __nv_bfloat
   LAUNCH_CHECK();
 }
 int launch_bn_bwd_apply(__nv_bfloat16* dy, const __nv_bfloat16* x_pre, const float* bn, const float* gamma, const double* sums,
-                        double count, size_t positions, int C, float* coef, float* dgamma, float* dbeta, cudaStream_t st) {
+                        const double* sums_local, double count, size_t positions, int C, float* coef, float* dgamma, float* dbeta,
+                        cudaStream_t st) {
   const size_t nvec = positions * C / 8;
-  bn_bwd_coef_kernel<<<(C + 127) / 128, 128, 0, st>>>(bn, gamma, sums, count, C, coef, dgamma, dbeta);
+  bn_bwd_coef_kernel<<<(C + 127) / 128, 128, 0, st>>>(bn, gamma, sums, sums_local, count, C, coef, dgamma, dbeta);
   CUDA_TRY(cudaGetLastError());
   bn_bwd_apply_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, st>>>((uint4*)dy, (const uint4*)x_pre, coef, nvec, C);
   LAUNCH_CHECK();

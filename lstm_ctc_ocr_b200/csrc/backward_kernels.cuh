@@ -13,7 +13,8 @@ int launch_colsum_bf16(const __nv_bfloat16* src, long long R, int C, float* out,
 int launch_bn_bwd_reduce(bool pool, const __nv_bfloat16* dout, const __nv_bfloat16* x_pre, __nv_bfloat16* dy, const float* bn,
                          double* sums, size_t out_positions, int C, cudaStream_t st);
 int launch_bn_bwd_apply(__nv_bfloat16* dy, const __nv_bfloat16* x_pre, const float* bn, const float* gamma, const double* sums,
-                        double count, size_t positions, int C, float* coef, float* dgamma, float* dbeta, cudaStream_t st);
+                        const double* sums_local, double count, size_t positions, int C, float* coef, float* dgamma, float* dbeta,
+                        cudaStream_t st);
 int launch_relu_bwd(__nv_bfloat16* d, const __nv_bfloat16* a, size_t n, cudaStream_t st);
 int launch_unpool_relu_bwd(int win, const __nv_bfloat16* dpool, const __nv_bfloat16* pooled, const uint8_t* argmax,
                            __nv_bfloat16* dpre, size_t out_positions, int Hp, int Wp, int C, cudaStream_t st);

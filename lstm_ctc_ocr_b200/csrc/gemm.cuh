@@ -45,7 +45,8 @@ enum Epi {
   EPI_XPROJ = 8,        // + bias -> bf16 [N*H, 2048]; columns >= 1024 (backward direction) stored reversed-by-length
   EPI_CONV_STORE = 9,   // conv: plain bf16 NHWC store (data-gradient convolutions)
   EPI_RELU_POOL22_T = 10,  // training variants of the pooled epilogues: also emit the arg-max window index (uint8)
-  EPI_RELU_POOL12_T = 11
+  EPI_RELU_POOL12_T = 11,
+  EPI_CONV_F32 = 12     // conv: raw f32 accumulators, NHWC store (f32-class path, forward_x3.cu: bias/BN/ReLU/pool + hi/lo split follow)
 };
 
 struct Params {
@@ -56,6 +57,10 @@ struct Params {
   int merged;            // conv: the tile's 4 sub-boxes are contiguous H rows of one image -> one 128-position TMA box
   int debug_skip_tma;    // probe only: producer arrives without loading (measures the MMA/epilogue ceiling)
   int row_shift_mul;     // +1 (conv5 forward: rows m, m+1) or -1 (conv5 data gradient: rows m, m-1)
+  // split-bf16 ("3xbf16", f32-class) operands: the activation tensor stores [hi | lo] halves and the K loop visits
+  // [hi | lo | hi] against weights [wh | wh | wl]; a virtual K-block index >= the fold wraps back onto the hi half.  0 = off.
+  int cin_phys;          // A_CONV3: physical 64-channel blocks per tap (= 2*Cin/64 when cin_blocks = 3*Cin/64)
+  int kb_phys;           // A_PLAIN: physical K-blocks per row shift (kb_per_shift counts the virtual ones)
   int M;                 // valid rows (plain modes)
   int Nc;                // total output columns
   // conv geometry (A_CONV3 and conv epilogues)
@@ -128,7 +133,7 @@ __device__ __forceinline__ void run_epilogue(const Params& p, const uint32_t tba
   int n_img = 0, h = 0, w = 0;
   bool valid = true;
   if (EPI == EPI_RELU || EPI == EPI_RELU_POOL22 || EPI == EPI_RELU_POOL12 || EPI == EPI_STATS || EPI == EPI_CONV_STORE ||
-      EPI == EPI_RELU_POOL22_T || EPI == EPI_RELU_POOL12_T) {
+      EPI == EPI_RELU_POOL22_T || EPI == EPI_RELU_POOL12_T || EPI == EPI_CONV_F32) {
     const int g = m_blk * 4 + q;
     n_img = g / p.sb_per_img;
     const int hb = g - n_img * p.sb_per_img;
@@ -272,6 +277,19 @@ __device__ __forceinline__ void run_epilogue(const Params& p, const uint32_t tba
                             ptx::pack_bf16x2(__uint_as_float(v[i + 10]), __uint_as_float(v[i + 11])),
                             ptx::pack_bf16x2(__uint_as_float(v[i + 12]), __uint_as_float(v[i + 13])),
                             ptx::pack_bf16x2(__uint_as_float(v[i + 14]), __uint_as_float(v[i + 15])));
+      }
+    }
+  } else if (EPI == EPI_CONV_F32) {
+    float* out = reinterpret_cast<float*>(p.out) + (((size_t)n_img * p.H + h) * p.Wd + w) * p.Nc + col0;
+#pragma unroll 1
+    for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(tbase + c0, v);
+      ptx::tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<uint4*>(out + c0 + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
     }
   } else if (EPI == EPI_RELU_POOL22_T || EPI == EPI_RELU_POOL12_T) {
@@ -517,11 +535,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (lane < nA) {
               uint8_t* a_dst = smem_a + stage * A_STAGE_BYTES;
               if (AMODE == A_PLAIN) {
-                const int rs = kb / p.kb_per_shift, kc = kb - rs * p.kb_per_shift;
+                const int rs = kb / p.kb_per_shift;
+                int kc = kb - rs * p.kb_per_shift;
+                if (p.kb_phys > 0 && kc >= p.kb_phys) kc -= p.kb_phys;
                 ptx::tma_load_2d(&tmA, &full_bar[stage], a_dst, kc * BLOCK_K, m_blk * BLOCK_M + rs * p.row_shift_mul);
               } else {
                 const int r = tap / 3, sx = tap - 3 * r;
-                ptx::tma_load_4d(&tmA, &full_bar[stage], a_dst + lane * 4096, cb * BLOCK_K, sx - 1, ch0 + r - 1, cn);
+                const int cbp = (p.cin_phys > 0 && cb >= p.cin_phys) ? cb - p.cin_phys : cb;
+                ptx::tma_load_4d(&tmA, &full_bar[stage], a_dst + lane * 4096, cbp * BLOCK_K, sx - 1, ch0 + r - 1, cn);
               }
             } else {
               ptx::tma_load_2d(&tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, b_row);

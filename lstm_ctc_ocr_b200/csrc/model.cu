@@ -121,7 +121,8 @@ extern "C" int crnn_model_create(const crnn_config* cfg, crnn_model** out) {
   if (!cfg || !out) return crnn_fail(CRNN_INVALID_VALUE, "model_create: null");
   if (cfg->img_height != 32 || cfg->nclasses != 64 || cfg->num_hid != 512)
     return crnn_fail(CRNN_UNSUPPORTED, "model_create: only IMG_HEIGHT=32, NCLASSES=64, NUM_HID=512 (the reference's net)");
-  if (cfg->compute_dtype != 1) return crnn_fail(CRNN_UNSUPPORTED, "model_create: compute_dtype must be 1 (bf16)");
+  if (cfg->compute_dtype != 1 && cfg->compute_dtype != 2)
+    return crnn_fail(CRNN_UNSUPPORTED, "model_create: compute_dtype must be 1 (bf16 operands) or 2 (f32-class split-bf16 operands)");
   crnn_model* m = new crnn_model();
   m->cfg = *cfg;
   for (auto& c : kConvs) {
@@ -196,8 +197,10 @@ extern "C" int crnn_model_create(const crnn_config* cfg, crnn_model** out) {
 
 extern "C" int crnn_model_destroy(crnn_model* m) {
   if (!m) return CRNN_OK;
+  x3_destroy(m);
   if (m->wblock) cudaFree(m->wblock);
   if (m->wblock_bwd) cudaFree(m->wblock_bwd);
+  if (m->d_peers) cudaFree(m->d_peers);
   for (auto e : m->prof_events) cudaEventDestroy(e);
   for (auto e : m->prof_events_bwd) cudaEventDestroy(e);
   for (auto e : m->chunk_events) cudaEventDestroy(e);
@@ -221,12 +224,14 @@ extern "C" int crnn_model_bind(crnn_model* m, float* params, float* grads, float
   m->params = params; m->grads = grads; m->adam_m = adam_m; m->adam_v = adam_v;
   m->dirty = true;
   m->dirty_bwd = true;
+  x3_params_changed(m);
   return CRNN_OK;
 }
 extern "C" int crnn_model_params_changed(crnn_model* m) {
   if (!m) return crnn_fail(CRNN_INVALID_VALUE, "null model");
   m->dirty = true;
   m->dirty_bwd = true;
+  x3_params_changed(m);
   return CRNN_OK;
 }
 
@@ -305,7 +310,7 @@ size_t layout_plan(Plan& pl, int N, int W, uint8_t* base, bool train) {
     pl.d_a2 = (__nv_bfloat16*)take(n * h2 * 8 * 128 * 2);
     pl.d_pre2 = (__nv_bfloat16*)take(n * h1 * 16 * 128 * 2);
     pl.d_a1 = (__nv_bfloat16*)take(n * h1 * 16 * 64 * 2);
-    pl.bn_bwd_sums = (double*)take(2 * 2 * 512 * 8);
+    pl.bn_bwd_sums = (double*)take(4 * 2 * 512 * 8);      // [local | global-batch] x [2 layers][2][512]
     pl.bn_bwd_coef = (float*)take(3 * 512 * 4);
   }
   return off;
@@ -314,6 +319,11 @@ size_t layout_plan(Plan& pl, int N, int W, uint8_t* base, bool train) {
 extern "C" int crnn_model_workspace_size(const crnn_model* m, int N, int W, int train, size_t* bytes) {
   if (!m || !bytes) return crnn_fail(CRNN_INVALID_VALUE, "workspace_size: null");
   if (N <= 0 || W < 8 || (W % 4) != 0) return crnn_fail(CRNN_INVALID_VALUE, "workspace_size: need N>0, W>=8, W%%4==0 (gen.py:58)");
+  if (m->cfg.compute_dtype == 2) {
+    if (train) return crnn_fail(CRNN_UNSUPPORTED, "workspace_size: the f32-class path (compute_dtype 2) is forward + CTC only");
+    *bytes = x3_workspace_size(N, W);
+    return CRNN_OK;
+  }
   Plan pl;
   *bytes = layout_plan(pl, N, W, nullptr, train != 0);
   return CRNN_OK;
@@ -399,6 +409,13 @@ static int forward_impl(crnn_model* m, const float* data, const float* host_data
   CRNN_TRY(crnn_model_workspace_size(m, N, W, m->training ? 1 : 0, &need));
   if (workspace_bytes < need) return crnn_fail(CRNN_WORKSPACE_TOO_SMALL, "forward: workspace %zu < %zu", workspace_bytes, need);
   if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return crnn_fail(CRNN_INVALID_VALUE, "forward: workspace must be 1024-byte aligned");
+  if (m->cfg.compute_dtype == 2) {
+    // f32-class path (forward_x3.cu): copy-then-compute when fed from host memory
+    if (host_data != nullptr) {
+      CUDA_TRY(cudaMemcpyAsync(const_cast<float*>(data), host_data, (size_t)N * W * 32 * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    return x3_forward(m, data, time_step_len, N, W, logits_out, workspace, workspace_bytes, st);
+  }
   if (m->dirty) CRNN_TRY(prepare_weights(m, st));
   Plan& pl = m->plan;
   CRNN_TRY(ensure_plan(m, N, W, workspace, st));
@@ -500,6 +517,11 @@ static int forward_impl(crnn_model* m, const float* data, const float* host_data
     else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_STATS, 4>(pl.tA_c41, m->tB_c41, p, sms, st)));
     STAGE_MARK();
     float* bn = pl.bn;
+    // batch statistics over the GLOBAL batch when the batch is sharded over ranks: the exchange is fused into the finalize kernel
+    if (m->dp_world > 1)
+      CRNN_TRY(dp_allreduce_bn_finalize(m, pl.stats, bn_count * m->dp_world, m->P("conv4_1/conv4_1/gamma"), m->P("conv4_1/conv4_1/beta"),
+                                        m->cfg.bn_eps, bn, st));
+    else
     CRNN_TRY(launch_bn_finalize(pl.stats, bn_count, m->P("conv4_1/conv4_1/gamma"), m->P("conv4_1/conv4_1/beta"),
                                 m->cfg.bn_eps, bn, bn + 512, bn + 1024, bn + 1536, 512, st));
     CRNN_TRY(launch_bn_apply_relu(pl.a4a_pre, pl.a4a, bn, bn + 512, (size_t)N * H2 * 4, 512, st));
@@ -513,6 +535,10 @@ static int forward_impl(crnn_model* m, const float* data, const float* host_data
     else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_STATS, 4>(pl.tA_c42, m->tB_c42, p, sms, st)));
     STAGE_MARK();
     float* bn = pl.bn + 2048;
+    if (m->dp_world > 1)
+      CRNN_TRY(dp_allreduce_bn_finalize(m, pl.stats + 1024, bn_count * m->dp_world, m->P("conv4_2/conv4_2/gamma"),
+                                        m->P("conv4_2/conv4_2/beta"), m->cfg.bn_eps, bn, st));
+    else
     CRNN_TRY(launch_bn_finalize(pl.stats + 1024, bn_count, m->P("conv4_2/conv4_2/gamma"), m->P("conv4_2/conv4_2/beta"),
                                 m->cfg.bn_eps, bn, bn + 512, bn + 1024, bn + 1536, 512, st));
     CRNN_TRY(launch_bn_apply_relu_pool12(pl.a4b_pre, pl.a4b, bn, bn + 512, (size_t)N * H2 * 2, 512, st));
@@ -683,6 +709,7 @@ extern "C" int crnn_total_loss(crnn_model* m, const float* costs, int N, float* 
 extern "C" int crnn_debug_tap(crnn_model* m, const char* name, float* dst, size_t dst_elems, void* workspace,
                               crnn_stream_t stream) {
   if (!m || !name || !dst) return crnn_fail(CRNN_INVALID_VALUE, "debug_tap: null");
+  if (m->cfg.compute_dtype == 2) return x3_debug_tap(m, name, dst, dst_elems, workspace, reinterpret_cast<cudaStream_t>(stream));
   Plan& pl = m->plan;
   if (pl.ws == nullptr || pl.ws != workspace) return crnn_fail(CRNN_INVALID_VALUE, "debug_tap: no forward ran on this workspace");
   const size_t n = pl.N, h1 = pl.H1, h2 = pl.H2;

@@ -100,6 +100,16 @@ struct crnn_model {
                              // 3 = smem slice -> bulk store -> multicast (default, "ms"); 0 = v1 with a cluster barrier per step (persistent)
   int lstm_upc = 32;         // hidden units per gate tile: 32 = persistent cluster kernel (default), 64 = per-step launches
   Plan plan;
+  void* x3 = nullptr;        // state of the f32-class path (compute_dtype 2, forward_x3.cu)
+  // ---- data parallelism: BatchNorm statistics over the GLOBAL batch + per-bucket "gradient ready" notifications
+  int dp_rank = 0, dp_world = 1;
+  crnn_allreduce_fn xchg_cb = nullptr;   // fallback exchange of the [2][512] f64 BN sums (e.g. NCCL through the host language)
+  void* xchg_user = nullptr;
+  void** d_peers = nullptr;              // device array [world] of peer inbox pointers (own inbox at [rank]); nullptr = no peer memory
+  int* d_peer_err = nullptr;
+  unsigned long long peer_epoch = 0;
+  crnn_grad_ready_fn grad_cb = nullptr;
+  void* grad_user = nullptr;
   std::vector<cudaEvent_t> chunk_events;   // crnn_forward_host: one per H2D chunk + one "staging free" event
   // per-stage CUDA-event profiling (crnn_profile_*): events are recorded on the caller's stream between stages
   std::vector<cudaEvent_t> prof_events;   // [slots][kNumStages + 1]
@@ -114,6 +124,19 @@ struct crnn_model {
   }
   float* P(const std::string& n) const { return params + find(n)->offset; }
 };
+
+// f32-class ("3xbf16") forward path, forward_x3.cu
+size_t x3_workspace_size(int N, int W);
+int x3_forward(crnn_model* m, const float* data, const int* time_step_len, int N, int W, float* logits_out, void* workspace,
+               size_t workspace_bytes, cudaStream_t st);
+int x3_debug_tap(crnn_model* m, const char* name, float* dst, size_t dst_elems, void* workspace, cudaStream_t st);
+void x3_destroy(crnn_model* m);
+void x3_params_changed(crnn_model* m);
+
+// SyncBN exchange (peer.cu): sums of `in` [1024] f64 over all ranks -> `out` (may alias `in`); optionally fused with the BN finalize
+int dp_allreduce_1024(crnn_model* m, const double* in, double* out, cudaStream_t st);
+int dp_allreduce_bn_finalize(crnn_model* m, double* stats, double count_global, const float* gamma, const float* beta, float eps,
+                             float* bn /*scale, shift, mean, invstd: [4][512]*/, cudaStream_t st);
 
 size_t layout_plan(Plan& pl, int N, int W, uint8_t* base, bool train);
 int prepare_weights(crnn_model* m, cudaStream_t st);

@@ -24,13 +24,15 @@ def _ptr(t):
 class CrnnModel:
     """Owns the flat f32 parameter buffer (TF variable names/layouts) and the C model handle."""
 
-    def __init__(self, weight_decay=1e-5, bn_eps=1e-3, device=None):
+    def __init__(self, weight_decay=1e-5, bn_eps=1e-3, device=None, compute_dtype="bf16"):
         if not torch.cuda.is_available():
             raise CrnnError("lstm_ctc_ocr_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         torch.cuda.set_device(self.device)
-        cfg = CrnnConfig(32, NCLASSES, 512, bn_eps, weight_decay, 1)
+        # "bf16": bf16 operands / f32 accumulate (throughput path); "f32": split-bf16 operands, f32-class (BASELINE configs[1])
+        self.compute_dtype = {"bf16": 1, "f32": 2, 1: 1, 2: 2}[compute_dtype]
+        cfg = CrnnConfig(32, NCLASSES, 512, bn_eps, weight_decay, self.compute_dtype)
         h = _lib.c_void_p()
         check(self.lib.crnn_model_create(cfg, h))
         self.handle = h

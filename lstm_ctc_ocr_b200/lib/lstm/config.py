@@ -43,6 +43,7 @@ _DEFAULTS = {
         "DISPLAY": 10, "LOG_IMAGE_ITERS": 100, "NUM_EPOCHS": 2000,
         "NUM_HID": 512, "NUM_LAYERS": 2, "BATCH_SIZE": 64,
         "SNAPSHOT_ITERS": 5000, "SNAPSHOT_PREFIX": "lstm", "SNAPSHOT_INFIX": "",
+        "SYNC_BN": True,        # not in the reference (single device): data-parallel runs use GLOBAL-batch BN statistics
     },
     "VAL": {"TXT": "annotation_val.txt", "VAL_STEP": 1000, "NUM_EPOCHS": 1000, "BATCH_SIZE": 128, "PRINT_NUM": 5},
     "TEST": {},

@@ -39,13 +39,13 @@ class TrainOp(Fetch):
         self.lr, self.global_step, self.clip = lr, global_step, clip
 
     def step_fn(self, eng, logits, grad, d_data, d_tsl):
-        from ... import parallel
-        eng.backward(d_data, d_tsl, grad)
-        world = parallel.world_size()
-        if world > 1:
-            parallel.allreduce_sum_(eng.grads)
+        eng.backward(d_data, d_tsl, grad)             # data parallel: announces gradient buckets, reduced on a side stream meanwhile
         self.global_step.assign(self.global_step.eval() + 1)
-        eng.clip_adam_step(self.lr.eval(), self.global_step.eval(), clip=self.clip, grad_mul=1.0 / world, wd_mul=float(world))
+        dp = getattr(eng, "_dp", None)
+        if dp is not None:
+            dp.step(self.lr.eval(), self.global_step.eval(), clip=self.clip)       # waits for the buckets; clip + Adam on the SUM / world
+        else:
+            eng.clip_adam_step(self.lr.eval(), self.global_step.eval(), clip=self.clip)
         return None
 
 
@@ -123,9 +123,9 @@ class SolverWrapper(object):
             eng.load_params(synthetic.init_params(cfg.RNG_SEED))       # global_variables_initializer
             eng._initialised = True
         eng.set_training(True)
-        if parallel.world_size() > 1:
-            parallel.broadcast_(eng.params)
-            eng.lib.crnn_model_params_changed(eng.handle)
+        if parallel.world_size() > 1 and getattr(eng, "_dp", None) is None:
+            # parameter broadcast, global-batch BatchNorm over peer memory, overlapped gradient buckets (parallel.DataParallel)
+            eng._dp = parallel.DataParallel(eng, sync_bn=bool(cfg.TRAIN.get("SYNC_BN", True)))
         if not restore:
             return 1
         path = self._latest_checkpoint()
