@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--no-decode-eq", action="store_true", help="skip the 10k-line decode-equality statistic")
     ap.add_argument("--no-sync-bn", action="store_true", help="N>1: per-replica BatchNorm statistics (round-1 behaviour)")
     ap.add_argument("--no-peer-memory", action="store_true", help="N>1: exchange the BN sums through NCCL instead of peer memory")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: one all-reduce of the whole gradient buffer after the backward (round-1 behaviour)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -213,7 +214,7 @@ def main():
     dp = None
     if world > 1:
         from lstm_ctc_ocr_b200 import parallel
-        dp = parallel.DataParallel(model, sync_bn=not args.no_sync_bn, overlap=True, peer_memory=not args.no_peer_memory)
+        dp = parallel.DataParallel(model, sync_bn=not args.no_sync_bn, overlap=not args.no_overlap, peer_memory=not args.no_peer_memory)
 
     # ---- rotating set of distinct input batches > L2 (8 x 33.5 MB at c3), resident in HBM
     nrot = max(2, int(np.ceil(160e6 / (N * W * 32 * 4))))
@@ -301,12 +302,13 @@ def main():
     # (a) feeder
     nwork = int(os.environ.get("CRNN_BENCH_FEED_WORKERS", "8"))
     arg_fn = lambda k: dict(k=k, batch_size=N, render=False, seed=3 + 1000 * rank, rank=0, world=1, width=W, cache=4)
-    feeder = datagen.PrefetchFeeder(arg_fn, num_workers=nwork, depth=4, max_width=W, batch_size=N, keep=2)
+    feeder = datagen.PrefetchFeeder(arg_fn, num_workers=nwork, depth=4, max_width=W, batch_size=N, keep=2,
+                                    warm=[arg_fn(k) for k in range(4)])      # every producer draws its 4 cached batches at start-up
     try:
         def feed_step(i):
             view, lab, ll, tsl = next(feeder)
             return run_on(view, np.asarray(lab, np.int32), np.asarray(ll, np.int32), np.asarray(tsl, np.int32))
-        for i in range(max(8, 6 * nwork)):    # producers come up and fill their batch caches
+        for i in range(max(16, 8 * nwork)):   # producers come up (caches filled by the pool initializer) and touch every ring slot once
             feed_step(i)
         feed_path = sess.last_feed_path
         ms_feed, e2e_loss = timed(feed_step, Ke)
@@ -390,12 +392,12 @@ def main():
                   key=lambda n: stages[n]["ms"])
         ach = flops[dom] / (max(stages[dom]["ms"], 1e-9) * 1e-3) / 1e12
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
         if os.path.exists(tp) and args.workload == "c3":
             traffic = json.load(open(tp))["kernels"].get(dom, {}).get("traffic_bytes")
         roofline = {"kernel": f"gemm_kernel<{dom}>", "bound": "tensor", "achieved": round(ach, 1), "peak": peaks["bf16_sustained"],
                     "unit": "TFLOP/s", "frac": round(ach / peaks["bf16_sustained"], 3), "traffic": traffic,
-                    "traffic_note": "DRAM read+write bytes of one launch from the committed ncu --set full capture (profiles/r1_ncu_traffic.json); "
+                    "traffic_note": "DRAM read+write bytes of one launch from the committed ncu --set full capture (profiles/r2_ncu_traffic.json); "
                                     "algorithmic bytes of conv4_2 = 268 MB in + 4.7 MB weights + 268 MB out",
                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']}); kernel timed inside a long step",
                     "whole_step_tflops": round(N * GFLOP_PER_IMG(W) / ms_step, 1)}
@@ -435,7 +437,8 @@ def main():
             line["gpu_launches"] = K * (1 + 2 * 6 + 4 + 2 + 2 * T + 4)
         if ms_train is not None:
             line["train_step"] = {"ms_per_step": round(ms_train, 4), "images_per_s": round(world * N / (ms_train / 1e3), 1),
-                                  "what": "fwd + CTC loss/grad + backward + " + ("NCCL all-reduce(28.6 MB f32) in 7 buckets overlapped with the backward + global-batch BN fwd/bwd + " if world > 1 else "") +
+                                  "what": "fwd + CTC loss/grad + backward + " + (("NCCL all-reduce(28.6 MB f32) in 7 buckets overlapped with the backward + " if not args.no_overlap else "one NCCL all-reduce(28.6 MB f32) after the backward + ") +
+                                          ("global-batch BN fwd/bwd + " if not args.no_sync_bn else "") if world > 1 else "") +
                                           "global-norm clip + Adam (BASELINE configs[4] per-GPU shape)",
                                   "stages_ms": bwd_stage_ms}
         if world == 1 and not args.no_cpu_baseline:

@@ -221,7 +221,8 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   if (m->dp_world > 1) CRNN_TRY(dp_allreduce_1024(m, sums42, gsum42, st));
   CRNN_TRY(launch_bn_bwd_apply(pl.d_pre4b, pl.a4b_pre, pl.bn + 2048, m->P("conv4_2/conv4_2/gamma"), gsum42, sums42, P4g, P4,
                                512, pl.bn_bwd_coef, G("conv4_2/conv4_2/gamma"), G("conv4_2/conv4_2/beta"), st));
-  CRNN_TRY(launch_colsum_bf16(pl.d_pre4b, (long long)P4, 512, G("conv4_2/biases"), 0, 0, st));
+  // conv4_2/biases: a bias in front of a batch-statistics BatchNorm has an analytically ZERO gradient (the BN backward projects
+  // the column sums of d(pre-BN) out); it stays at the zero the buffer was cleared to instead of summing 134 MB of rounding noise
   BMARK();
   {
     gemm_tn::Params p = tn_conv(N, H2, 4, 512, 512, G("conv4_2/weights"), pl.wm4);
@@ -242,7 +243,7 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   if (m->dp_world > 1) CRNN_TRY(dp_allreduce_1024(m, sums41, gsum41, st));
   CRNN_TRY(launch_bn_bwd_apply(pl.d_pre4a, pl.a4a_pre, pl.bn, m->P("conv4_1/conv4_1/gamma"), gsum41, sums41, P4g, P4, 512,
                                pl.bn_bwd_coef, G("conv4_1/conv4_1/gamma"), G("conv4_1/conv4_1/beta"), st));
-  CRNN_TRY(launch_colsum_bf16(pl.d_pre4a, (long long)P4, 512, G("conv4_1/biases"), 0, 0, st));
+  // conv4_1/biases: analytically zero as well (see conv4_2)
   BMARK();
   {
     gemm_tn::Params p = tn_conv(N, H2, 4, 256, 512, G("conv4_1/weights"), pl.wm4);
@@ -260,7 +261,8 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   BMARK();
   // ------------------------------------------------------------------ conv3_2: 1x2 pool + ReLU backward
   CRNN_TRY(launch_unpool_relu_bwd(2, pl.d_a3p, pl.a3p, pl.am3, pl.d_pre32, (size_t)N * H2 * 4, H2, 4, 256, st));
-  CRNN_TRY(launch_colsum_bf16(pl.d_pre32, (long long)N * H2 * 8, 256, G("conv3_2/biases"), 0, 0, st));
+  // bias gradient = column sums of the POOLED gradient where the pooled output is positive (each value is routed to one position)
+  CRNN_TRY(launch_colsum_masked_bf16(pl.d_a3p, pl.a3p, (long long)N * H2 * 4, 256, G("conv3_2/biases"), st));
   BMARK();
   {
     gemm_tn::Params p = tn_conv(N, H2, 8, 256, 256, G("conv3_2/weights"), pl.wm3);
@@ -294,7 +296,7 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   BMARK();
   // ------------------------------------------------------------------ conv2: 2x2 pool + ReLU backward
   CRNN_TRY(launch_unpool_relu_bwd(4, pl.d_a2, pl.a2, pl.am2, pl.d_pre2, (size_t)N * H2 * 8, H2, 8, 128, st));
-  CRNN_TRY(launch_colsum_bf16(pl.d_pre2, (long long)N * H1 * 16, 128, G("conv2/biases"), 0, 0, st));
+  CRNN_TRY(launch_colsum_masked_bf16(pl.d_a2, pl.a2, (long long)N * H2 * 8, 128, G("conv2/biases"), st));
   BMARK();
   {
     gemm_tn::Params p = tn_conv(N, H1, 16, 64, 128, G("conv2/weights"), pl.wm2);

@@ -48,8 +48,13 @@ __global__ void __launch_bounds__(256) dlogits_rows_kernel(const float* __restri
 
 // ---- column sums of a bf16 matrix [R, C] into f32 out[map(c)] (+=). perm_upc > 0: LSTM gate permutation inverse
 // (two directions of 1024 permuted columns each -> TF column order, out has 2 x 1024 entries `dir_stride` apart).
-__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, long long R, int C,
-                                                          float* __restrict__ out, int perm_upc, long long dir_stride) {
+// `mask` != nullptr: only elements whose mask value is > 0 count (the ReLU mask of a POOLED activation: the bias gradient of
+// a conv followed by ReLU + max-pool is the column sum of the pooled gradient where the pooled output is positive -- every
+// pooled gradient value is routed to exactly one pre-pool position -- so the 4x (2x) larger un-pooled tensor need not be re-read).
+// `Cmod` > 0: the matrix is a [R, C] VIEW of a narrower [.., Cmod] tensor (Cmod divides C): column c accumulates into out[c % Cmod].
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ mask,
+                                                          long long R, int C, int Cmod, float* __restrict__ out, int perm_upc,
+                                                          long long dir_stride) {
   // block handles 256 columns (8 per thread x 32 lanes) x a strided set of rows (8 warps)
   const int cb = blockIdx.y * 256 + (threadIdx.x & 31) * 8;
   const bool okc = cb < C;
@@ -58,16 +63,23 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   for (int i = 0; i < 8; ++i) part[i] = 0.f;
   const long long stride = (long long)gridDim.x * 8;
   for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < R; r += 4 * stride) {
-    uint4 q[4];
+    uint4 q[4], mk[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long long rr = r + u * stride;
       q[u] = (okc && rr < R) ? __ldg(reinterpret_cast<const uint4*>(src + rr * C + cb)) : make_uint4(0u, 0u, 0u, 0u);
+      if (mask != nullptr) mk[u] = (okc && rr < R) ? __ldg(reinterpret_cast<const uint4*>(mask + rr * C + cb)) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       float v[8];
       unpack8(q[u], v);
+      if (mask != nullptr) {
+        float y[8];
+        unpack8(mk[u], y);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (y[i] > 0.f) ? v[i] : 0.f;
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) part[i] += v[i];
     }
@@ -91,7 +103,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
       const int g = (pc % (4 * perm_upc)) / perm_upc, u = (pc / (4 * perm_upc)) * perm_upc + pc % perm_upc;
       dst = out + dir * dir_stride + g * 256 + u;
     } else {
-      dst = out + c;
+      dst = out + (Cmod > 0 ? c % Cmod : c);
     }
     atomicAdd(dst, t);
   }
@@ -483,7 +495,17 @@ int launch_dlogits_rows(const float* dlogits, __nv_bfloat16* rows, float* dbias,
 }
 int launch_colsum_bf16(const __nv_bfloat16* src, long long R, int C, float* out, int perm_upc, long long dir_stride, cudaStream_t st) {
   dim3 grid(296, (C + 255) / 256);
-  colsum_bf16_kernel<<<grid, 256, 0, st>>>(src, R, C, out, perm_upc, dir_stride);
+  colsum_bf16_kernel<<<grid, 256, 0, st>>>(src, nullptr, R, C, 0, out, perm_upc, dir_stride);
+  LAUNCH_CHECK();
+}
+// out[c] += sum over rows of src[r][c] where mask[r][c] > 0.  Narrow tensors (C = 128) are read as a [R/2, 256] view so that
+// every lane of the 256-column block works.
+int launch_colsum_masked_bf16(const __nv_bfloat16* src, const __nv_bfloat16* mask, long long R, int C, float* out, cudaStream_t st) {
+  int Cv = C, Cmod = 0;
+  long long Rv = R;
+  if (C < 256 && 256 % C == 0 && R % (256 / C) == 0) { Cv = 256; Cmod = C; Rv = R / (256 / C); }
+  dim3 grid(296, (Cv + 255) / 256);
+  colsum_bf16_kernel<<<grid, 256, 0, st>>>(src, mask, Rv, Cv, Cmod, out, 0, 0);
   LAUNCH_CHECK();
 }
 int launch_bn_bwd_reduce(bool pool, const __nv_bfloat16* dout, const __nv_bfloat16* x_pre, __nv_bfloat16* dy, const float* bn,

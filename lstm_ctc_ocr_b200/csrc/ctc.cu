@@ -24,6 +24,7 @@
 //            sum of alpha*beta/y via shared-memory accumulators, write grad row (HBM write, coalesced)
 // No tensor cores: the dynamic program is a scan, not a contraction.
 #include "common.cuh"
+#include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -529,6 +530,219 @@ ctc_fast_kernel(const float* __restrict__ logits, float* __restrict__ grad, cons
   ptx::bulk_wait_read_all();
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// ctc_tma_kernel: same arithmetic as ctc_fast_kernel, different data movement.  The round-1 ncu source view of
+// ctc_fast_kernel put ~1/3 of its samples on the per-thread `cp.async.bulk` issue loops: UBLKCP takes its operands from
+// UNIFORM registers, so a warp whose 32 lanes each issue their own row copy executes them one lane at a time (ELECT / R2UR /
+// BRA.U.ANY).  Here ONE thread issues two tensor-map loads for the whole utterance -- logits [T,N,64] f32 viewed as
+// {32, 2, N, T} with a {32, 1, 1, T} box, i.e. the left and the right 128-byte half of all T rows -- into two 128B-swizzled
+// tiles (thread = frame then reads its own 128-byte rows without bank conflicts: chunk q of row t lives at q ^ (t & 7)), and
+// the gradient tile leaves through two tensor-map stores.
+// ---------------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FAST_THREADS, 8)
+ctc_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const __grid_constant__ CUtensorMap tm_grad, float* __restrict__ grad,
+               const int* __restrict__ flat_labels, const int* __restrict__ label_len, const int* __restrict__ input_len, int T, int N,
+               int blank, int max_label_len, float grad_scale, float* __restrict__ costs, int tile_rows) {
+  extern __shared__ uint8_t sm_raw[];
+  // tile_rows = T rounded up to 8: a half tile is tile_rows x 128 B, both halves 1024-byte aligned
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~uintptr_t(1023));
+  const int half_floats = tile_rows * 32;
+  float* s_x = reinterpret_cast<float*>(base);                 // [2][tile_rows][32] swizzled: logits -> p -> gradient rows
+  const int AS = fast_alpha_stride(max_label_len), ES = fast_label_stride(max_label_len);
+  float* s_alpha = s_x + 2 * half_floats;          // [T][AS]
+  float* s_beta = s_alpha + (size_t)T * AS;        // [T][AS]
+  float* s_el = s_beta + (size_t)T * AS;           // [T][ES]  log2 y_t(label k)
+  float* s_eb = s_el + (size_t)T * ES;             // [T]      log2 y_t(blank)
+  float* s_k = s_eb + T;                           // [T]      grad_scale / sum_c 2^(x-m)
+  __shared__ uint64_t s_bar;
+  __shared__ int s_ext[32];
+  __shared__ int s_off, s_repeats, s_bad;
+  auto F4 = [&](int t, int g) { return (g >> 3) * half_floats + t * 32 + (((g & 7) ^ (t & 7)) << 2); };
+  auto EL = [&](int t, int c) { return F4(t, c >> 2) + (c & 3); };
+
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int L = label_len[n];
+  const int Tn = max(0, min(input_len[n], T));
+  const int S = 2 * L + 1;
+
+  if (tid == 0) {
+    ptx::prefetch_tmap(&tm_logits);
+    ptx::mbar_init(&s_bar, 1);
+    ptx::fence_barrier_init();
+    s_repeats = 0;
+    s_bad = 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    ptx::mbar_arrive_expect_tx(&s_bar, (uint32_t)(2 * T * 128));
+    ptx::tma_load_4d(&tm_logits, &s_bar, s_x, 0, 0, n, 0);
+    ptx::tma_load_4d(&tm_logits, &s_bar, s_x + half_floats, 0, 1, n, 0);
+  }
+  // label bookkeeping while the tile is in flight: offset = sum(label_len[0..n)), extended labels, repeat count
+  if (warp == 0) {
+    int acc = 0;
+    for (int i = lane; i < n; i += 32) acc += __ldg(label_len + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_off = acc;
+  }
+  __syncthreads();
+  bool too_long = (L < 0) || (L > max_label_len) || (S > 32);
+  if (!too_long && tid < 32) {
+    int v = blank, rep = 0, bad = 0;
+    if (tid < S && (tid & 1)) {
+      v = flat_labels[s_off + (tid >> 1)];
+      if (v < 0 || v >= CTC_C || v == blank) { bad = 1; v = blank; }
+      if (tid >= 3 && v == flat_labels[s_off + (tid >> 1) - 1]) rep = 1;
+    }
+    s_ext[tid] = v;
+    rep = __popc(__ballot_sync(0xffffffffu, rep));
+    bad = __any_sync(0xffffffffu, bad);
+    if (tid == 0) { s_repeats = rep; s_bad = bad; }
+  }
+  __syncthreads();
+  too_long = too_long || (s_bad != 0);
+  ptx::mbar_wait(&s_bar, 0);                        // also required before an early exit: the copies target this CTA's smem
+
+  const bool feasible = !too_long && Tn > 0 && (L + s_repeats <= Tn);
+  if (!feasible) {
+    if (tid == 0) costs[n] = too_long ? __int_as_float(0x7fc00000) : 0.0f;
+    if (grad != nullptr)
+      for (int i = tid; i < T * (CTC_C / 4); i += FAST_THREADS)
+        reinterpret_cast<float4*>(grad + ((size_t)(i / (CTC_C / 4)) * N + n) * CTC_C)[i % (CTC_C / 4)] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+
+  // ---------------- phase 0: thread = frame ----------------
+  for (int t = tid; t < Tn; t += FAST_THREADS) {
+    float v[CTC_C];
+#pragma unroll
+    for (int g = 0; g < CTC_C / 4; ++g) {
+      const float4 x = *reinterpret_cast<const float4*>(s_x + F4(t, g));
+      v[4 * g] = x.x; v[4 * g + 1] = x.y; v[4 * g + 2] = x.z; v[4 * g + 3] = x.w;
+    }
+    float mx[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) mx[q] = fmaxf(fmaxf(v[4 * q], v[4 * q + 1]), fmaxf(v[4 * q + 2], v[4 * q + 3]));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) mx[q] = fmaxf(fmaxf(mx[4 * q], mx[4 * q + 1]), fmaxf(mx[4 * q + 2], mx[4 * q + 3]));
+    const float mm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * LOG2E;
+    float sum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < CTC_C; ++j) {
+      v[j] = ptx::ex2(fmaf(v[j], LOG2E, -mm));
+      sum[j & 3] += v[j];
+    }
+    const float tot = (sum[0] + sum[1]) + (sum[2] + sum[3]);
+    const float lse2 = mm + ptx::lg2(tot);
+    // emission scores come from the raw logits still in shared memory
+    s_eb[t] = fmaf(s_x[EL(t, blank)], LOG2E, -lse2);
+    for (int k = 0; k < L; ++k) s_el[(size_t)t * ES + k] = fmaf(s_x[EL(t, s_ext[2 * k + 1])], LOG2E, -lse2);
+    s_k[t] = __fdividef(grad_scale, tot);
+#pragma unroll
+    for (int g = 0; g < CTC_C / 4; ++g)
+      *reinterpret_cast<float4*>(s_x + F4(t, g)) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+  }
+  __syncthreads();
+
+  // ---------------- phase 1: alpha and reversed beta, one instruction stream (identical to ctc_fast_kernel) ----------------
+  {
+    const bool packed = (S <= 16);
+    if (warp < (packed ? 1 : 2)) {
+      const int W = packed ? 16 : 32;
+      const int half = packed ? (lane >> 4) : warp;            // 0 = alpha, 1 = beta (state order reversed)
+      const int j = packed ? (lane & 15) : lane;
+      const bool valid = j < S;
+      const int s = valid ? (half ? S - 1 - j : j) : 0;
+      bool ok2;
+      if (half == 0) ok2 = valid && (s >= 2) && (s_ext[s] != blank) && (s_ext[s] != s_ext[s - 2]);
+      else           ok2 = valid && (s + 2 < S) && (s_ext[s + 2] != blank) && (s_ext[s + 2] != s_ext[s]);
+      const float k1 = (valid && j >= 1) ? 0.f : NEG_INF;
+      const float k2 = ok2 ? 0.f : NEG_INF;
+      const int seg = lane & ~(W - 1);
+      const int src1 = seg | ((j - 1) & (W - 1)), src2 = seg | ((j - 2) & (W - 1));
+      const float k1n = __shfl_sync(0xffffffffu, k1, seg | ((j + 1) & (W - 1)));
+      const float k2n = __shfl_sync(0xffffffffu, k2, seg | ((j + 2) & (W - 1)));
+      float* buf = (half ? s_beta : s_alpha) + s;
+      const float* ep = (s & 1) ? (s_el + (s >> 1)) : s_eb;
+      const int estride = (s & 1) ? ES : 1;
+      const int dt = half ? -1 : 1;
+      int t = half ? Tn - 1 : 0;
+      float a = (valid && j < 2) ? ep[(size_t)t * estride] : NEG_INF;
+      float a1 = a + k1n, a2 = a + k2n;
+      if (valid) buf[(size_t)t * AS] = a;
+      float e_next = (Tn > 1) ? ep[(size_t)(t + dt) * estride] : 0.f;
+      for (int step = 1; step < Tn; ++step) {
+        t += dt;
+        const float e = e_next;
+        if (step + 1 < Tn) e_next = ep[(size_t)(t + dt) * estride];
+        const float c = fmaxf(a, -1e30f);
+        const float u1 = __shfl_sync(0xffffffffu, a1, src1);
+        const float u2 = __shfl_sync(0xffffffffu, a2, src2);
+        const float m = max3(c, u1, u2);
+        const float sum = ptx::ex2(a - m) + (ptx::ex2(u1 - m) + ptx::ex2(u2 - m));
+        const float lg = ptx::lg2(sum), me = m + e;
+        a = lg + me;
+        a1 = lg + (me + k1n);
+        a2 = lg + (me + k2n);
+        if (valid) buf[(size_t)t * AS] = a;
+      }
+    }
+  }
+  __syncthreads();
+
+  const float aS1 = s_alpha[(size_t)(Tn - 1) * AS + (S - 1)];
+  const float aS2 = (S >= 2) ? s_alpha[(size_t)(Tn - 1) * AS + (S - 2)] : NEG_INF;
+  const float ll2 = lse3(aS1, aS2, NEG_INF);
+  if (tid == 0) costs[n] = -ll2 * LN2;
+  if (grad == nullptr) return;
+
+  // ---------------- phase 2: thread = frame, gradient rows built in place, two tensor-map stores for the utterance ----------------
+  for (int t = tid; t < T; t += FAST_THREADS) {
+    if (t >= Tn || ll2 == NEG_INF) {
+#pragma unroll
+      for (int g = 0; g < CTC_C / 4; ++g) *reinterpret_cast<float4*>(s_x + F4(t, g)) = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      const float k = s_k[t];
+#pragma unroll
+      for (int g = 0; g < CTC_C / 4; ++g) {
+        float4 x = *reinterpret_cast<float4*>(s_x + F4(t, g));
+        x.x *= k; x.y *= k; x.z *= k; x.w *= k;
+        *reinterpret_cast<float4*>(s_x + F4(t, g)) = x;
+      }
+      const float* al = s_alpha + (size_t)t * AS;
+      const float* be = s_beta + (size_t)t * AS;
+      const float eb = s_eb[t] + ll2;
+      float wb = ptx::ex2(al[0] + be[0] - eb);                       // blank states: one accumulated update
+      for (int kk = 0; kk < L; ++kk) {
+        const float el = s_el[(size_t)t * ES + kk] + ll2;
+        const float w = ptx::ex2(al[2 * kk + 1] + be[2 * kk + 1] - el);   // alpha*beta / y / p(l|x)
+        wb += ptx::ex2(al[2 * kk + 2] + be[2 * kk + 2] - eb);
+        const int ci = EL(t, s_ext[2 * kk + 1]);
+        s_x[ci] = fmaf(-grad_scale, w, s_x[ci]);
+      }
+      const int bi = EL(t, blank);
+      s_x[bi] = fmaf(-grad_scale, wb, s_x[bi]);
+    }
+  }
+  ptx::fence_proxy_async_smem();                    // generic-proxy writes of the tile -> visible to the TMA store
+  __syncthreads();
+  if (tid == 0) {
+    ptx::tma_store_4d(&tm_grad, s_x, 0, 0, n, 0);
+    ptx::tma_store_4d(&tm_grad, s_x + half_floats, 0, 1, n, 0);
+    ptx::bulk_commit();
+    ptx::bulk_wait_read_all();
+  }
+}
+
+size_t ctc_tma_smem_bytes(int T, int max_label_len) {
+  const int tile_rows = (T + 7) / 8 * 8;
+  return 1024 + (size_t)2 * tile_rows * 128 +
+         sizeof(float) * (size_t)T * (2 * fast_alpha_stride(max_label_len) + fast_label_stride(max_label_len) + 2);
+}
+
 size_t ctc_fast_smem_bytes(int T, int max_label_len) {
   return sizeof(float) * (size_t)T * (FAST_XS + 2 * fast_alpha_stride(max_label_len) + fast_label_stride(max_label_len) + 2);
 }
@@ -593,6 +807,36 @@ bool ctc_force_generic() {
   return e != nullptr && strcmp(e, "generic") == 0;
 }
 
+// [T, N, 64] f32 viewed as {32, 2, N, T}: box = the left or right 128-byte half of all T rows of one utterance, 128B swizzle
+int make_tmap_ctc(CUtensorMap* m, const float* base, int T, int N) {
+  typedef CUresult (*PFN)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                          const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static PFN enc = nullptr;
+  if (!enc) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return crnn_fail(CRNN_CUDA_ERROR, "cuTensorMapEncodeTiled unavailable");
+    enc = reinterpret_cast<PFN>(p);
+  }
+  cuuint64_t dims[4] = {32, 2, (cuuint64_t)N, (cuuint64_t)T};
+  cuuint64_t strides[3] = {128, 256, (cuuint64_t)N * 256};
+  cuuint32_t box[4] = {32, 1, 1, (cuuint32_t)T};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return crnn_fail(CRNN_CUDA_ERROR, "cuTensorMapEncodeTiled(ctc) failed: %d", (int)r);
+  return CRNN_OK;
+}
+
+// which S <= 32 kernel: "tma" (default: tensor-map tile load/store), "fast" (round 1: per-thread bulk row copies), "generic"
+int ctc_kernel_choice() {
+  const char* e = getenv("CRNN_CTC_KERNEL");
+  if (e != nullptr && strcmp(e, "generic") == 0) return 2;
+  if (e != nullptr && strcmp(e, "fast") == 0) return 1;
+  return 0;
+}
+
 }  // namespace
 
 extern "C" int crnn_ctc_workspace_size(int T, int N, int C, int max_label_len, size_t* bytes) {
@@ -613,6 +857,21 @@ extern "C" int crnn_ctc_loss(const float* logits, float* grad, const int* flat_l
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int S = 2 * max_label_len + 1;
   const bool aligned = (reinterpret_cast<uintptr_t>(logits) % 16 == 0) && (grad == nullptr || reinterpret_cast<uintptr_t>(grad) % 16 == 0);
+  if (S <= 32 && aligned && T <= 256 && ctc_kernel_choice() == 0 && ctc_tma_smem_bytes(T, max_label_len) <= 200 * 1024) {
+    CUtensorMap tl, tg;
+    CRNN_TRY(make_tmap_ctc(&tl, logits, T, N));
+    CRNN_TRY(make_tmap_ctc(&tg, grad != nullptr ? grad : logits, T, N));
+    const size_t smem = ctc_tma_smem_bytes(T, max_label_len);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+      CUDA_TRY(cudaFuncSetAttribute(ctc_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_smem = smem;
+    }
+    ctc_tma_kernel<<<N, FAST_THREADS, smem, st>>>(tl, tg, grad, flat_labels, label_len, input_len, T, N, blank, max_label_len, grad_scale,
+                                                  costs, (T + 7) / 8 * 8);
+    CUDA_TRY(cudaGetLastError());
+    return CRNN_OK;
+  }
   if (S <= 32 && aligned && ctc_fast_smem_bytes(T, max_label_len) <= 200 * 1024 && !ctc_force_generic()) {
     const size_t smem = ctc_fast_smem_bytes(T, max_label_len);
     CUDA_TRY(cudaFuncSetAttribute(ctc_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

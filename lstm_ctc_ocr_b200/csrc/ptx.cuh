@@ -105,6 +105,13 @@ __device__ __forceinline__ void tma_load_4d(const void* tmap, uint64_t* bar, voi
       : "memory");
 }
 
+// smem tile -> global through a tensor map (bulk async group; complete with bulk_commit / bulk_wait_read_all)
+__device__ __forceinline__ void tma_store_4d(const void* tmap, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {   // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),

@@ -255,6 +255,17 @@ def _worker(shm_name, kwargs):
     return _fill(_attach(shm_name).buf, kwargs)
 
 
+def _warm_synth_cache(kwargs_list):
+    """Pool initializer: every producer process generates its cached synthetic batches up front (a cache miss inside a timed
+    region would stall the consumer for the ~0.4 s it takes to draw 8.4 M random pixels)."""
+    for kw in kwargs_list:
+        kw = dict(kw)
+        cache = kw.pop("cache", 0)
+        key = (kw["batch_size"], kw.get("width"), kw.get("seed"), kw.get("rank"), kw["k"] % max(cache, 1))
+        if cache and key not in _SYNTH_CACHE:
+            _SYNTH_CACHE[key] = make_batch(**dict(kw, k=kw["k"] % cache))
+
+
 class PrefetchFeeder(object):
     """Prefetching feeder in front of the solver: a ring of PAGE-LOCKED shared-memory slots filled by producer processes.
 
@@ -266,7 +277,7 @@ class PrefetchFeeder(object):
     crnn_forward_host).  The ring has ``depth + keep`` slots: the views of the last ``keep`` delivered batches are never
     rewritten, so the consumer may still be DMA-ing from batch j while batches j+1 .. j+depth are produced."""
 
-    def __init__(self, arg_fn, num_workers=4, depth=3, max_width=256, batch_size=None, pinned=True, keep=3):
+    def __init__(self, arg_fn, num_workers=4, depth=3, max_width=256, batch_size=None, pinned=True, keep=3, warm=None):
         from multiprocessing import shared_memory
         self.arg_fn, self.depth, self.keep = arg_fn, max(1, int(depth)), max(1, int(keep))
         self.num_workers = int(num_workers)
@@ -296,7 +307,9 @@ class PrefetchFeeder(object):
         self._next_yield = 0
         if self.num_workers > 0:
             import multiprocessing as mp
-            self._pool = mp.get_context("spawn").Pool(self.num_workers)
+            # `warm`: kwargs of the batches every producer should pre-generate (synthetic `cache` streams)
+            self._pool = (mp.get_context("spawn").Pool(self.num_workers, initializer=_warm_synth_cache, initargs=(list(warm),))
+                          if warm else mp.get_context("spawn").Pool(self.num_workers))
 
     def _slot(self, k):
         return self._shm[k % len(self._shm)]

@@ -46,16 +46,17 @@ def _ctc_case(T, N, lens, ilens, seed, scale=2.0):
     return x, lab, ll, il, O.ctc_loss_np(x, lab, ll, il)
 
 
-@pytest.mark.parametrize("kernel", ["fast", "generic"])
+@pytest.mark.parametrize("kernel", ["tma", "fast", "generic"])
 @pytest.mark.parametrize("case", ["ragged", "edge", "two_warp", "many_frames", "long_ks2", "long_ks4"])
 def test_ctc_loss_and_grad_vs_oracle(case, kernel, monkeypatch):
-    """ctc_fast_kernel (S <= 32) and the generic ctc_loss_kernel<KS> against the fp64 oracle; CRNN_CTC_KERNEL=generic
-    routes the S <= 32 cases through the generic kernel as well."""
+    """ctc_tma_kernel (S <= 32, default: one tensor-map tile load/store per utterance), ctc_fast_kernel (S <= 32, round 1:
+    per-thread bulk row copies) and the generic ctc_loss_kernel<KS> against the fp64 oracle; CRNN_CTC_KERNEL=fast|generic routes
+    the S <= 32 cases through the other two kernels."""
     from lstm_ctc_ocr_b200 import engine
-    if kernel == "generic":
+    if kernel != "tma":
         if case.startswith("long_ks"):
             pytest.skip("S > 32 always runs the generic kernel")
-        monkeypatch.setenv("CRNN_CTC_KERNEL", "generic")
+        monkeypatch.setenv("CRNN_CTC_KERNEL", kernel)
     if case == "ragged":
         rng = np.random.default_rng(0)
         N, T = 37, 24

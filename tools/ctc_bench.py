@@ -1,5 +1,5 @@
 """CTC loss+gradient kernel alone at the C3 shape (T=63, N=1024, C=64): CUDA-event time per launch for the fast (S <= 32)
-and the generic kernel, rotating over input sets larger than L2.  Usage: python tools/ctc_bench.py [N] [T]"""
+(tma = tensor-map tile load/store, fast = per-thread bulk row copies) and the generic kernel, rotating over input sets larger than L2.  Usage: python tools/ctc_bench.py [N] [T]"""
 import json
 import os
 import sys
@@ -12,10 +12,10 @@ from lstm_ctc_ocr_b200 import engine, synthetic  # noqa: E402
 
 
 def run(N, T, max_len, kernel, reps=200, sets=10):
-    if kernel == "generic":
-        os.environ["CRNN_CTC_KERNEL"] = "generic"
+    if kernel in ("generic", "fast"):
+        os.environ["CRNN_CTC_KERNEL"] = kernel
     else:
-        os.environ.pop("CRNN_CTC_KERNEL", None)
+        os.environ.pop("CRNN_CTC_KERNEL", None)         # "tma": the default S <= 32 kernel
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(3)
     ll = rng.integers(min(4, max_len), max_len + 1, size=N).astype(np.int32)
@@ -45,5 +45,5 @@ if __name__ == "__main__":
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
     T = int(sys.argv[2]) if len(sys.argv) > 2 else 63
     for max_len in (6, 15):
-        for k in ("fast", "generic"):
+        for k in ("tma", "fast", "generic"):
             print(json.dumps(run(N, T, max_len, k)))
