@@ -326,6 +326,85 @@ __global__ void __launch_bounds__(CTC_THREADS, 8) ctc_loss_kernel(const float* _
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Phase 1 of the S <= 32 kernels, second generation ("me" = mantissa/exponent).  The round-2 ncu source view put ~47 % of the
+// kernel on the 62-step alpha/beta chain: every step of the log2-space recursion is SHFL -> FMNMX3 -> FADD -> MUFU.EX2 -> FADD ->
+// FADD -> MUFU.LG2 -> FADD, ~300 cycles with one or two warps per scheduler.  Here a state is carried as a PAIR
+// (m in [1,2) or 0, integer exponent e), value m * 2^e: the sum of the three predecessors is three exact power-of-two scalings
+// (integer shifts into the exponent field) and two FADDs, the emission is a multiplication by (ym, ye) -- split off the log2
+// emission ONE STEP AHEAD, so its EX2 is off the chain --, renormalisation is integer arithmetic on the exponent field.  No
+// transcendental on the dependency chain, and -- unlike a linear-space recursion with a shared per-frame scale -- no loss of
+// range: the exponent is a 32-bit integer, so a state 2^-5000 below its neighbour is still carried (the log-space kernels' and
+// warp-ctc's behaviour on confidently-wrong frames).  What is stored per (t, s) is still log2(alpha) = lg2(m) + e (the LG2 is
+// off the chain), so phases 0 and 2 are unchanged.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int ME_EMIN = -(1 << 28);
+
+__device__ __forceinline__ void me_split(float z, float& ym, int& ye) {
+  if (!(z > -100000.f)) { ym = 0.f; ye = 0; return; }          // log2 y below -1e5 (or NaN/-inf): probability zero
+  const float fl = floorf(z);
+  ym = ptx::ex2(z - fl);
+  ye = (int)fl;
+}
+__device__ __forceinline__ float me_pow2(int d) {               // 2^d for d <= 0; 0 beyond f32 resolution of the larger addend
+  return d < -64 ? 0.f : __int_as_float((d + 127) << 23);
+}
+
+__device__ __forceinline__ void ctc_recursion_me(float* s_alpha, float* s_beta, const float* s_el, const float* s_eb, const int* s_ext,
+                                                 int AS, int ES, int S, int Tn, int blank, int warp, int lane) {
+  const bool packed = (S <= 16);
+  if (warp >= (packed ? 1 : 2)) return;
+  const int W = packed ? 16 : 32;
+  const int half = packed ? (lane >> 4) : warp;            // 0 = alpha, 1 = beta (state order reversed)
+  const int j = packed ? (lane & 15) : lane;
+  const bool valid = j < S;
+  const int s = valid ? (half ? S - 1 - j : j) : 0;
+  bool ok2;
+  if (half == 0) ok2 = valid && (s >= 2) && (s_ext[s] != blank) && (s_ext[s] != s_ext[s - 2]);
+  else           ok2 = valid && (s + 2 < S) && (s_ext[s + 2] != blank) && (s_ext[s + 2] != s_ext[s]);
+  const bool ok1 = valid && j >= 1;
+  const int seg = lane & ~(W - 1);
+  const int src1 = seg | ((j - 1) & (W - 1)), src2 = seg | ((j - 2) & (W - 1));
+  float* buf = (half ? s_beta : s_alpha) + s;
+  const float* ep = (s & 1) ? (s_el + (s >> 1)) : s_eb;
+  const int estride = (s & 1) ? ES : 1;
+  const int dt = half ? -1 : 1;
+  int t = half ? Tn - 1 : 0;
+  float m, ymn = 0.f;
+  int e, yen = 0;
+  {
+    float ym; int ye;
+    me_split(ep[(size_t)t * estride], ym, ye);
+    const bool live = valid && j < 2 && ym > 0.f;
+    m = live ? ym : 0.f;
+    e = live ? ye : ME_EMIN;
+    if (valid) buf[(size_t)t * AS] = live ? ptx::lg2(m) + (float)e : NEG_INF;
+  }
+  if (Tn > 1) me_split(ep[(size_t)(t + dt) * estride], ymn, yen);
+  for (int step = 1; step < Tn; ++step) {
+    t += dt;
+    const float ym = ymn;
+    const int ye = yen;
+    if (step + 1 < Tn) me_split(ep[(size_t)(t + dt) * estride], ymn, yen);      // next frame's emission: off the chain
+    float m1 = __shfl_sync(0xffffffffu, m, src1);
+    int e1 = __shfl_sync(0xffffffffu, e, src1);
+    float m2 = __shfl_sync(0xffffffffu, m, src2);
+    int e2 = __shfl_sync(0xffffffffu, e, src2);
+    if (!ok1) { m1 = 0.f; e1 = ME_EMIN; }
+    if (!ok2) { m2 = 0.f; e2 = ME_EMIN; }
+    const int emax = max(e, max(e1, e2));
+    const float sum = m * me_pow2(e - emax) + (m1 * me_pow2(e1 - emax) + m2 * me_pow2(e2 - emax));
+    const float pr = sum * ym;                                        // [1, 12) or 0
+    const uint32_t pb = __float_as_uint(pr);
+    const int k = (int)(pb >> 23) - 127;
+    const bool live = valid && pr > 0.f;
+    m = live ? __uint_as_float(pb - ((uint32_t)k << 23)) : 0.f;       // exponent field back to 127: m in [1, 2)
+    e = live ? emax + ye + k : ME_EMIN;
+    if (valid) buf[(size_t)t * AS] = live ? ptx::lg2(m) + (float)e : NEG_INF;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------------
 // Fast path: S <= 32.  Shared-memory rows use a stride of 68 floats (272 B: 16-B aligned for the bulk copies and
 // conflict-free when every thread of a quarter-warp reads a float4 of its own row); alpha/beta/emission tables use odd
@@ -339,7 +418,7 @@ __host__ __device__ inline int fast_label_stride(int max_label_len) { return max
 __global__ void __launch_bounds__(FAST_THREADS, 8)
 ctc_fast_kernel(const float* __restrict__ logits, float* __restrict__ grad, const int* __restrict__ flat_labels,
                 const int* __restrict__ label_len, const int* __restrict__ input_len, int T, int N, int blank,
-                int max_label_len, float grad_scale, float* __restrict__ costs) {
+                int max_label_len, float grad_scale, float* __restrict__ costs, int recur) {
   extern __shared__ __align__(16) float sm[];
   const int AS = fast_alpha_stride(max_label_len), ES = fast_label_stride(max_label_len);
   float* s_x = sm;                                 // [T][68]  logits -> p -> gradient row
@@ -441,7 +520,9 @@ ctc_fast_kernel(const float* __restrict__ logits, float* __restrict__ grad, cons
   __syncthreads();
 
   // ---------------- phase 1: alpha and reversed beta, one instruction stream ----------------
-  {
+  if (recur) {
+    ctc_recursion_me(s_alpha, s_beta, s_el, s_eb, s_ext, AS, ES, S, Tn, blank, warp, lane);
+  } else {
     const bool packed = (S <= 16);
     if (warp < (packed ? 1 : 2)) {
       const int W = packed ? 16 : 32;
@@ -543,7 +624,7 @@ ctc_fast_kernel(const float* __restrict__ logits, float* __restrict__ grad, cons
 __global__ void __launch_bounds__(FAST_THREADS, 8)
 ctc_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const __grid_constant__ CUtensorMap tm_grad, float* __restrict__ grad,
                const int* __restrict__ flat_labels, const int* __restrict__ label_len, const int* __restrict__ input_len, int T, int N,
-               int blank, int max_label_len, float grad_scale, float* __restrict__ costs, int tile_rows) {
+               int blank, int max_label_len, float grad_scale, float* __restrict__ costs, int tile_rows, int recur) {
   extern __shared__ uint8_t sm_raw[];
   // tile_rows = T rounded up to 8: a half tile is tile_rows x 128 B, both halves 1024-byte aligned
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~uintptr_t(1023));
@@ -648,7 +729,9 @@ ctc_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const __grid_const
   __syncthreads();
 
   // ---------------- phase 1: alpha and reversed beta, one instruction stream (identical to ctc_fast_kernel) ----------------
-  {
+  if (recur) {
+    ctc_recursion_me(s_alpha, s_beta, s_el, s_eb, s_ext, AS, ES, S, Tn, blank, warp, lane);
+  } else {
     const bool packed = (S <= 16);
     if (warp < (packed ? 1 : 2)) {
       const int W = packed ? 16 : 32;
@@ -829,12 +912,18 @@ int make_tmap_ctc(CUtensorMap* m, const float* base, int T, int N) {
   return CRNN_OK;
 }
 
-// which S <= 32 kernel: "tma" (default: tensor-map tile load/store), "fast" (round 1: per-thread bulk row copies), "generic"
+// which S <= 32 kernel: "fast" (default: per-thread bulk row copies), "tma" (one tensor-map tile load/store per utterance: measured
+// 2 us SLOWER at C3, kept selectable and tested), "generic"
 int ctc_kernel_choice() {
   const char* e = getenv("CRNN_CTC_KERNEL");
   if (e != nullptr && strcmp(e, "generic") == 0) return 2;
-  if (e != nullptr && strcmp(e, "fast") == 0) return 1;
-  return 0;
+  if (e != nullptr && strcmp(e, "tma") == 0) return 0;
+  return 1;
+}
+// alpha/beta recursion of the S <= 32 kernels: "me" (default, mantissa/exponent pairs: no transcendental on the chain) or "log"
+int ctc_recur_choice() {
+  const char* e = getenv("CRNN_CTC_RECUR");
+  return (e != nullptr && strcmp(e, "log") == 0) ? 0 : 1;
 }
 
 }  // namespace
@@ -868,7 +957,7 @@ extern "C" int crnn_ctc_loss(const float* logits, float* grad, const int* flat_l
       attr_smem = smem;
     }
     ctc_tma_kernel<<<N, FAST_THREADS, smem, st>>>(tl, tg, grad, flat_labels, label_len, input_len, T, N, blank, max_label_len, grad_scale,
-                                                  costs, (T + 7) / 8 * 8);
+                                                  costs, (T + 7) / 8 * 8, ctc_recur_choice());
     CUDA_TRY(cudaGetLastError());
     return CRNN_OK;
   }
@@ -876,7 +965,7 @@ extern "C" int crnn_ctc_loss(const float* logits, float* grad, const int* flat_l
     const size_t smem = ctc_fast_smem_bytes(T, max_label_len);
     CUDA_TRY(cudaFuncSetAttribute(ctc_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ctc_fast_kernel<<<N, FAST_THREADS, smem, st>>>(logits, grad, flat_labels, label_len, input_len, T, N, blank, max_label_len,
-                                                   grad_scale, costs);
+                                                   grad_scale, costs, ctc_recur_choice());
     CUDA_TRY(cudaGetLastError());
     return CRNN_OK;
   }

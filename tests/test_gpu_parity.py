@@ -46,17 +46,17 @@ def _ctc_case(T, N, lens, ilens, seed, scale=2.0):
     return x, lab, ll, il, O.ctc_loss_np(x, lab, ll, il)
 
 
-@pytest.mark.parametrize("kernel", ["tma", "fast", "generic"])
+@pytest.mark.parametrize("kernel", ["fast", "fast-log", "tma", "tma-log", "generic"])
 @pytest.mark.parametrize("case", ["ragged", "edge", "two_warp", "many_frames", "long_ks2", "long_ks4"])
 def test_ctc_loss_and_grad_vs_oracle(case, kernel, monkeypatch):
-    """ctc_tma_kernel (S <= 32, default: one tensor-map tile load/store per utterance), ctc_fast_kernel (S <= 32, round 1:
-    per-thread bulk row copies) and the generic ctc_loss_kernel<KS> against the fp64 oracle; CRNN_CTC_KERNEL=fast|generic routes
-    the S <= 32 cases through the other two kernels."""
+    """ctc_fast_kernel (S <= 32, default: per-thread bulk row copies), ctc_tma_kernel (S <= 32: one tensor-map tile load/store per
+    utterance) -- each with the mantissa/exponent recursion (default) and the log2-space recursion (`-log`) -- and the generic
+    ctc_loss_kernel<KS> against the fp64 oracle; CRNN_CTC_KERNEL / CRNN_CTC_RECUR select them."""
     from lstm_ctc_ocr_b200 import engine
-    if kernel != "tma":
-        if case.startswith("long_ks"):
-            pytest.skip("S > 32 always runs the generic kernel")
-        monkeypatch.setenv("CRNN_CTC_KERNEL", kernel)
+    if kernel != "fast" and case.startswith("long_ks"):
+        pytest.skip("S > 32 always runs the generic kernel")
+    monkeypatch.setenv("CRNN_CTC_KERNEL", kernel.split("-")[0])
+    monkeypatch.setenv("CRNN_CTC_RECUR", "log" if kernel.endswith("-log") else "me")
     if case == "ragged":
         rng = np.random.default_rng(0)
         N, T = 37, 24
@@ -103,13 +103,16 @@ def test_ctc_fast_kernel_extreme_logits_match_generic(monkeypatch):
     lens = rng.integers(0, 16, size=N); ilens = rng.integers(32, T + 1, size=N)
     x, lab, ll, il, (co, go) = _ctc_case(T, N, lens, ilens, seed=9, scale=30.0)
     t = lambda a: torch.tensor(a, device=DEV)
-    c, g = engine.ctc_loss(t(x), t(lab), t(ll), t(il), want_grad=True)
     monkeypatch.setenv("CRNN_CTC_KERNEL", "generic")
     cg, gg = engine.ctc_loss(t(x), t(lab), t(ll), t(il), want_grad=True)
-    assert torch.isfinite(c).all() and torch.isfinite(g).all()
-    assert np.allclose(c.cpu().numpy(), co, rtol=2e-4, atol=1e-3)
-    assert np.allclose(c.cpu().numpy(), cg.cpu().numpy(), rtol=2e-4, atol=1e-3)
-    assert np.abs(g.cpu().numpy() - go).max() < 4e-3 and float((g - gg).abs().max()) < 4e-3
+    for kern, recur in (("fast", "me"), ("fast", "log"), ("tma", "me")):
+        monkeypatch.setenv("CRNN_CTC_KERNEL", kern)
+        monkeypatch.setenv("CRNN_CTC_RECUR", recur)
+        c, g = engine.ctc_loss(t(x), t(lab), t(ll), t(il), want_grad=True)
+        assert torch.isfinite(c).all() and torch.isfinite(g).all(), (kern, recur)
+        assert np.allclose(c.cpu().numpy(), co, rtol=2e-4, atol=1e-3), (kern, recur)
+        assert np.allclose(c.cpu().numpy(), cg.cpu().numpy(), rtol=2e-4, atol=1e-3), (kern, recur)
+        assert np.abs(g.cpu().numpy() - go).max() < 4e-3 and float((g - gg).abs().max()) < 4e-3, (kern, recur)
 
 
 def test_ctc_grad_scale_and_rowsum_property_full_size():

@@ -4,6 +4,10 @@ N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/c3_topo.txt 2>&1
 if [ "$N" = "2" ]; then
+  timeout 400 python -m pytest tests/test_gpu_parity.py tests/test_gpu_shapes.py -m gpu -q --timeout=300 -k "ctc or gradients" > gpurun_out/c3_pytest_ctc.log 2>&1
+  echo "pytest rc=$?" >> gpurun_out/c3_pytest_ctc.log
+  tail -4 gpurun_out/c3_pytest_ctc.log
+  timeout 100 python tools/ctc_bench.py > gpurun_out/c3_ctc.log 2>&1; cat gpurun_out/c3_ctc.log
   timeout 600 python -m pytest tests/test_gpu_dp.py -m gpu -q --timeout=500 > gpurun_out/c3_pytest_dp.log 2>&1
   echo "pytest rc=$?" >> gpurun_out/c3_pytest_dp.log
   tail -5 gpurun_out/c3_pytest_dp.log
