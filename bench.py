@@ -174,6 +174,8 @@ def main():
     ap.add_argument("--no-sync-bn", action="store_true", help="N>1: per-replica BatchNorm statistics (round-1 behaviour)")
     ap.add_argument("--no-peer-memory", action="store_true", help="N>1: exchange the BN sums through NCCL instead of peer memory")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one all-reduce of the whole gradient buffer after the backward (round-1 behaviour)")
+    ap.add_argument("--bucket-mb", type=float, default=8.0, help="N>1: merge announced gradient ranges until this many MB are ready")
+    ap.add_argument("--sm-reserve", type=int, default=8, help="N>1 with overlap: SMs the persistent backward kernels leave to the collectives")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -197,6 +199,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
     if world > 1:
+        if not args.no_overlap:
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", str(max(args.sm_reserve, 1)))     # the overlapped collectives fit the reserved SMs
         dist.init_process_group("nccl", device_id=dev)
     N, W, desc = WORKLOADS[args.workload]
     T = W // 4 - 1
@@ -214,7 +218,8 @@ def main():
     dp = None
     if world > 1:
         from lstm_ctc_ocr_b200 import parallel
-        dp = parallel.DataParallel(model, sync_bn=not args.no_sync_bn, overlap=not args.no_overlap, peer_memory=not args.no_peer_memory)
+        dp = parallel.DataParallel(model, sync_bn=not args.no_sync_bn, overlap=not args.no_overlap, peer_memory=not args.no_peer_memory,
+                                   min_bucket_bytes=int(args.bucket_mb * (1 << 20)), sm_reserve=args.sm_reserve)
 
     # ---- rotating set of distinct input batches > L2 (8 x 33.5 MB at c3), resident in HBM
     nrot = max(2, int(np.ceil(160e6 / (N * W * 32 * 4))))
@@ -437,7 +442,7 @@ def main():
             line["gpu_launches"] = K * (1 + 2 * 6 + 4 + 2 + 2 * T + 4)
         if ms_train is not None:
             line["train_step"] = {"ms_per_step": round(ms_train, 4), "images_per_s": round(world * N / (ms_train / 1e3), 1),
-                                  "what": "fwd + CTC loss/grad + backward + " + (("NCCL all-reduce(28.6 MB f32) in 7 buckets overlapped with the backward + " if not args.no_overlap else "one NCCL all-reduce(28.6 MB f32) after the backward + ") +
+                                  "what": "fwd + CTC loss/grad + backward + " + ((f"NCCL all-reduce(28.6 MB f32) in buckets >= {args.bucket_mb:g} MB overlapped with the backward ({args.sm_reserve} SMs reserved) + " if not args.no_overlap else "one NCCL all-reduce(28.6 MB f32) after the backward + ") +
                                           ("global-batch BN fwd/bwd + " if not args.no_sync_bn else "") if world > 1 else "") +
                                           "global-norm clip + Adam (BASELINE configs[4] per-GPU shape)",
                                   "stages_ms": bwd_stage_ms}

@@ -172,6 +172,9 @@ typedef int  (*crnn_allreduce_fn)(void* user, void* dev_ptr, size_t count, int i
 typedef void (*crnn_grad_ready_fn)(void* user, int64_t offset, int64_t count, crnn_stream_t stream);
 int     crnn_model_set_data_parallel(crnn_model* m, int rank, int world, crnn_allreduce_fn allreduce, void* user);
 int     crnn_model_set_grad_ready_callback(crnn_model* m, crnn_grad_ready_fn fn, void* user);
+/* Leave `sms` SMs free in the persistent kernels of crnn_backward (their grids are num_sms - sms CTAs), so that the collective
+ * kernels the caller launches from the grad-ready callback find free SMs instead of delaying the tail of a full-GPU grid. */
+int     crnn_model_set_backward_sm_reserve(crnn_model* m, int sms);
 /* Peer-memory inboxes (cudaMalloc + CUDA IPC): create one per rank, exchange the 64-byte handles through the host language
  * (e.g. torch.distributed.all_gather_object), open the peers', hand all `world` pointers (own at [rank]) to the model. */
 size_t  crnn_peer_inbox_bytes(void);

@@ -53,6 +53,7 @@ SIGNATURES = {
     "crnn_last_grad_norm": (c_int, [c_void_p, c_float, ctypes.POINTER(c_float), c_void_p]),
     "crnn_model_set_data_parallel": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "crnn_model_set_grad_ready_callback": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "crnn_model_set_backward_sm_reserve": (c_int, [c_void_p, c_int]),
     "crnn_peer_inbox_bytes": (c_size_t, []),
     "crnn_peer_inbox_create": (c_int, [ctypes.POINTER(c_void_p), c_void_p]),
     "crnn_peer_inbox_open": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),

@@ -98,7 +98,7 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   if (workspace_bytes < need) return crnn_fail(CRNN_WORKSPACE_TOO_SMALL, "backward: workspace %zu < %zu", workspace_bytes, need);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (m->dirty_bwd) CRNN_TRY(prepare_weights_bwd(m, st));
-  const int H1 = pl.H1, H2 = pl.H2, T = pl.T, sms = m->num_sms;
+  const int H1 = pl.H1, H2 = pl.H2, T = pl.T, sms = m->num_sms - m->bwd_sm_reserve;
   const long long R = (long long)N * H2;
   auto G = [&](const std::string& n) { return m->grads + m->find(n)->offset; };
   auto notify = [&](const char* first, const char* next) {     // gradients of tensors [first, next) of the table are final

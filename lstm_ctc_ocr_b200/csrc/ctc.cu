@@ -328,9 +328,9 @@ __global__ void __launch_bounds__(CTC_THREADS, 8) ctc_loss_kernel(const float* _
 
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// Phase 1 of the S <= 32 kernels, second generation ("me" = mantissa/exponent).  The round-2 ncu source view put ~47 % of the
-// kernel on the 62-step alpha/beta chain: every step of the log2-space recursion is SHFL -> FMNMX3 -> FADD -> MUFU.EX2 -> FADD ->
-// FADD -> MUFU.LG2 -> FADD, ~300 cycles with one or two warps per scheduler.  Here a state is carried as a PAIR
+// Phase 1 of the S <= 32 kernels, alternative ("me" = mantissa/exponent, CRNN_CTC_RECUR=me).  The round-2 ncu source view put ~47 %
+// of the kernel on the 62-step alpha/beta chain: every step of the log2-space recursion is SHFL -> FMNMX3 -> FADD -> MUFU.EX2 -> FADD
+// -> FADD -> MUFU.LG2 -> FADD.  Here a state is carried as a PAIR
 // (m in [1,2) or 0, integer exponent e), value m * 2^e: the sum of the three predecessors is three exact power-of-two scalings
 // (integer shifts into the exponent field) and two FADDs, the emission is a multiplication by (ym, ye) -- split off the log2
 // emission ONE STEP AHEAD, so its EX2 is off the chain --, renormalisation is integer arithmetic on the exponent field.  No
@@ -338,6 +338,9 @@ __global__ void __launch_bounds__(CTC_THREADS, 8) ctc_loss_kernel(const float* _
 // range: the exponent is a 32-bit integer, so a state 2^-5000 below its neighbour is still carried (the log-space kernels' and
 // warp-ctc's behaviour on confidently-wrong frames).  What is stored per (t, s) is still log2(alpha) = lg2(m) + e (the LG2 is
 // off the chain), so phases 0 and 2 are unchanged.
+// MEASURED (B200, T=63, N=1024): 24.7 us vs 18.5 us for the log2-space chain -- the pair arithmetic needs ~3x the dependent
+// integer/select instructions per step, and with one or two warps per scheduler the chain is bound by instruction latency, not by
+// the MUFU pipe.  Kept as the high-accuracy option (costs agree with the fp64 oracle to ~1e-8 relative instead of ~1e-5).
 // ---------------------------------------------------------------------------------------------------------------------------
 constexpr int ME_EMIN = -(1 << 28);
 
@@ -920,10 +923,12 @@ int ctc_kernel_choice() {
   if (e != nullptr && strcmp(e, "tma") == 0) return 0;
   return 1;
 }
-// alpha/beta recursion of the S <= 32 kernels: "me" (default, mantissa/exponent pairs: no transcendental on the chain) or "log"
+// alpha/beta recursion of the S <= 32 kernels: "log" (default: log2-space, 3 EX2 + 1 LG2 per step) or "me" (mantissa/exponent pairs:
+// no transcendental on the chain and ~1e-8 relative accuracy instead of ~1e-5, but MORE dependent integer/select instructions per
+// step -- measured 24.7 us vs 18.5 us at C3, so it is the accuracy option, not the speed option)
 int ctc_recur_choice() {
   const char* e = getenv("CRNN_CTC_RECUR");
-  return (e != nullptr && strcmp(e, "log") == 0) ? 0 : 1;
+  return (e != nullptr && strcmp(e, "me") == 0) ? 1 : 0;
 }
 
 }  // namespace

@@ -108,6 +108,7 @@ struct crnn_model {
   void** d_peers = nullptr;              // device array [world] of peer inbox pointers (own inbox at [rank]); nullptr = no peer memory
   int* d_peer_err = nullptr;
   unsigned long long peer_epoch = 0;
+  int bwd_sm_reserve = 0;                // SMs left free by the persistent backward kernels (for overlapped collectives)
   crnn_grad_ready_fn grad_cb = nullptr;
   void* grad_user = nullptr;
   std::vector<cudaEvent_t> chunk_events;   // crnn_forward_host: one per H2D chunk + one "staging free" event

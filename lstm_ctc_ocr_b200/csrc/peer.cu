@@ -140,6 +140,12 @@ extern "C" int crnn_model_set_grad_ready_callback(crnn_model* m, crnn_grad_ready
   return CRNN_OK;
 }
 
+extern "C" int crnn_model_set_backward_sm_reserve(crnn_model* m, int sms) {
+  if (!m || sms < 0 || sms > m->num_sms / 2) return crnn_fail(CRNN_INVALID_VALUE, "set_backward_sm_reserve: bad value");
+  m->bwd_sm_reserve = sms;
+  return CRNN_OK;
+}
+
 extern "C" int crnn_model_set_peers(crnn_model* m, int rank, int world, void* const* inbox_ptrs_host) {
   if (!m || world < 1 || rank < 0 || rank >= world || world > MAX_WORLD) return crnn_fail(CRNN_INVALID_VALUE, "set_peers: bad rank/world");
   if (m->d_peers) { cudaFree(m->d_peers); m->d_peers = nullptr; }

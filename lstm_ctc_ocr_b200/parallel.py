@@ -70,15 +70,24 @@ def bucket_ranges(table, total):
 
 
 class GradBuckets(object):
-    """Overlap of the gradient all-reduce with the backward pass: registered as the model's grad-ready callback."""
+    """Overlap of the gradient all-reduce with the backward pass: registered as the model's grad-ready callback.
 
-    def __init__(self, eng):
+    The announced ranges arrive in descending address order and are contiguous, so they are merged until `min_bucket_bytes` are
+    ready; each bucket is all-reduced on a side stream.  `sm_reserve` SMs are left free by the persistent backward kernels so the
+    collective's CTAs do not delay the tail of a 148-CTA grid (measured on 2 GPUs: 7 un-merged buckets on a full GPU cost +0.38 ms
+    per step over one all-reduce at the end -- every NCCL kernel displaced persistent CTAs for its whole duration)."""
+
+    def __init__(self, eng, min_bucket_bytes=8 << 20, sm_reserve=8):
         self.eng = eng
         self.stream = torch.cuda.Stream(device=eng.device)
         self.pending = []
         self.error = None
         self.enabled = True
         self.seen = []
+        self.min_bucket_bytes = int(min_bucket_bytes)
+        self.ready = None                                          # merged (offset, count) not yet launched
+        self.launched = 0
+        _lib.check(eng.lib.crnn_model_set_backward_sm_reserve(eng.handle, int(sm_reserve)))
         self._cb = _lib.GRAD_READY_FN(self._on_ready)             # keep the ctypes thunk alive
         _lib.check(eng.lib.crnn_model_set_grad_ready_callback(eng.handle, ctypes.cast(self._cb, ctypes.c_void_p), None))
 
@@ -87,16 +96,32 @@ class GradBuckets(object):
             self.seen.append((int(offset), int(count)))
             if not self.enabled or world_size() <= 1:
                 return
-            ev = torch.cuda.Event()
-            ev.record()                                            # everything enqueued so far produced this range
-            self.stream.wait_event(ev)
-            with torch.cuda.stream(self.stream):
-                self.pending.append(dist.all_reduce(self.eng.grads[offset:offset + count], op=dist.ReduceOp.SUM, async_op=True))
+            if self.ready is not None and offset + count == self.ready[0]:
+                self.ready = (int(offset), self.ready[1] + int(count))          # contiguous with the range announced before it
+            else:
+                self._launch()
+                self.ready = (int(offset), int(count))
+            if self.ready[1] * 4 >= self.min_bucket_bytes:
+                self._launch()
         except Exception as e:                                     # exceptions cannot cross the C frame: re-raised by finish()
             self.error = e
 
+    def _launch(self):
+        if self.ready is None:
+            return
+        offset, count = self.ready
+        self.ready = None
+        ev = torch.cuda.Event()
+        ev.record()                                                # everything enqueued so far produced this range
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            self.pending.append(dist.all_reduce(self.eng.grads[offset:offset + count], op=dist.ReduceOp.SUM, async_op=True))
+        self.launched += 1
+
     def finish(self):
         """Make the current (compute) stream wait for every bucket's all-reduce; returns the ranges seen this step."""
+        if self.enabled and world_size() > 1 and self.error is None:
+            self._launch()                                         # the remainder (conv1 + conv2: the only exposed exchange)
         for w in self.pending:
             w.wait()
         self.pending = []
@@ -109,6 +134,7 @@ class GradBuckets(object):
     def close(self):
         try:
             _lib.check(self.eng.lib.crnn_model_set_grad_ready_callback(self.eng.handle, None, None))
+            _lib.check(self.eng.lib.crnn_model_set_backward_sm_reserve(self.eng.handle, 0))
         except Exception:
             pass
 
@@ -121,14 +147,14 @@ class DataParallel(object):
         dp.step(lr, step)                     # waits for the buckets, then clip + Adam on the reduced gradient
     """
 
-    def __init__(self, eng, sync_bn=True, overlap=True, peer_memory=True):
+    def __init__(self, eng, sync_bn=True, overlap=True, peer_memory=True, min_bucket_bytes=8 << 20, sm_reserve=8):
         self.eng = eng
         self.rank, self.world = rank(), world_size()
         self.sync_bn, self.peer = bool(sync_bn), False
         self._inbox = None
         self._opened = []
         self._xcb = None
-        self.buckets = GradBuckets(eng) if overlap else None
+        self.buckets = GradBuckets(eng, min_bucket_bytes=min_bucket_bytes, sm_reserve=sm_reserve) if overlap else None
         if self.world > 1:
             broadcast_(eng.params)
             _lib.check(eng.lib.crnn_model_params_changed(eng.handle))

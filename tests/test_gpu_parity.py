@@ -46,17 +46,17 @@ def _ctc_case(T, N, lens, ilens, seed, scale=2.0):
     return x, lab, ll, il, O.ctc_loss_np(x, lab, ll, il)
 
 
-@pytest.mark.parametrize("kernel", ["fast", "fast-log", "tma", "tma-log", "generic"])
+@pytest.mark.parametrize("kernel", ["fast", "fast-me", "tma", "tma-me", "generic"])
 @pytest.mark.parametrize("case", ["ragged", "edge", "two_warp", "many_frames", "long_ks2", "long_ks4"])
 def test_ctc_loss_and_grad_vs_oracle(case, kernel, monkeypatch):
     """ctc_fast_kernel (S <= 32, default: per-thread bulk row copies), ctc_tma_kernel (S <= 32: one tensor-map tile load/store per
-    utterance) -- each with the mantissa/exponent recursion (default) and the log2-space recursion (`-log`) -- and the generic
+    utterance) -- each with the log2-space recursion (default) and the mantissa/exponent recursion (`-me`) -- and the generic
     ctc_loss_kernel<KS> against the fp64 oracle; CRNN_CTC_KERNEL / CRNN_CTC_RECUR select them."""
     from lstm_ctc_ocr_b200 import engine
     if kernel != "fast" and case.startswith("long_ks"):
         pytest.skip("S > 32 always runs the generic kernel")
     monkeypatch.setenv("CRNN_CTC_KERNEL", kernel.split("-")[0])
-    monkeypatch.setenv("CRNN_CTC_RECUR", "log" if kernel.endswith("-log") else "me")
+    monkeypatch.setenv("CRNN_CTC_RECUR", "me" if kernel.endswith("-me") else "log")
     if case == "ragged":
         rng = np.random.default_rng(0)
         N, T = 37, 24

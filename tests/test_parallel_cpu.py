@@ -56,3 +56,32 @@ def test_shard_batch_rejects_uneven_split():
     data, lab, ll, tsl = synthetic.synth_batch(6, 24, seed=1)
     with pytest.raises(ValueError):
         parallel.shard_batch(data, lab, ll, tsl, 0, 4)
+
+
+def test_bucket_ranges_tile_the_flat_gradient_buffer():
+    """parallel.bucket_ranges mirrors the 7 notifications of csrc/backward.cu: announcement order LSTM+logits first, conv1+conv2
+    last; the ranges tile [0, 7 158 592) exactly once (24 tensors, 7 158 592 parameters)."""
+    from collections import OrderedDict
+    from lstm_ctc_ocr_b200 import parallel, synthetic
+    p = synthetic.init_params(3)
+    order = []
+    for name in ("conv1", "conv2", "conv3_1", "conv3_2"):
+        order += [f"{name}/weights", f"{name}/biases"]
+    for name in ("conv4_1", "conv4_2"):
+        order += [f"{name}/weights", f"{name}/biases", f"{name}/{name}/beta", f"{name}/{name}/gamma"]
+    order += ["conv5/weights", "conv5/biases"]
+    for d in ("fw", "bw"):
+        order += [f"logits/bidirectional_rnn/{d}/lstm_cell/weights", f"logits/bidirectional_rnn/{d}/lstm_cell/biases"]
+    order += ["logits/weights", "logits/biases"]
+    assert sorted(order) == sorted(p)
+    table, off = OrderedDict(), 0
+    for k in order:
+        table[k] = (off, p[k].shape)
+        off += p[k].size
+    assert off == 7158592
+    r = parallel.bucket_ranges(table, off)
+    assert len(r) == 7 and sum(c for _, c in r) == off
+    assert r[0] == (table["logits/bidirectional_rnn/fw/lstm_cell/weights"][0], 1574912 + 32832)        # LSTM + logits, announced first
+    assert r[-1] == (0, 640 + 73856)                                                                    # conv1 + conv2, announced last
+    covered = sorted(r)
+    assert covered[0][0] == 0 and all(a[0] + a[1] == b[0] for a, b in zip(covered, covered[1:])) and covered[-1][0] + covered[-1][1] == off

@@ -13,7 +13,7 @@ from lstm_ctc_ocr_b200 import engine, synthetic  # noqa: E402
 
 def run(N, T, max_len, kernel, reps=200, sets=10):
     os.environ["CRNN_CTC_KERNEL"] = kernel.split("-")[0]          # fast (default) | tma | generic
-    os.environ["CRNN_CTC_RECUR"] = "log" if kernel.endswith("-log") else "me"
+    os.environ["CRNN_CTC_RECUR"] = "me" if kernel.endswith("-me") else "log"
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(3)
     ll = rng.integers(min(4, max_len), max_len + 1, size=N).astype(np.int32)
@@ -43,5 +43,5 @@ if __name__ == "__main__":
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
     T = int(sys.argv[2]) if len(sys.argv) > 2 else 63
     for max_len in (6, 15):
-        for k in ("fast", "fast-log", "tma", "tma-log", "generic"):
+        for k in ("fast", "fast-me", "tma", "tma-me", "generic"):
             print(json.dumps(run(N, T, max_len, k)))

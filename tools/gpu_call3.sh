@@ -19,14 +19,20 @@ run() { # name, extra flags
   python - <<PY
 import json
 try:
-    d = json.load(open("gpurun_out/c3_bench_${N}gpu_$1.json"))
+    d = json.loads([l for l in open("gpurun_out/c3_bench_${N}gpu_$1.json") if l.startswith("{")][-1])
     print("$1", d["value"], d["ms_per_step"], "e2e", d["e2e"]["value"], "train", d.get("train_step", {}).get("ms_per_step"))
 except Exception as e:
     print("$1 failed", e)
 PY
 }
-run default ""
-run nccl_bn "--no-peer-memory"
-run no_sync_bn "--no-sync-bn"
-run no_overlap "--no-overlap"
+if [ "$N" = "2" ]; then
+  run default ""
+  run nccl_bn "--no-peer-memory"
+  run no_sync_bn "--no-sync-bn"
+  run no_overlap "--no-overlap"
+else
+  run default ""
+  run no_overlap "--no-overlap"
+  run r1_behaviour "--no-overlap --no-sync-bn"
+fi
 tail -3 gpurun_out/c3_bench_${N}gpu_default.err
