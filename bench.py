@@ -173,7 +173,9 @@ def main():
     ap.add_argument("--no-decode-eq", action="store_true", help="skip the 10k-line decode-equality statistic")
     ap.add_argument("--no-sync-bn", action="store_true", help="N>1: per-replica BatchNorm statistics (round-1 behaviour)")
     ap.add_argument("--no-peer-memory", action="store_true", help="N>1: exchange the BN sums through NCCL instead of peer memory")
-    ap.add_argument("--no-overlap", action="store_true", help="N>1: one all-reduce of the whole gradient buffer after the backward (round-1 behaviour)")
+    ap.add_argument("--overlap", action="store_true", help="N>1: all-reduce merged gradient buckets on a side stream during the backward "
+                                                           "(default: one all-reduce after it; measured faster, profiles/r2_scaling.md)")
+    ap.add_argument("--sync-bn-forward", action="store_true", help="N>1: global-batch BN also in the forward-only metric (default: replicas)")
     ap.add_argument("--bucket-mb", type=float, default=8.0, help="N>1: merge announced gradient ranges until this many MB are ready")
     ap.add_argument("--sm-reserve", type=int, default=8, help="N>1 with overlap: SMs the persistent backward kernels leave to the collectives")
     args = ap.parse_args()
@@ -199,7 +201,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
     if world > 1:
-        if not args.no_overlap:
+        if args.overlap:
             os.environ.setdefault("NCCL_MAX_NCHANNELS", str(max(args.sm_reserve, 1)))     # the overlapped collectives fit the reserved SMs
         dist.init_process_group("nccl", device_id=dev)
     N, W, desc = WORKLOADS[args.workload]
@@ -218,8 +220,13 @@ def main():
     dp = None
     if world > 1:
         from lstm_ctc_ocr_b200 import parallel
-        dp = parallel.DataParallel(model, sync_bn=not args.no_sync_bn, overlap=not args.no_overlap, peer_memory=not args.no_peer_memory,
+        dp = parallel.DataParallel(model, sync_bn=not args.no_sync_bn, overlap=args.overlap, peer_memory=not args.no_peer_memory,
                                    min_bucket_bytes=int(args.bucket_mb * (1 << 20)), sm_reserve=args.sm_reserve)
+        # forward + CTC metric: independent replicas, each normalising with the statistics of ITS batch of 1024 (what N reference
+        # processes would do; decode is "replicas only").  The training step below switches to GLOBAL-batch statistics.
+        train_sync_bn = dp.sync_bn
+        if not args.sync_bn_forward:
+            dp.set_sync_bn(False)
 
     # ---- rotating set of distinct input batches > L2 (8 x 33.5 MB at c3), resident in HBM
     nrot = max(2, int(np.ceil(160e6 / (N * W * 32 * 4))))
@@ -335,6 +342,21 @@ def main():
 
     # ---- BASELINE configs[4] companion: full training step (fwd + CTC + backward + [NCCL grad all-reduce] + clip + Adam)
     ms_train = None
+    ms_fwd_sync = None
+    if dp is not None and train_sync_bn:
+        dp.set_sync_bn(True)
+        if not args.sync_bn_forward:
+            # the same forward + CTC step with BatchNorm over the GLOBAL batch (2 x 8 KB exchanged inside the BN finalize kernel)
+            for i in range(3):
+                step(i)
+            sync_all()
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record()
+            for i in range(K):
+                step(i)
+            h1.record()
+            sync_all()
+            ms_fwd_sync = h0.elapsed_time(h1) / K
     if not args.no_train:
         model.set_training(True)
         Kt = max(3, min(K, 10))
@@ -370,11 +392,12 @@ def main():
 
     # ---- max over ranks
     if world > 1:
-        t = torch.tensor([ms_total, ms_e2e, ms_train or 0.0, ms_fresh, ms_refed], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_total, ms_e2e, ms_train or 0.0, ms_fresh, ms_refed, ms_fwd_sync or 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, ms_e2e = float(t[0]), float(t[1])
         ms_train = float(t[2]) if ms_train is not None else None
         ms_fresh, ms_refed = float(t[3]), float(t[4])
+        ms_fwd_sync = float(t[5]) if ms_fwd_sync is not None else None
     ms_step = ms_total / K
     value = world * N / (ms_step / 1e3)
     e2e_value = world * N / (ms_e2e / Ke / 1e3)
@@ -413,7 +436,9 @@ def main():
             "config": {"workload": desc, "batch_per_gpu": N, "global_batch": N * world, "width": W, "T": T,
                        "parallelism": (f"dp{world}: batch sharded over ranks; BatchNorm over the GLOBAL batch -- 2 exchanges of 8 KB per forward, "
                                        f"{'fused into the BN finalize kernel over NVLink peer memory' if (dp is not None and dp.peer) else 'NCCL all-reduce'}"
-                                       if (dp is not None and dp.sync_bn) else f"dp{world} (batch-sharded replicas, per-replica BN statistics)"),
+                                       if (dp is not None and args.sync_bn_forward and not args.no_sync_bn)
+                                       else f"dp{world}: independent replicas for forward + CTC (each BatchNorm over its own batch of {N}); "
+                                            f"the train_step entry shards ONE global batch (global-batch BN, gradient all-reduce)"),
                        "l2": f"rotating {nrot} distinct input batches ({nrot * N * W * 32 * 4 / 1e6:.0f} MB > 126 MB L2); "
                              f"per-step activation traffic ~2.5 GB"},
             "loss": round(loss_val, 5),
@@ -440,10 +465,15 @@ def main():
                                                "achieved counts the ALGORITHMIC flops once"}
             line.pop("stages", None)
             line["gpu_launches"] = K * (1 + 2 * 6 + 4 + 2 + 2 * T + 4)
+        if ms_fwd_sync is not None:
+            line["global_batch_bn_forward"] = {"ms_per_step": round(ms_fwd_sync, 4), "images_per_s": round(world * N / (ms_fwd_sync / 1e3), 1),
+                                               "what": "the same forward + CTC step with BatchNorm statistics over the GLOBAL batch "
+                                                       f"({world * N} lines): two 8 KB exchanges per step inside the BN finalize kernel "
+                                                       f"({'NVLink peer memory' if dp.peer else 'NCCL callback'}); the extra time is the wait for the slowest rank"}
         if ms_train is not None:
             line["train_step"] = {"ms_per_step": round(ms_train, 4), "images_per_s": round(world * N / (ms_train / 1e3), 1),
-                                  "what": "fwd + CTC loss/grad + backward + " + ((f"NCCL all-reduce(28.6 MB f32) in buckets >= {args.bucket_mb:g} MB overlapped with the backward ({args.sm_reserve} SMs reserved) + " if not args.no_overlap else "one NCCL all-reduce(28.6 MB f32) after the backward + ") +
-                                          ("global-batch BN fwd/bwd + " if not args.no_sync_bn else "") if world > 1 else "") +
+                                  "what": "fwd + CTC loss/grad + backward + " + ((f"NCCL all-reduce(28.6 MB f32) in buckets >= {args.bucket_mb:g} MB overlapped with the backward ({args.sm_reserve} SMs reserved) + " if args.overlap else "one NCCL all-reduce(28.6 MB f32) after the backward + ") +
+                                          ("global-batch BatchNorm (sums exchanged inside the BN kernels over NVLink peer memory) fwd/bwd + " if not args.no_sync_bn else "") if world > 1 else "") +
                                           "global-norm clip + Adam (BASELINE configs[4] per-GPU shape)",
                                   "stages_ms": bwd_stage_ms}
         if world == 1 and not args.no_cpu_baseline:

@@ -297,11 +297,14 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const __nv_bfloat16* _
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cg = lane & 7;
   const int slot = warp * 4 + (lane >> 3);
-  float acc[9][8], accb[8];
+  // accumulators as f32x2 pairs of adjacent channels: the 288 FMAs per pooled position issue as 144 FFMA2 (the 3-register scalar
+  // FFMA issues every other cycle per scheduler on sm_100 -- the same ceiling the SIMT forward conv1 hit; r2 ncu: issue-bound at 46 %)
+  uint64_t acc2[9][4];
+  float accb[8];
 #pragma unroll
   for (int k = 0; k < 9; ++k)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc2[k][j] = 0ull;
 #pragma unroll
   for (int j = 0; j < 8; ++j) accb[j] = 0.f;
 
@@ -354,21 +357,29 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const __nv_bfloat16* _
       for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
-          float gs[8];
+          uint64_t gs2[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) gs[j] = (idx[j] == (uint32_t)(dy * 2 + dx)) ? g[j] : 0.f;
+          for (int j = 0; j < 4; ++j)
+            gs2[j] = ptx::pack_f32x2((idx[2 * j] == (uint32_t)(dy * 2 + dx)) ? g[2 * j] : 0.f,
+                                     (idx[2 * j + 1] == (uint32_t)(dy * 2 + dx)) ? g[2 * j + 1] : 0.f);
 #pragma unroll
           for (int r = 0; r < 3; ++r)
 #pragma unroll
             for (int s2 = 0; s2 < 3; ++s2) {
               const float x = patch[dy + r][dx + s2];
+              const uint64_t x2 = ptx::pack_f32x2(x, x);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) acc[r * 3 + s2][j] = fmaf(x, gs[j], acc[r * 3 + s2][j]);
+              for (int j = 0; j < 4; ++j) acc2[r * 3 + s2][j] = ptx::ffma2(x2, gs2[j], acc2[r * 3 + s2][j]);
             }
         }
     }
   }
   // block reduction: lanes sharing a channel group (lane ^ 8, ^ 16), then the 8 warps through shared memory
+  float acc[9][8];
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ptx::unpack_f32x2(acc2[k][j], acc[k][2 * j], acc[k][2 * j + 1]);
 #pragma unroll
   for (int k = 0; k < 9; ++k)
 #pragma unroll

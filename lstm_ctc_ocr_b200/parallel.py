@@ -143,11 +143,16 @@ class DataParallel(object):
     """Everything a rank needs around one CrnnModel: parameter broadcast, global-batch BatchNorm, overlapped gradient exchange.
 
         dp = DataParallel(eng)                # after dist.init_process_group, once
-        ... eng.forward / ctc_loss / eng.backward ...      (crnn_backward announces the buckets; they reduce on a side stream)
-        dp.step(lr, step)                     # waits for the buckets, then clip + Adam on the reduced gradient
+        ... eng.forward / ctc_loss / eng.backward ...
+        dp.step(lr, step)                     # gradient all-reduce, then clip + Adam on the reduced gradient
+
+    `overlap=True` reduces merged gradient buckets on a side stream while the backward still runs (GradBuckets).  Measured on
+    B200 it does NOT pay for this model (profiles/r2_scaling.md: 8 GPUs 13.41 ms vs 13.20 ms per step, 2 GPUs 13.25 vs 12.87):
+    the whole exchange is ~0.15 ms of a 13 ms step while every overlapped NCCL kernel displaces CTAs of the persistent
+    full-GPU GEMM grids for its duration -- so the default is ONE all-reduce of the flat buffer after the backward.
     """
 
-    def __init__(self, eng, sync_bn=True, overlap=True, peer_memory=True, min_bucket_bytes=8 << 20, sm_reserve=8):
+    def __init__(self, eng, sync_bn=True, overlap=False, peer_memory=True, min_bucket_bytes=8 << 20, sm_reserve=8):
         self.eng = eng
         self.rank, self.world = rank(), world_size()
         self.sync_bn, self.peer = bool(sync_bn), False
@@ -158,11 +163,12 @@ class DataParallel(object):
         if self.world > 1:
             broadcast_(eng.params)
             _lib.check(eng.lib.crnn_model_params_changed(eng.handle))
-            if self.sync_bn:
-                self._xcb = _lib.ALLREDUCE_FN(self._allreduce_cb)
-                _lib.check(eng.lib.crnn_model_set_data_parallel(eng.handle, self.rank, self.world, ctypes.cast(self._xcb, ctypes.c_void_p), None))
-                if peer_memory:
-                    self.peer = self.setup_peer_memory()
+            self._xcb = _lib.ALLREDUCE_FN(self._allreduce_cb)
+            _lib.check(eng.lib.crnn_model_set_data_parallel(eng.handle, self.rank, self.world, ctypes.cast(self._xcb, ctypes.c_void_p), None))
+            if peer_memory:
+                self.peer = self.setup_peer_memory()
+            if not self.sync_bn:
+                self.set_sync_bn(False)
 
     # ---- fallback exchange of the BN sums: an NCCL all-reduce issued from the callback --------------------------------
     def _allreduce_cb(self, user, dev_ptr, count, is_f64, stream):
@@ -211,6 +217,15 @@ class DataParallel(object):
         torch.cuda.synchronize(self.eng.device)
         dist.barrier()                                             # every inbox is zeroed and mapped before the first exchange
         return True
+
+    def set_sync_bn(self, flag):
+        """Switch the BN layers between GLOBAL-batch statistics (training semantics of the single-device reference) and
+        per-replica statistics (independent inference replicas).  The peer inboxes / callback stay registered."""
+        if self.world <= 1:
+            return
+        cb = ctypes.cast(self._xcb, ctypes.c_void_p) if self._xcb is not None else None
+        _lib.check(self.eng.lib.crnn_model_set_data_parallel(self.eng.handle, self.rank if flag else 0, self.world if flag else 1, cb, None))
+        self.sync_bn = bool(flag)
 
     def peer_error(self):
         e = _lib.c_int()

@@ -25,14 +25,10 @@ except Exception as e:
     print("$1 failed", e)
 PY
 }
+run default ""
+run sync_bn_forward "--sync-bn-forward"
 if [ "$N" = "2" ]; then
-  run default ""
-  run nccl_bn "--no-peer-memory"
-  run no_sync_bn "--no-sync-bn"
-  run no_overlap "--no-overlap"
-else
-  run default ""
-  run no_overlap "--no-overlap"
-  run r1_behaviour "--no-overlap --no-sync-bn"
+  run overlap "--overlap"
+  run nccl_bn "--sync-bn-forward --no-peer-memory"
 fi
 tail -3 gpurun_out/c3_bench_${N}gpu_default.err
