@@ -389,6 +389,7 @@ def main():
         fbuf = np.zeros((Kt, nst), dtype=np.float32)
         check(model.lib.crnn_profile_read(model.handle, fbuf.ctypes.data, nfb))
         bwd_stage_ms["forward_total(train mode)"] = round(float(fbuf[:nfb.value].sum(axis=1).mean()), 4)
+        fwd_train_stage_ms = {n_: round(float(v_), 4) for n_, v_ in zip(stage_names, fbuf[:nfb.value].mean(axis=0))} if nfb.value > 0 else {}
 
     # ---- max over ranks
     if world > 1:
@@ -475,7 +476,7 @@ def main():
                                   "what": "fwd + CTC loss/grad + backward + " + ((f"NCCL all-reduce(28.6 MB f32) in buckets >= {args.bucket_mb:g} MB overlapped with the backward ({args.sm_reserve} SMs reserved) + " if args.overlap else "one NCCL all-reduce(28.6 MB f32) after the backward + ") +
                                           ("global-batch BatchNorm (sums exchanged inside the BN kernels over NVLink peer memory) fwd/bwd + " if not args.no_sync_bn else "") if world > 1 else "") +
                                           "global-norm clip + Adam (BASELINE configs[4] per-GPU shape)",
-                                  "stages_ms": bwd_stage_ms}
+                                  "stages_ms": bwd_stage_ms, "forward_stages_train_mode_ms": fwd_train_stage_ms}
         if world == 1 and not args.no_cpu_baseline:
             sn = args.cpu_sample
             r = cpu_reference(sn, W, steps=8, warmup=2)
