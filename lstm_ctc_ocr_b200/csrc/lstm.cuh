@@ -40,8 +40,8 @@ struct Params {
   const int* seq_len;           // [Nimg]
   int Nimg, Npad, H, T, tiles_per_dir;
   // training only (nullptr for inference): activations the backward recurrence needs
-  __nv_bfloat16* gates;         // [2 dirs][Nimg][T steps][4 gates i,j,f,o][256] post-activation
-  float* csave;                 // [2 dirs][Nimg][T steps][256] cell state after the step
+  __nv_bfloat16* gates;         // post-activation gates i,j,f,o, coalesced per batch tile: layout in common.cuh (lstm_gate_off)
+  float* csave;                 // cell state after the step (lstm_c_off)
   int swap_ls;                  // debug (CRNN_LSTM_SWAPLS=1): exchange the LBO/SBO fields of the no-swizzle A descriptor
   long long* trace;             // debug (CRNN_LSTM_TRACE=1): clock64 stamps of CTAs 0 and 5, steps 8..11, 16 events each
 };
@@ -216,19 +216,19 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_con
             }
           }
           if (p.gates != nullptr) {
-            const size_t srow = ((size_t)dir * p.Nimg + n) * p.T + s;
-            __nv_bfloat16* gs = p.gates + srow * 1024 + rank * UPC + u0;
-            float* cs = p.csave + srow * 256 + rank * UPC + u0;
+            const size_t dts = (size_t)unit * p.T + s;                  // coalesced saved-state layout, common.cuh
+            __nv_bfloat16* gs = p.gates + lstm_gate_off(dts, 0, rank * UPC + u0, row);
+            float* cs = p.csave + lstm_c_off(dts, rank * UPC + u0, row);
 #pragma unroll
             for (int i = 0; i < HALF; i += 8) {
-              *reinterpret_cast<uint4*>(gs + 0 * 256 + i) = make_uint4(ptx::pack_bf16x2(__uint_as_float(gi[i]), __uint_as_float(gi[i + 1])), ptx::pack_bf16x2(__uint_as_float(gi[i + 2]), __uint_as_float(gi[i + 3])), ptx::pack_bf16x2(__uint_as_float(gi[i + 4]), __uint_as_float(gi[i + 5])), ptx::pack_bf16x2(__uint_as_float(gi[i + 6]), __uint_as_float(gi[i + 7])));
-              *reinterpret_cast<uint4*>(gs + 1 * 256 + i) = make_uint4(ptx::pack_bf16x2(__uint_as_float(gj[i]), __uint_as_float(gj[i + 1])), ptx::pack_bf16x2(__uint_as_float(gj[i + 2]), __uint_as_float(gj[i + 3])), ptx::pack_bf16x2(__uint_as_float(gj[i + 4]), __uint_as_float(gj[i + 5])), ptx::pack_bf16x2(__uint_as_float(gj[i + 6]), __uint_as_float(gj[i + 7])));
-              *reinterpret_cast<uint4*>(gs + 2 * 256 + i) = make_uint4(ptx::pack_bf16x2(__uint_as_float(gf[i]), __uint_as_float(gf[i + 1])), ptx::pack_bf16x2(__uint_as_float(gf[i + 2]), __uint_as_float(gf[i + 3])), ptx::pack_bf16x2(__uint_as_float(gf[i + 4]), __uint_as_float(gf[i + 5])), ptx::pack_bf16x2(__uint_as_float(gf[i + 6]), __uint_as_float(gf[i + 7])));
-              *reinterpret_cast<uint4*>(gs + 3 * 256 + i) = make_uint4(ptx::pack_bf16x2(__uint_as_float(go[i]), __uint_as_float(go[i + 1])), ptx::pack_bf16x2(__uint_as_float(go[i + 2]), __uint_as_float(go[i + 3])), ptx::pack_bf16x2(__uint_as_float(go[i + 4]), __uint_as_float(go[i + 5])), ptx::pack_bf16x2(__uint_as_float(go[i + 6]), __uint_as_float(go[i + 7])));
+              *reinterpret_cast<uint4*>(gs + 0 * LSTM_GATE_STRIDE + (i >> 3) * LSTM_GCHUNK_STRIDE) = make_uint4(ptx::pack_bf16x2(__uint_as_float(gi[i]), __uint_as_float(gi[i + 1])), ptx::pack_bf16x2(__uint_as_float(gi[i + 2]), __uint_as_float(gi[i + 3])), ptx::pack_bf16x2(__uint_as_float(gi[i + 4]), __uint_as_float(gi[i + 5])), ptx::pack_bf16x2(__uint_as_float(gi[i + 6]), __uint_as_float(gi[i + 7])));
+              *reinterpret_cast<uint4*>(gs + 1 * LSTM_GATE_STRIDE + (i >> 3) * LSTM_GCHUNK_STRIDE) = make_uint4(ptx::pack_bf16x2(__uint_as_float(gj[i]), __uint_as_float(gj[i + 1])), ptx::pack_bf16x2(__uint_as_float(gj[i + 2]), __uint_as_float(gj[i + 3])), ptx::pack_bf16x2(__uint_as_float(gj[i + 4]), __uint_as_float(gj[i + 5])), ptx::pack_bf16x2(__uint_as_float(gj[i + 6]), __uint_as_float(gj[i + 7])));
+              *reinterpret_cast<uint4*>(gs + 2 * LSTM_GATE_STRIDE + (i >> 3) * LSTM_GCHUNK_STRIDE) = make_uint4(ptx::pack_bf16x2(__uint_as_float(gf[i]), __uint_as_float(gf[i + 1])), ptx::pack_bf16x2(__uint_as_float(gf[i + 2]), __uint_as_float(gf[i + 3])), ptx::pack_bf16x2(__uint_as_float(gf[i + 4]), __uint_as_float(gf[i + 5])), ptx::pack_bf16x2(__uint_as_float(gf[i + 6]), __uint_as_float(gf[i + 7])));
+              *reinterpret_cast<uint4*>(gs + 3 * LSTM_GATE_STRIDE + (i >> 3) * LSTM_GCHUNK_STRIDE) = make_uint4(ptx::pack_bf16x2(__uint_as_float(go[i]), __uint_as_float(go[i + 1])), ptx::pack_bf16x2(__uint_as_float(go[i + 2]), __uint_as_float(go[i + 3])), ptx::pack_bf16x2(__uint_as_float(go[i + 4]), __uint_as_float(go[i + 5])), ptx::pack_bf16x2(__uint_as_float(go[i + 6]), __uint_as_float(go[i + 7])));
             }
 #pragma unroll
             for (int i = 0; i < HALF; i += 4)
-              *reinterpret_cast<float4*>(cs + i) = make_float4(cst[u0 + i], cst[u0 + i + 1], cst[u0 + i + 2], cst[u0 + i + 3]);
+              *reinterpret_cast<float4*>(cs + (i >> 2) * LSTM_CCHUNK_STRIDE) = make_float4(cst[u0 + i], cst[u0 + i + 1], cst[u0 + i + 2], cst[u0 + i + 3]);
           }
 #pragma unroll
           for (int i = 0; i < HALF / 2; ++i) hp[i] = ptx::pack_bf16x2(hv[2 * i], hv[2 * i + 1]);
@@ -546,18 +546,18 @@ lstm_mc_kernel(const __grid_constant__ CUtensorMap tmW, const Params p) {
         else *reinterpret_cast<uint4*>(lo) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
       }
       if (active && p.gates != nullptr) {
-        const size_t srow = ((size_t)dir * p.Nimg + n) * p.T + s;
-        __nv_bfloat16* gs = p.gates + srow * 1024 + rank * UPC + u0;
-        float* cs = p.csave + srow * 256 + rank * UPC + u0;
+        const size_t dts = (size_t)unit * p.T + s;                  // coalesced saved-state layout, common.cuh
+        __nv_bfloat16* gs = p.gates + lstm_gate_off(dts, 0, rank * UPC + u0, row);
+        float* cs = p.csave + lstm_c_off(dts, rank * UPC + u0, row);
 #pragma unroll
         for (int i = 0; i < HALF; i += 8) {
-          *reinterpret_cast<uint4*>(gs + 0 * 256 + i) = make_uint4(ptx::pack_bf16x2(__uint_as_float(gi[i]), __uint_as_float(gi[i + 1])), ptx::pack_bf16x2(__uint_as_float(gi[i + 2]), __uint_as_float(gi[i + 3])), ptx::pack_bf16x2(__uint_as_float(gi[i + 4]), __uint_as_float(gi[i + 5])), ptx::pack_bf16x2(__uint_as_float(gi[i + 6]), __uint_as_float(gi[i + 7])));
-          *reinterpret_cast<uint4*>(gs + 1 * 256 + i) = make_uint4(ptx::pack_bf16x2(__uint_as_float(gj[i]), __uint_as_float(gj[i + 1])), ptx::pack_bf16x2(__uint_as_float(gj[i + 2]), __uint_as_float(gj[i + 3])), ptx::pack_bf16x2(__uint_as_float(gj[i + 4]), __uint_as_float(gj[i + 5])), ptx::pack_bf16x2(__uint_as_float(gj[i + 6]), __uint_as_float(gj[i + 7])));
-          *reinterpret_cast<uint4*>(gs + 2 * 256 + i) = make_uint4(ptx::pack_bf16x2(__uint_as_float(gf[i]), __uint_as_float(gf[i + 1])), ptx::pack_bf16x2(__uint_as_float(gf[i + 2]), __uint_as_float(gf[i + 3])), ptx::pack_bf16x2(__uint_as_float(gf[i + 4]), __uint_as_float(gf[i + 5])), ptx::pack_bf16x2(__uint_as_float(gf[i + 6]), __uint_as_float(gf[i + 7])));
-          *reinterpret_cast<uint4*>(gs + 3 * 256 + i) = make_uint4(ptx::pack_bf16x2(__uint_as_float(go[i]), __uint_as_float(go[i + 1])), ptx::pack_bf16x2(__uint_as_float(go[i + 2]), __uint_as_float(go[i + 3])), ptx::pack_bf16x2(__uint_as_float(go[i + 4]), __uint_as_float(go[i + 5])), ptx::pack_bf16x2(__uint_as_float(go[i + 6]), __uint_as_float(go[i + 7])));
+          *reinterpret_cast<uint4*>(gs + 0 * LSTM_GATE_STRIDE + (i >> 3) * LSTM_GCHUNK_STRIDE) = make_uint4(ptx::pack_bf16x2(__uint_as_float(gi[i]), __uint_as_float(gi[i + 1])), ptx::pack_bf16x2(__uint_as_float(gi[i + 2]), __uint_as_float(gi[i + 3])), ptx::pack_bf16x2(__uint_as_float(gi[i + 4]), __uint_as_float(gi[i + 5])), ptx::pack_bf16x2(__uint_as_float(gi[i + 6]), __uint_as_float(gi[i + 7])));
+          *reinterpret_cast<uint4*>(gs + 1 * LSTM_GATE_STRIDE + (i >> 3) * LSTM_GCHUNK_STRIDE) = make_uint4(ptx::pack_bf16x2(__uint_as_float(gj[i]), __uint_as_float(gj[i + 1])), ptx::pack_bf16x2(__uint_as_float(gj[i + 2]), __uint_as_float(gj[i + 3])), ptx::pack_bf16x2(__uint_as_float(gj[i + 4]), __uint_as_float(gj[i + 5])), ptx::pack_bf16x2(__uint_as_float(gj[i + 6]), __uint_as_float(gj[i + 7])));
+          *reinterpret_cast<uint4*>(gs + 2 * LSTM_GATE_STRIDE + (i >> 3) * LSTM_GCHUNK_STRIDE) = make_uint4(ptx::pack_bf16x2(__uint_as_float(gf[i]), __uint_as_float(gf[i + 1])), ptx::pack_bf16x2(__uint_as_float(gf[i + 2]), __uint_as_float(gf[i + 3])), ptx::pack_bf16x2(__uint_as_float(gf[i + 4]), __uint_as_float(gf[i + 5])), ptx::pack_bf16x2(__uint_as_float(gf[i + 6]), __uint_as_float(gf[i + 7])));
+          *reinterpret_cast<uint4*>(gs + 3 * LSTM_GATE_STRIDE + (i >> 3) * LSTM_GCHUNK_STRIDE) = make_uint4(ptx::pack_bf16x2(__uint_as_float(go[i]), __uint_as_float(go[i + 1])), ptx::pack_bf16x2(__uint_as_float(go[i + 2]), __uint_as_float(go[i + 3])), ptx::pack_bf16x2(__uint_as_float(go[i + 4]), __uint_as_float(go[i + 5])), ptx::pack_bf16x2(__uint_as_float(go[i + 6]), __uint_as_float(go[i + 7])));
         }
 #pragma unroll
-        for (int i = 0; i < HALF; i += 4) *reinterpret_cast<float4*>(cs + i) = make_float4(cst[i], cst[i + 1], cst[i + 2], cst[i + 3]);
+        for (int i = 0; i < HALF; i += 4) *reinterpret_cast<float4*>(cs + (i >> 2) * LSTM_CCHUNK_STRIDE) = make_float4(cst[i], cst[i + 1], cst[i + 2], cst[i + 3]);
       }
       if (warp_idx == 2) LSTM_TRACE(10);
     }

@@ -34,8 +34,8 @@ constexpr int BAR_OFFSET = B_BYTES + STAGES * A_STAGE;
 constexpr int SMEM_BYTES = BAR_OFFSET + 256 + 1024;
 
 struct Params {
-  const __nv_bfloat16* gates;     // [2][Nimg][T][4][256]  (saved by the forward kernel)
-  const float* csave;             // [2][Nimg][T][256]
+  const __nv_bfloat16* gates;     // saved by the forward kernel, coalesced per batch tile (common.cuh: lstm_gate_off)
+  const float* csave;             // (common.cuh: lstm_c_off)
   const __nv_bfloat16* d_out;     // [Nimg*H, 512] gradient w.r.t. the LSTM output (frame order)
   __nv_bfloat16* dz_state;        // [2 bufs][2 dirs][Npad][1024] step-order exchange buffer
   __nv_bfloat16* dz_all;          // [Nimg*H, 2048] frame order, permuted gate columns, [fw | bw]
@@ -144,16 +144,15 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
     } else {
       const bool active = s < len;
       const int t = active ? (dir ? (len - 1 - s) : s) : s;
-      const size_t srow = ((size_t)dir * p.Nimg + n) * p.T + s;
+      const size_t dts = (size_t)unit * p.T + s;                    // coalesced saved-state layout, common.cuh
       // The saved forward state of step s-1 (gates, c, c_prev, d_out: ~0.7 KB per thread, long evicted from L2) is pulled
       // into L2 one step ahead so the dependent loads of the next iteration do not pay HBM latency on the serial chain.
       if (s >= 1 && (s - 1) < len) {
-        const size_t prow = srow - 1;
         const int tp = dir ? (len - s) : (s - 1);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.gates + prow * 1024 + g * 256 + rank * UPC));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.csave + prow * 256 + rank * UPC));
-        if (s >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.csave + (prow - 1) * 256 + rank * UPC));
+        for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.gates + lstm_gate_off(dts - 1, g, rank * UPC, row)));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.csave + lstm_c_off(dts - 1, rank * UPC, row)));
+        if (s >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.csave + lstm_c_off(dts - 2, rank * UPC, row)));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p.d_out + ((size_t)n * p.H + tp) * 512 + dir * 256 + rank * UPC));
       }
       if (has_rec) {
@@ -176,23 +175,23 @@ lstm_bwd_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant_
         }
         float dzi[16], dzj[16], dzf[16], dzo[16];
         if (active) {
-          const __nv_bfloat16* gs = p.gates + srow * 1024 + rank * UPC + u0;
-          const float* cs = p.csave + srow * 256 + rank * UPC + u0;
+          const __nv_bfloat16* gs = p.gates + lstm_gate_off(dts, 0, rank * UPC + u0, row);
+          const float* cs = p.csave + lstm_c_off(dts, rank * UPC + u0, row);
           const __nv_bfloat16* dout = p.d_out + ((size_t)n * p.H + t) * 512 + dir * 256 + rank * UPC + u0;
           float gi[16], gj[16], gf[16], go[16], cc[16], cp[16], dh[16];
 #pragma unroll
           for (int v = 0; v < 2; ++v) {
-            unpack8(__ldg(reinterpret_cast<const uint4*>(gs + 0 * 256) + v), gi + 8 * v);
-            unpack8(__ldg(reinterpret_cast<const uint4*>(gs + 1 * 256) + v), gj + 8 * v);
-            unpack8(__ldg(reinterpret_cast<const uint4*>(gs + 2 * 256) + v), gf + 8 * v);
-            unpack8(__ldg(reinterpret_cast<const uint4*>(gs + 3 * 256) + v), go + 8 * v);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(gs + 0 * LSTM_GATE_STRIDE + v * LSTM_GCHUNK_STRIDE)), gi + 8 * v);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(gs + 1 * LSTM_GATE_STRIDE + v * LSTM_GCHUNK_STRIDE)), gj + 8 * v);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(gs + 2 * LSTM_GATE_STRIDE + v * LSTM_GCHUNK_STRIDE)), gf + 8 * v);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(gs + 3 * LSTM_GATE_STRIDE + v * LSTM_GCHUNK_STRIDE)), go + 8 * v);
             unpack8(__ldg(reinterpret_cast<const uint4*>(dout) + v), dh + 8 * v);
           }
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(cs) + v);
+            const float4 a = __ldg(reinterpret_cast<const float4*>(cs + v * LSTM_CCHUNK_STRIDE));
             cc[4 * v] = a.x; cc[4 * v + 1] = a.y; cc[4 * v + 2] = a.z; cc[4 * v + 3] = a.w;
-            const float4 b = (s > 0) ? __ldg(reinterpret_cast<const float4*>(cs - 256) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 b = (s > 0) ? __ldg(reinterpret_cast<const float4*>(cs - LSTM_CSTEP_STRIDE + v * LSTM_CCHUNK_STRIDE)) : make_float4(0.f, 0.f, 0.f, 0.f);
             cp[4 * v] = b.x; cp[4 * v + 1] = b.y; cp[4 * v + 2] = b.z; cp[4 * v + 3] = b.w;
           }
 #pragma unroll
@@ -341,15 +340,14 @@ lstm_bwd_ks_kernel(const __grid_constant__ CUtensorMap tmW, const Params p, uint
       const bool has_rec = (s < p.T - 1);
       const bool active = s < len;
       const int t = active ? (dir ? (len - 1 - s) : s) : s;
-      const size_t srow = ((size_t)dir * p.Nimg + n) * p.T + s;
+      const size_t dts = (size_t)unit * p.T + s;                    // coalesced saved-state layout, common.cuh
       // pull the next step's saved state into L2 one step ahead (it was evicted long ago)
       if (s >= 1 && (s - 1) < len) {
-        const size_t prow = srow - 1;
         const int tp = dir ? (len - s) : (s - 1);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.gates + prow * 1024 + g * 256 + rank * UPC + u0));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.csave + prow * 256 + rank * UPC + u0));
-        if (s >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.csave + (prow - 1) * 256 + rank * UPC + u0));
+        for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.gates + lstm_gate_off(dts - 1, g, rank * UPC + u0, row)));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.csave + lstm_c_off(dts - 1, rank * UPC + u0, row)));
+        if (s >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.csave + lstm_c_off(dts - 2, rank * UPC + u0, row)));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p.d_out + ((size_t)n * p.H + tp) * 512 + dir * 256 + rank * UPC + u0));
       }
 
@@ -383,20 +381,20 @@ lstm_bwd_ks_kernel(const __grid_constant__ CUtensorMap tmW, const Params p, uint
       uint4 qg[4][2], qd[2];
       float4 qc[4], qp[4];
       if (active) {
-        const __nv_bfloat16* gs = p.gates + srow * 1024 + rank * UPC + u0;
-        const float* cs = p.csave + srow * 256 + rank * UPC + u0;
+        const __nv_bfloat16* gs = p.gates + lstm_gate_off(dts, 0, rank * UPC + u0, row);
+        const float* cs = p.csave + lstm_c_off(dts, rank * UPC + u0, row);
         const __nv_bfloat16* dout = p.d_out + ((size_t)n * p.H + t) * 512 + dir * 256 + rank * UPC + u0;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          qg[g][0] = __ldg(reinterpret_cast<const uint4*>(gs + g * 256));
-          qg[g][1] = __ldg(reinterpret_cast<const uint4*>(gs + g * 256) + 1);
+          qg[g][0] = __ldg(reinterpret_cast<const uint4*>(gs + g * LSTM_GATE_STRIDE));
+          qg[g][1] = __ldg(reinterpret_cast<const uint4*>(gs + g * LSTM_GATE_STRIDE + LSTM_GCHUNK_STRIDE));
         }
         qd[0] = __ldg(reinterpret_cast<const uint4*>(dout));
         qd[1] = __ldg(reinterpret_cast<const uint4*>(dout) + 1);
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-          qc[v] = __ldg(reinterpret_cast<const float4*>(cs) + v);
-          qp[v] = (s > 0) ? __ldg(reinterpret_cast<const float4*>(cs - 256) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+          qc[v] = __ldg(reinterpret_cast<const float4*>(cs + v * LSTM_CCHUNK_STRIDE));
+          qp[v] = (s > 0) ? __ldg(reinterpret_cast<const float4*>(cs - LSTM_CSTEP_STRIDE + v * LSTM_CCHUNK_STRIDE)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       if (has_rec) {

@@ -293,8 +293,8 @@ size_t layout_plan(Plan& pl, int N, int W, uint8_t* base, bool train) {
     pl.am1 = (uint8_t*)take(n * h1 * 16 * 64);
     pl.am2 = (uint8_t*)take(n * h2 * 8 * 128);
     pl.am3 = (uint8_t*)take(n * h2 * 4 * 256);
-    pl.gates = (__nv_bfloat16*)take((size_t)2 * n * T * 1024 * 2);
-    pl.csave = (float*)take((size_t)2 * n * T * 256 * 4);
+    pl.gates = (__nv_bfloat16*)take((size_t)2 * pl.Npad * T * 1024 * 2);     // per 128-row batch tile (common.cuh: lstm_gate_off)
+    pl.csave = (float*)take((size_t)2 * pl.Npad * T * 256 * 4);
     pl.dl_rows = (__nv_bfloat16*)take(n * h2 * 64 * 2);
     pl.d_lstm_out = (__nv_bfloat16*)take(n * h2 * 512 * 2);
     pl.dz_all = (__nv_bfloat16*)take(n * h2 * 2048 * 2);
