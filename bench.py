@@ -474,7 +474,8 @@ def main():
         if ms_train is not None:
             line["train_step"] = {"ms_per_step": round(ms_train, 4), "images_per_s": round(world * N / (ms_train / 1e3), 1),
                                   "what": "fwd + CTC loss/grad + backward + " + ((f"NCCL all-reduce(28.6 MB f32) in buckets >= {args.bucket_mb:g} MB overlapped with the backward ({args.sm_reserve} SMs reserved) + " if args.overlap else "one NCCL all-reduce(28.6 MB f32) after the backward + ") +
-                                          ("global-batch BatchNorm (sums exchanged inside the BN kernels over NVLink peer memory) fwd/bwd + " if not args.no_sync_bn else "") if world > 1 else "") +
+                                          (("global-batch BatchNorm (sums exchanged inside the BN kernels over NVLink peer memory) fwd/bwd + " if (dp is not None and dp.peer)
+                                            else "global-batch BatchNorm (sums through an NCCL all-reduce callback) fwd/bwd + ") if not args.no_sync_bn else "") if world > 1 else "") +
                                           "global-norm clip + Adam (BASELINE configs[4] per-GPU shape)",
                                   "stages_ms": bwd_stage_ms, "forward_stages_train_mode_ms": fwd_train_stage_ms}
         if world == 1 and not args.no_cpu_baseline:

@@ -217,10 +217,10 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   double* sums41 = pl.bn_bwd_sums;
   double* gsum42 = m->dp_world > 1 ? pl.bn_bwd_sums + 3072 : sums42;
   double* gsum41 = m->dp_world > 1 ? pl.bn_bwd_sums + 2048 : sums41;
-  CRNN_TRY(launch_bn_bwd_reduce(true, pl.d_a4b, pl.a4b_pre, pl.d_pre4b, pl.bn + 2048, sums42, P4 / 2, 512, st));
+  CRNN_TRY(launch_bn_bwd_reduce(true, pl.d_a4b, pl.a4b_pre, pl.bn + 2048, sums42, P4 / 2, 512, st));
   if (m->dp_world > 1) CRNN_TRY(dp_allreduce_1024(m, sums42, gsum42, st));
-  CRNN_TRY(launch_bn_bwd_apply(pl.d_pre4b, pl.a4b_pre, pl.bn + 2048, m->P("conv4_2/conv4_2/gamma"), gsum42, sums42, P4g, P4,
-                               512, pl.bn_bwd_coef, G("conv4_2/conv4_2/gamma"), G("conv4_2/conv4_2/beta"), st));
+  CRNN_TRY(launch_bn_bwd_apply(true, pl.d_a4b, pl.a4b_pre, pl.d_pre4b, pl.bn + 2048, m->P("conv4_2/conv4_2/gamma"), gsum42, sums42, P4g,
+                               P4 / 2, 512, pl.bn_bwd_coef, G("conv4_2/conv4_2/gamma"), G("conv4_2/conv4_2/beta"), st));
   // conv4_2/biases: a bias in front of a batch-statistics BatchNorm has an analytically ZERO gradient (the BN backward projects
   // the column sums of d(pre-BN) out); it stays at the zero the buffer was cleared to instead of summing 134 MB of rounding noise
   BMARK();
@@ -239,9 +239,9 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   }
   BMARK();
   // ------------------------------------------------------------------ conv4_1: ReLU + BN backward
-  CRNN_TRY(launch_bn_bwd_reduce(false, pl.d_pre4a, pl.a4a_pre, pl.d_pre4a, pl.bn, sums41, P4, 512, st));
+  CRNN_TRY(launch_bn_bwd_reduce(false, pl.d_pre4a, pl.a4a_pre, pl.bn, sums41, P4, 512, st));
   if (m->dp_world > 1) CRNN_TRY(dp_allreduce_1024(m, sums41, gsum41, st));
-  CRNN_TRY(launch_bn_bwd_apply(pl.d_pre4a, pl.a4a_pre, pl.bn, m->P("conv4_1/conv4_1/gamma"), gsum41, sums41, P4g, P4, 512,
+  CRNN_TRY(launch_bn_bwd_apply(false, pl.d_pre4a, pl.a4a_pre, pl.d_pre4a, pl.bn, m->P("conv4_1/conv4_1/gamma"), gsum41, sums41, P4g, P4, 512,
                                pl.bn_bwd_coef, G("conv4_1/conv4_1/gamma"), G("conv4_1/conv4_1/beta"), st));
   // conv4_1/biases: analytically zero as well (see conv4_2)
   BMARK();
@@ -298,7 +298,14 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   CRNN_TRY(launch_unpool_relu_bwd(4, pl.d_a2, pl.a2, pl.am2, pl.d_pre2, (size_t)N * H2 * 8, H2, 8, 128, st));
   CRNN_TRY(launch_colsum_masked_bf16(pl.d_a2, pl.a2, (long long)N * H2 * 8, 128, G("conv2/biases"), st));
   BMARK();
-  {
+  if (m->conv2_wgrad_swap) {
+    // operands swapped (r2): A = d(pre-activation) [positions x 128 co] on the M side, B = a1 with FOUR tap-shifted 64-channel boxes
+    // per 256-column N tile (columns = (tap, ci)); 3 N tiles cover the 9 taps.  N = 256 runs the MMA at full rate where the
+    // Cout = 128 N tile of the straight formulation halves it (0.66 ms for 309 GFLOP).
+    gemm_tn::Params p = tn_conv(N, H1, 16, 64, 128, G("conv2/weights"), pl.wm2);
+    p.tap_pack_n = 1; p.num_taps = 1; p.num_m_tiles = 1; p.num_n_tiles = 3; p.M = 128; p.N = 9 * 64; p.ldo = 128; p.tap_stride = 0;
+    CRNN_TRY((launch_gemm_tn<256, gemm_tn::TN_CONV, 4>(pl.tW_p2, pl.tW_a1, p, sms, st)));
+  } else {
     gemm_tn::Params p = tn_conv(N, H1, 16, 64, 128, G("conv2/weights"), pl.wm2);
     p.num_n_tiles = 1;
     // Cin = 64 fills only half of a 128-row MMA tile: view dW [9*64, 128] as ONE matrix and let each tile hold two taps

@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   }
 }
 
-// ---- BatchNorm (+ReLU, + optional 1x2 max-pool) backward, pass 1:
+// ---- BatchNorm (+ReLU, + optional 1x2 max-pool) backward, pass 1 (sums only -- r2: the routed gradient dy is NOT written here
+// any more; pass 2 re-derives it from the same two inputs, which saves one 268 MB write + one 268 MB read per BN layer):
 //   dy = routed upstream gradient at the pre-BN resolution, masked by ReLU;  sums[c] += dy, sums[C + c] += dy * xhat
 // POOL = true (conv4_2 / pool3): dout is [P, Wp/2.., C] pooled; x_pre is [P*2 positions..]; the max is re-derived from
 // the saved pre-BN tensor (first position wins ties).  POOL = false (conv4_1): dout has the same shape as x_pre.
@@ -163,8 +164,6 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
         s1[i] += gy;
         s2[i] += d0[i] * (x0[i] - mu[i]) * is[i] + d1[i] * (x1[i] - mu[i]) * is[i];
       }
-      dy[(2 * pos) * vpc + cv] = pack8(d0);
-      dy[(2 * pos + 1) * vpc + cv] = pack8(d1);
     } else {
       float x[8], d[8];
       unpack8(cx0, x);
@@ -175,7 +174,6 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
         s1[i] += d[i];
         s2[i] += d[i] * (x[i] - mu[i]) * is[i];
       }
-      dy[pos * vpc + cv] = pack8(d);
     }
   }
   // block reduction over the rows_per_block row groups, then one f64 atomic per channel per block
@@ -211,26 +209,57 @@ __global__ void bn_bwd_coef_kernel(const float* __restrict__ bn, const float* __
   dbeta[c] += (float)sums_local[c];
   dgamma[c] += (float)sums_local[C + c];
 }
-// pass 2b: elementwise, in place on dy
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(uint4* __restrict__ dy, const uint4* __restrict__ x_pre,
-                                                           const float* __restrict__ coef, size_t nvec, int C) {
+// pass 2b: dx = A*dy + B + C*x with dy re-derived from (dout, x_pre) exactly as pass 1 derived it (the masked / routed values are
+// copies of bf16 inputs, so both passes see identical numbers).  POOL: one thread per POOLED position and 8 channels, writes the
+// two pre-pool positions; else elementwise (dx may alias dout).
+template <bool POOL>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* dout, const uint4* __restrict__ x_pre,
+                                                           const float* __restrict__ bn, const float* __restrict__ coef,
+                                                           uint4* dx, size_t nvec_out, int C) {
   const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i0 >= nvec) return;
-  const int c = (int)((i0 * 8) % C);
-  float d[8], x[8], A[8], B[8], Cc[8];
-  unpack8(dy[i0], d);
-  unpack8(__ldg(x_pre + i0), x);
+  if (i0 >= nvec_out) return;
+  const int vpc = C / 8;
+  const size_t pos = i0 / vpc;
+  const int cv = (int)(i0 - pos * vpc);
+  const int c = cv * 8;
+  float g[8], A[8], B[8], Cc[8], sc[8], sh[8];
+  unpack8(POOL ? __ldg(dout + i0) : dout[i0], g);          // !POOL: dx aliases dout (same element, read before written)
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const float4 a4 = __ldg(reinterpret_cast<const float4*>(coef + c) + h), b4 = __ldg(reinterpret_cast<const float4*>(coef + C + c) + h),
                  c4 = __ldg(reinterpret_cast<const float4*>(coef + 2 * C + c) + h);
+    const float4 s4 = __ldg(reinterpret_cast<const float4*>(bn + c) + h), h4 = __ldg(reinterpret_cast<const float4*>(bn + C + c) + h);
     A[4 * h] = a4.x; A[4 * h + 1] = a4.y; A[4 * h + 2] = a4.z; A[4 * h + 3] = a4.w;
     B[4 * h] = b4.x; B[4 * h + 1] = b4.y; B[4 * h + 2] = b4.z; B[4 * h + 3] = b4.w;
     Cc[4 * h] = c4.x; Cc[4 * h + 1] = c4.y; Cc[4 * h + 2] = c4.z; Cc[4 * h + 3] = c4.w;
+    sc[4 * h] = s4.x; sc[4 * h + 1] = s4.y; sc[4 * h + 2] = s4.z; sc[4 * h + 3] = s4.w;
+    sh[4 * h] = h4.x; sh[4 * h + 1] = h4.y; sh[4 * h + 2] = h4.z; sh[4 * h + 3] = h4.w;
   }
+  if (POOL) {
+    float x0[8], x1[8], o0[8], o1[8];
+    unpack8(__ldg(x_pre + (2 * pos) * vpc + cv), x0);
+    unpack8(__ldg(x_pre + (2 * pos + 1) * vpc + cv), x1);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) d[i] = fmaf(A[i], d[i], fmaf(Cc[i], x[i], B[i]));
-  dy[i0] = pack8(d);
+    for (int i = 0; i < 8; ++i) {
+      const float y0 = __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(x0[i], sc[i], sh[i]), 0.f)));
+      const float y1 = __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(x1[i], sc[i], sh[i]), 0.f)));
+      const bool first = (y0 >= y1);
+      const float gy = ((first ? y0 : y1) > 0.f) ? g[i] : 0.f;
+      o0[i] = fmaf(A[i], first ? gy : 0.f, fmaf(Cc[i], x0[i], B[i]));
+      o1[i] = fmaf(A[i], first ? 0.f : gy, fmaf(Cc[i], x1[i], B[i]));
+    }
+    dx[(2 * pos) * vpc + cv] = pack8(o0);
+    dx[(2 * pos + 1) * vpc + cv] = pack8(o1);
+  } else {
+    float x[8], o[8];
+    unpack8(__ldg(x_pre + i0), x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float y = fmaf(x[i], sc[i], sh[i]);
+      o[i] = fmaf(A[i], (y > 0.f) ? g[i] : 0.f, fmaf(Cc[i], x[i], B[i]));
+    }
+    dx[i0] = pack8(o);
+  }
 }
 
 // ---- ReLU backward in place: d *= (a > 0)       (conv3_1)
@@ -535,19 +564,21 @@ int launch_colsum_masked_bf16(const __nv_bfloat16* src, const __nv_bfloat16* mas
   colsum_bf16_kernel<<<grid, 256, 0, st>>>(src, mask, Rv, Cv, Cmod, out, 0, 0);
   LAUNCH_CHECK();
 }
-int launch_bn_bwd_reduce(bool pool, const __nv_bfloat16* dout, const __nv_bfloat16* x_pre, __nv_bfloat16* dy, const float* bn,
-                         double* sums, size_t out_positions, int C, cudaStream_t st) {
-  if (pool) bn_bwd_reduce_kernel<true><<<592, 256, 0, st>>>((const uint4*)dout, (const uint4*)x_pre, (uint4*)dy, bn, sums, out_positions, C);
-  else bn_bwd_reduce_kernel<false><<<592, 256, 0, st>>>((const uint4*)dout, (const uint4*)x_pre, (uint4*)dy, bn, sums, out_positions, C);
+int launch_bn_bwd_reduce(bool pool, const __nv_bfloat16* dout, const __nv_bfloat16* x_pre, const float* bn, double* sums,
+                         size_t out_positions, int C, cudaStream_t st) {
+  if (pool) bn_bwd_reduce_kernel<true><<<592, 256, 0, st>>>((const uint4*)dout, (const uint4*)x_pre, nullptr, bn, sums, out_positions, C);
+  else bn_bwd_reduce_kernel<false><<<592, 256, 0, st>>>((const uint4*)dout, (const uint4*)x_pre, nullptr, bn, sums, out_positions, C);
   LAUNCH_CHECK();
 }
-int launch_bn_bwd_apply(__nv_bfloat16* dy, const __nv_bfloat16* x_pre, const float* bn, const float* gamma, const double* sums,
-                        const double* sums_local, double count, size_t positions, int C, float* coef, float* dgamma, float* dbeta,
-                        cudaStream_t st) {
-  const size_t nvec = positions * C / 8;
+// dx = BN/ReLU(/pool) backward of dout; out_positions = positions of dout (pooled positions when pool); dx may alias dout when !pool
+int launch_bn_bwd_apply(bool pool, const __nv_bfloat16* dout, const __nv_bfloat16* x_pre, __nv_bfloat16* dx, const float* bn,
+                        const float* gamma, const double* sums, const double* sums_local, double count, size_t out_positions, int C,
+                        float* coef, float* dgamma, float* dbeta, cudaStream_t st) {
+  const size_t nvec = out_positions * C / 8;
   bn_bwd_coef_kernel<<<(C + 127) / 128, 128, 0, st>>>(bn, gamma, sums, sums_local, count, C, coef, dgamma, dbeta);
   CUDA_TRY(cudaGetLastError());
-  bn_bwd_apply_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, st>>>((uint4*)dy, (const uint4*)x_pre, coef, nvec, C);
+  if (pool) bn_bwd_apply_kernel<true><<<(unsigned)((nvec + 255) / 256), 256, 0, st>>>((const uint4*)dout, (const uint4*)x_pre, bn, coef, (uint4*)dx, nvec, C);
+  else bn_bwd_apply_kernel<false><<<(unsigned)((nvec + 255) / 256), 256, 0, st>>>((const uint4*)dout, (const uint4*)x_pre, bn, coef, (uint4*)dx, nvec, C);
   LAUNCH_CHECK();
 }
 int launch_relu_bwd(__nv_bfloat16* d, const __nv_bfloat16* a, size_t n, cudaStream_t st) {

@@ -11,11 +11,11 @@ struct WdSegs {
 int launch_dlogits_rows(const float* dlogits, __nv_bfloat16* rows, float* dbias, int T, int N, int H, cudaStream_t st);
 int launch_colsum_bf16(const __nv_bfloat16* src, long long R, int C, float* out, int perm_upc, long long dir_stride, cudaStream_t st);
 int launch_colsum_masked_bf16(const __nv_bfloat16* src, const __nv_bfloat16* mask, long long R, int C, float* out, cudaStream_t st);
-int launch_bn_bwd_reduce(bool pool, const __nv_bfloat16* dout, const __nv_bfloat16* x_pre, __nv_bfloat16* dy, const float* bn,
-                         double* sums, size_t out_positions, int C, cudaStream_t st);
-int launch_bn_bwd_apply(__nv_bfloat16* dy, const __nv_bfloat16* x_pre, const float* bn, const float* gamma, const double* sums,
-                        const double* sums_local, double count, size_t positions, int C, float* coef, float* dgamma, float* dbeta,
-                        cudaStream_t st);
+int launch_bn_bwd_reduce(bool pool, const __nv_bfloat16* dout, const __nv_bfloat16* x_pre, const float* bn, double* sums,
+                         size_t out_positions, int C, cudaStream_t st);
+int launch_bn_bwd_apply(bool pool, const __nv_bfloat16* dout, const __nv_bfloat16* x_pre, __nv_bfloat16* dx, const float* bn,
+                        const float* gamma, const double* sums, const double* sums_local, double count, size_t out_positions, int C,
+                        float* coef, float* dgamma, float* dbeta, cudaStream_t st);
 int launch_relu_bwd(__nv_bfloat16* d, const __nv_bfloat16* a, size_t n, cudaStream_t st);
 int launch_unpool_relu_bwd(int win, const __nv_bfloat16* dpool, const __nv_bfloat16* pooled, const uint8_t* argmax,
                            __nv_bfloat16* dpre, size_t out_positions, int Hp, int Wp, int C, cudaStream_t st);

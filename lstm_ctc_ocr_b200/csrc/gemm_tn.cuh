@@ -35,6 +35,10 @@ struct Params {
   int sb_per_img, bh, Wd, H, Nimg, Cin;
   int merged, kb_per_img;                    // TN_CONV: 64-position boxes (2*bh rows) when H % (2*bh) == 0
   int tap_pack;                              // TN_CONV with Cin == 64: an M tile packs TWO taps (rows = (tap, ci)) -> 5 tiles, not 9 half-empty ones
+  int tap_pack_n;                            // TN_CONV with Cin == 64, operands SWAPPED (r2, conv2 weight gradient): A = the output gradient
+                                             // (M = Cout), B = the activation with FOUR tap-shifted 64-channel boxes per 256-column N tile
+                                             // (columns = (tap, ci)); N = 256 restores the MMA rate the Cout = 128 N tile halves.  The
+                                             // accumulator is written transposed: out[(tap*64 + ci) * ldo + co]
   int a_row_shift;                           // TN_PLAIN: A rows are read at k + a_row_shift (conv5's second tap)
   // output
   float* out;
@@ -126,9 +130,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         decode(item, tap, m_blk, n_blk, kb0, kb1);
         int r = tap / 3, s = tap - 3 * r;
         int ccol = isA ? (m_blk * BLOCK_M + 64 * j) : (n_blk * BLOCK_N + 64 * j);
+        bool shifted = isA;                                 // which operand's boxes carry the (r-1, s-1) tap shift
         if (AMODE == TN_CONV && p.tap_pack && isA) {       // A block j of tile m_blk is tap 2*m_blk + j, channels 0..63
           const int tp = min(2 * m_blk + j, 8);             // the 10th (non-existent) tap re-reads tap 8; its rows are masked
           r = tp / 3; s = tp - 3 * r; ccol = 0;
+        }
+        if (AMODE == TN_CONV && p.tap_pack_n) {            // B block j of tile n_blk is tap 4*n_blk + j (taps >= 9: columns masked)
+          shifted = !isA;
+          if (!isA) { const int tp = min(4 * n_blk + j, 8); r = tp / 3; s = tp - 3 * r; ccol = 0; }
         }
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -141,14 +150,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // 64 consecutive positions = 2*bh rows of one image in one box
             const int n = kb / p.kb_per_img;
             const int h0 = (kb - n * p.kb_per_img) * 2 * p.bh;
-            ptx::tma_load_4d(tm, &full_bar[stage], dst, ccol, isA ? s - 1 : 0, h0 + (isA ? r - 1 : 0), n);
+            ptx::tma_load_4d(tm, &full_bar[stage], dst, ccol, shifted ? s - 1 : 0, h0 + (shifted ? r - 1 : 0), n);
           } else {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               const int g = kb * 2 + half;                     // 32-position sub-box index
               const int n = g / p.sb_per_img;
               const int h0 = (g - n * p.sb_per_img) * p.bh;
-              ptx::tma_load_4d(tm, &full_bar[stage], dst + half * 4096, ccol, isA ? s - 1 : 0, h0 + (isA ? r - 1 : 0), n);
+              ptx::tma_load_4d(tm, &full_bar[stage], dst + half * 4096, ccol, shifted ? s - 1 : 0, h0 + (shifted ? r - 1 : 0), n);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -202,6 +211,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(tbase + c0, v);
         ptx::tmem_ld_wait();
+        if (AMODE == TN_CONV && p.tap_pack_n) {
+          // swapped operands: row = output channel co, column = (tap, ci).  Written transposed into the HWIO gradient
+          // out[(tap*64 + ci) * ldo + co]; the lanes of a warp are consecutive co -> one 128-byte segment per instruction
+          const int tp = 4 * n_blk + (c0 >> 6), ci0 = c0 & 63;
+          if (okm && tp < 9) {
+            float* dst = p.out + (long long)(tp * 64 + ci0) * p.ldo + m;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(dst + (long long)i * p.ldo, __uint_as_float(v[i]));
+          }
+          continue;
+        }
         const int ncol = n_blk * BLOCK_N + c0;
         if (okm && ncol < p.N) {
           float* dst;
@@ -213,8 +233,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             dst = orow + ncol;
           }
+          // split-K reduction straight into the gradient tensor: 128-bit vector reds (a quarter of the L2 atomic transactions of
+          // scalar atomicAdd; every destination is 16-byte aligned: tensor offsets, row strides and column starts are multiples of 4)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) atomicAdd(dst + i, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; i += 4)
+            ptx::red_add_v4_f32(dst + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
         }
       }
       ptx::tc_fence_before();
@@ -382,8 +405,11 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           } else {
             dst = orow + ncol;
           }
+          // split-K reduction straight into the gradient tensor: 128-bit vector reds (a quarter of the L2 atomic transactions of
+          // scalar atomicAdd; every destination is 16-byte aligned: tensor offsets, row strides and column starts are multiples of 4)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) atomicAdd(dst + i, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; i += 4)
+            ptx::red_add_v4_f32(dst + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
         }
       }
       ptx::tc_fence_before();

@@ -155,6 +155,7 @@ extern "C" int crnn_model_create(const crnn_config* cfg, crnn_model** out) {
   if (const char* e = getenv("CRNN_GEMM2")) m->use_2cta = std::string(e) != "0";
   if (const char* e = getenv("CRNN_BPTT")) m->bptt_ks = std::string(e) != "ring";        // debug A/B switch
   if (const char* e = getenv("CRNN_CONV1")) m->conv1_tc = std::string(e) != "simt";    // debug A/B switch
+  if (const char* e = getenv("CRNN_CONV2_WGRAD")) m->conv2_wgrad_swap = std::string(e) != "old";   // debug A/B switch
   if (const char* e = getenv("CRNN_CONV2")) m->conv2_swap = std::string(e) != "pos";    // debug A/B switch: "pos" = position-major gemm.cuh kernel
   if (const char* e = getenv("CRNN_LSTM_IMPL")) {                                                      // debug A/B switch
     m->lstm_upc = (std::string(e) == "step") ? 64 : 32;

@@ -94,6 +94,7 @@ struct crnn_model {
   CUtensorMap tBh_c2, tBh_c31, tBh_c32, tBh_c41, tBh_c42, tBh_c5, tBh_x;   // same weights, box = 128 rows: per-CTA half of a 256-row N tile
   bool use_2cta = true;      // cta_group::2 GEMM pairs for the Nc % 256 == 0 layers (CRNN_GEMM2=0 disables; debug A/B switch)
   bool conv1_tc = true;      // conv1 + pool1 on the tensor cores (conv1_tc.cuh, split-bf16 operands); CRNN_CONV1=simt -> kernels.cu
+  bool conv2_wgrad_swap = true;   // conv2 weight gradient with swapped operands + 4 taps per N tile (gemm_tn.cuh tap_pack_n); CRNN_CONV2_WGRAD=old -> 2 taps per M tile
   bool conv2_swap = true;    // conv2 with channels on the MMA M side and 256 positions on N (conv_swap.cuh); CRNN_CONV2=pos -> gemm.cuh
   int lstm_mc = 3;           // recurrence through lstm::lstm_mc_kernel (no per-step cluster barrier): 1 = global slice + multicast bulk copy
                              // (CRNN_LSTM_IMPL=mc), 2 = slices pushed smem -> peer smem (CRNN_LSTM_IMPL=ds),

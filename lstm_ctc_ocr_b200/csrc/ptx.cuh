@@ -105,6 +105,11 @@ __device__ __forceinline__ void tma_load_4d(const void* tmap, uint64_t* bar, voi
       : "memory");
 }
 
+// 128-bit vector reduction into global memory (PTX ISA 8.1, sm_90+): one L2 atomic transaction for 4 consecutive floats
+__device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // smem tile -> global through a tensor map (bulk async group; complete with bulk_commit / bulk_wait_read_all)
 __device__ __forceinline__ void tma_store_4d(const void* tmap, const void* src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
