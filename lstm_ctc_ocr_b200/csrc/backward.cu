@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include "backward_kernels.cuh"
+#include "conv_swap.cuh"
 #include "gemm_launch.h"
 #include "kernels.cuh"
 #include "lstm_bwd.cuh"
@@ -30,6 +31,7 @@ extern "C" int crnn_model_set_training(crnn_model* m, int flag) {
     CRNN_TRY(make_tmap_2d(&m->tD_c32, m->Bd_c32, 256, 2304, 2304, 256));
     CRNN_TRY(make_tmap_2d(&m->tD_c31, m->Bd_c31, 128, 2304, 2304, 128));
     CRNN_TRY(make_tmap_2d(&m->tD_c2, m->Bd_c2, 64, 1152, 1152, 64));
+    CRNN_TRY(make_tmap_2d(&m->tDs_c2, m->Bd_c2, 64, 1152, 1152, 128));
     CRNN_TRY(make_tmap_2d(&m->tD_c5, m->Bd_c5, 1024, 1024, 1024, 256));
     CRNN_TRY(make_tmap_2d(&m->tD_l, m->Bld, 512, 64, 64, 256));
     CRNN_TRY(make_tmap_2d(&m->tD_x, m->Bxb, 512, 2048, 2048, 256));
@@ -313,7 +315,11 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
     CRNN_TRY((launch_gemm_tn<128, gemm_tn::TN_CONV, 6>(pl.tW_a1, pl.tW_p2, p, sms, st)));
   }
   BMARK();
-  {
+  if (m->conv2_dgrad_swap) {
+    convsw::DgradParams p;
+    p.Nimg = N; p.H = H1; p.tiles_per_img = (H1 + 15) / 16; p.out = pl.d_a1;
+    CRNN_TRY(launch_conv2_dgrad_swap(pl.tG_p2s, m->tDs_c2, p, sms, st));
+  } else {
     gemm::Params p = conv_params(N, H1, 16, 128, 64, 64, nullptr, pl.d_a1, pl.mg2);
     CRNN_TRY((launch_gemm<64, gemm::A_CONV3, gemm::EPI_CONV_STORE, 8>(pl.tG_p2, m->tD_c2, p, sms, st)));
   }

@@ -176,11 +176,164 @@ conv2_swap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// conv2 DATA gradient with the same operand swap (r2).  d_a1[p, ci] = sum over taps, co of d_pre2[p + tap', co] * W'[ci][(tap', co)]
+// is a 3x3 SAME convolution of the [N, H, 16, 128] gradient with the flipped / transposed kernel (Bd_c2, backward_kernels.cu):
+// only 64 output channels.  Position-major (gemm.cuh, BLOCK_N = 64) it ran the MMA at N = 64, a quarter of the 128x256x16 rate
+// (0.60 ms for 309 GFLOP).  Here the 64 channels sit on the M side (rows 64..127 of the weight box are out of bounds of the
+// tensor map, i.e. zero-filled by TMA: half of the M = 128 MMA is padding) and N is 256 positions: half the padded work at the
+// full rate.  K-blocks = 9 taps x 2 blocks of 64 gradient channels.  Epilogue: lane = input channel (quadrants 0 and 1 only),
+// column = position; plain bf16 store (the ReLU / pool1 backward is folded into conv1's weight-gradient kernel).
+// ---------------------------------------------------------------------------------------------------------------------------
+struct DgradParams {
+  int Nimg, H;            // gradient [Nimg, H, 16, 128] -> d_a1 [Nimg, H, 16, 64]
+  int tiles_per_img;      // ceil(H / 16)
+  __nv_bfloat16* out;
+};
+
+static __global__ void __launch_bounds__(NUM_THREADS, 1)
+conv2_dgrad_swap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const DgradParams p) {
+  constexpr uint32_t IDESC = ptx::make_idesc_bf16(128, 256);
+  constexpr int NUM_KB = 18;                 // 9 taps x 2 channel blocks
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.Nimg * p.tiles_per_img;
+
+  if (warp_idx == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmX);
+    ptx::prefetch_tmap(&tmW);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tmem_full[s], 1);
+      ptx::mbar_init(&tmem_empty[s], NUM_EPI_WARPS);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp_idx == 1) {
+    ptx::tmem_alloc(tmem_ptr, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp_idx == 0) {
+    if (lane < 3) {                          // lanes 0/1: the two 128-position gradient boxes, lane 2: the weight box
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n = tile / p.tiles_per_img;
+        const int h0 = (tile - n * p.tiles_per_img) * 16;
+        for (int kb = 0; kb < NUM_KB; ++kb) {
+          const int tap = kb >> 1, cb = kb & 1;
+          const int r = tap / 3, sx = tap - 3 * r;
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * STAGE_BYTES;
+          if (lane == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          if (lane < 2) ptx::tma_load_4d(&tmX, &full_bar[stage], st + W_BYTES + lane * (X_BYTES / 2), cb * 64, sx - 1, h0 + lane * 8 + r - 1, n);
+          else ptx::tma_load_2d(&tmW, &full_bar[stage], st, kb * 64, 0);       // rows 64..127: out of bounds -> zero fill
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp_idx == 1) {
+    if (lane == 0) {
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        ptx::mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < NUM_KB; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t a_desc = ptx::make_desc_k_sw128(ptx::smem_u32(smem + stage * STAGE_BYTES));
+          const uint64_t b_desc = ptx::make_desc_k_sw128(ptx::smem_u32(smem + stage * STAGE_BYTES + W_BYTES));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0);
+          ptx::tc_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::tc_commit(&tmem_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp_idx & 3;
+    const int ch = (warp_idx - 2) >> 2;      // column half: 8 of the tile's 16 H-rows
+    const int c = q * 32 + lane;              // input channel of this thread (valid for q < 2)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int n = tile / p.tiles_per_img;
+      const int h0 = (tile - n * p.tiles_per_img) * 16;
+      const int acc = it & 1;
+      ptx::mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      if (q < 2) {
+        const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + ch * 128;
+#pragma unroll 1
+        for (int pr = 0; pr < 4; ++pr) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(tbase + pr * 32, v);     // columns: [row h (16 w) | row h+1 (16 w)]
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int hr = 0; hr < 2; ++hr) {
+            const int h = h0 + ch * 8 + 2 * pr + hr;
+            if (h < p.H) {
+              __nv_bfloat16* o = p.out + (((size_t)n * p.H + h) * 16) * 64 + c;
+#pragma unroll
+              for (int w = 0; w < 16; ++w) o[(size_t)w * 64] = __float2bfloat16_rn(__uint_as_float(v[hr * 16 + w]));
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace convsw
 
 template <bool TRAIN>
 static int launch_conv2_swap(const CUtensorMap& x, const CUtensorMap& w, const convsw::Params& p, int num_sms, cudaStream_t st) {
   auto kern = convsw::conv2_swap_kernel<TRAIN>;
+  static bool attr = false;
+  if (!attr) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, convsw::SMEM_BYTES));
+    attr = true;
+  }
+  const int tiles = p.Nimg * p.tiles_per_img;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, convsw::NUM_THREADS, convsw::SMEM_BYTES, st>>>(x, w, p);
+  CUDA_TRY(cudaGetLastError());
+  return CRNN_OK;
+}
+
+static int launch_conv2_dgrad_swap(const CUtensorMap& x, const CUtensorMap& w, const convsw::DgradParams& p, int num_sms, cudaStream_t st) {
+  auto kern = convsw::conv2_dgrad_swap_kernel;
   static bool attr = false;
   if (!attr) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, convsw::SMEM_BYTES));
