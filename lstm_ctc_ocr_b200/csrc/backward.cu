@@ -291,7 +291,13 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   }
   notify("conv3_1/weights", "conv3_2/weights");
   BMARK();
-  {
+  if (m->conv2_dgrad_swap) {
+    // conv3_1's data gradient has 128 output channels: position-major it is an N = 128 tile (half the MMA rate); swapped, the 128
+    // channels fill the M side and N is 256 positions (32 H rows x 8)
+    convsw::DgradParams p;
+    p.Nimg = N; p.H = H2; p.tiles_per_img = (H2 + 31) / 32; p.out = pl.d_a2;
+    CRNN_TRY((launch_conv_dgrad_swap<8, 4, 128>(pl.tG_p31s, m->tD_c31, p, sms, st)));
+  } else {
     gemm::Params p = conv_params(N, H2, 8, 256, 128, 128, nullptr, pl.d_a2, pl.mg3);
     CRNN_TRY((launch_gemm<128, gemm::A_CONV3, gemm::EPI_CONV_STORE, 6>(pl.tG_p31, m->tD_c31, p, sms, st)));
   }
@@ -318,7 +324,7 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   if (m->conv2_dgrad_swap) {
     convsw::DgradParams p;
     p.Nimg = N; p.H = H1; p.tiles_per_img = (H1 + 15) / 16; p.out = pl.d_a1;
-    CRNN_TRY(launch_conv2_dgrad_swap(pl.tG_p2s, m->tDs_c2, p, sms, st));
+    CRNN_TRY((launch_conv_dgrad_swap<16, 2, 64>(pl.tG_p2s, m->tDs_c2, p, sms, st)));
   } else {
     gemm::Params p = conv_params(N, H1, 16, 128, 64, 64, nullptr, pl.d_a1, pl.mg2);
     CRNN_TRY((launch_gemm<64, gemm::A_CONV3, gemm::EPI_CONV_STORE, 8>(pl.tG_p2, m->tD_c2, p, sms, st)));

@@ -178,7 +178,7 @@ conv2_swap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// conv2 DATA gradient with the same operand swap (r2).  d_a1[p, ci] = sum over taps, co of d_pre2[p + tap', co] * W'[ci][(tap', co)]
+// DATA gradients of the narrow layers (conv2: 64 input channels, conv3_1: 128) with the same operand swap (r2).  conv2:  d_a1[p, ci] = sum over taps, co of d_pre2[p + tap', co] * W'[ci][(tap', co)]
 // is a 3x3 SAME convolution of the [N, H, 16, 128] gradient with the flipped / transposed kernel (Bd_c2, backward_kernels.cu):
 // only 64 output channels.  Position-major (gemm.cuh, BLOCK_N = 64) it ran the MMA at N = 64, a quarter of the 128x256x16 rate
 // (0.60 ms for 309 GFLOP).  Here the 64 channels sit on the M side (rows 64..127 of the weight box are out of bounds of the
@@ -186,16 +186,21 @@ conv2_swap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 // full rate.  K-blocks = 9 taps x 2 blocks of 64 gradient channels.  Epilogue: lane = input channel (quadrants 0 and 1 only),
 // column = position; plain bf16 store (the ReLU / pool1 backward is folded into conv1's weight-gradient kernel).
 // ---------------------------------------------------------------------------------------------------------------------------
+// Templated on the geometry so that conv3_1's data gradient (Cin = 128: N = 128 position-major, half the MMA rate) takes the same
+// route: WD = positions per H row (16 / 8), CB = 64-channel blocks of the incoming gradient (2 / 4), MVALID = output channels (64 / 128).
 struct DgradParams {
-  int Nimg, H;            // gradient [Nimg, H, 16, 128] -> d_a1 [Nimg, H, 16, 64]
-  int tiles_per_img;      // ceil(H / 16)
+  int Nimg, H;            // gradient [Nimg, H, WD, 64*CB] -> [Nimg, H, WD, MVALID]
+  int tiles_per_img;      // ceil(H / (256 / WD))
   __nv_bfloat16* out;
 };
 
-static __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv2_dgrad_swap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const DgradParams p) {
+template <int WD, int CB, int MVALID>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_dgrad_swap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const DgradParams p) {
   constexpr uint32_t IDESC = ptx::make_idesc_bf16(128, 256);
-  constexpr int NUM_KB = 18;                 // 9 taps x 2 channel blocks
+  constexpr int NUM_KB = 9 * CB;             // 9 taps x CB channel blocks
+  constexpr int RT = 256 / WD;               // H rows per tile (two TMA boxes of RT/2 rows)
+  constexpr int RC = 32 / WD;                // H rows per 32-column accumulator chunk
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BAR_OFFSET);
@@ -235,15 +240,15 @@ conv2_dgrad_swap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n = tile / p.tiles_per_img;
-        const int h0 = (tile - n * p.tiles_per_img) * 16;
+        const int h0 = (tile - n * p.tiles_per_img) * RT;
         for (int kb = 0; kb < NUM_KB; ++kb) {
-          const int tap = kb >> 1, cb = kb & 1;
+          const int tap = kb / CB, cb = kb - tap * CB;
           const int r = tap / 3, sx = tap - 3 * r;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
           if (lane == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          if (lane < 2) ptx::tma_load_4d(&tmX, &full_bar[stage], st + W_BYTES + lane * (X_BYTES / 2), cb * 64, sx - 1, h0 + lane * 8 + r - 1, n);
-          else ptx::tma_load_2d(&tmW, &full_bar[stage], st, kb * 64, 0);       // rows 64..127: out of bounds -> zero fill
+          if (lane < 2) ptx::tma_load_4d(&tmX, &full_bar[stage], st + W_BYTES + lane * (X_BYTES / 2), cb * 64, sx - 1, h0 + lane * (RT / 2) + r - 1, n);
+          else ptx::tma_load_2d(&tmW, &full_bar[stage], st, kb * 64, 0);       // MVALID = 64: rows 64..127 out of bounds -> zero fill
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -274,29 +279,29 @@ conv2_dgrad_swap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     __syncwarp();
   } else {
     const int q = warp_idx & 3;
-    const int ch = (warp_idx - 2) >> 2;      // column half: 8 of the tile's 16 H-rows
-    const int c = q * 32 + lane;              // input channel of this thread (valid for q < 2)
+    const int ch = (warp_idx - 2) >> 2;      // column half: RT/2 of the tile's RT H-rows
+    const int c = q * 32 + lane;              // input channel of this thread (valid for c < MVALID)
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int n = tile / p.tiles_per_img;
-      const int h0 = (tile - n * p.tiles_per_img) * 16;
+      const int h0 = (tile - n * p.tiles_per_img) * RT;
       const int acc = it & 1;
       ptx::mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       ptx::tc_fence_after();
-      if (q < 2) {
+      if (q * 32 < MVALID) {
         const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + ch * 128;
 #pragma unroll 1
         for (int pr = 0; pr < 4; ++pr) {
           uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(tbase + pr * 32, v);     // columns: [row h (16 w) | row h+1 (16 w)]
+          ptx::tmem_ld_32x32b_x32(tbase + pr * 32, v);     // columns: RC consecutive H rows of WD positions each
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int hr = 0; hr < 2; ++hr) {
-            const int h = h0 + ch * 8 + 2 * pr + hr;
+          for (int hr = 0; hr < RC; ++hr) {
+            const int h = h0 + ch * (RT / 2) + pr * RC + hr;
             if (h < p.H) {
-              __nv_bfloat16* o = p.out + (((size_t)n * p.H + h) * 16) * 64 + c;
+              __nv_bfloat16* o = p.out + (((size_t)n * p.H + h) * WD) * MVALID + c;
 #pragma unroll
-              for (int w = 0; w < 16; ++w) o[(size_t)w * 64] = __float2bfloat16_rn(__uint_as_float(v[hr * 16 + w]));
+              for (int w = 0; w < WD; ++w) o[(size_t)w * MVALID] = __float2bfloat16_rn(__uint_as_float(v[hr * WD + w]));
             }
           }
         }
@@ -332,8 +337,9 @@ static int launch_conv2_swap(const CUtensorMap& x, const CUtensorMap& w, const c
   return CRNN_OK;
 }
 
-static int launch_conv2_dgrad_swap(const CUtensorMap& x, const CUtensorMap& w, const convsw::DgradParams& p, int num_sms, cudaStream_t st) {
-  auto kern = convsw::conv2_dgrad_swap_kernel;
+template <int WD, int CB, int MVALID>
+static int launch_conv_dgrad_swap(const CUtensorMap& x, const CUtensorMap& w, const convsw::DgradParams& p, int num_sms, cudaStream_t st) {
+  auto kern = convsw::conv_dgrad_swap_kernel<WD, CB, MVALID>;
   static bool attr = false;
   if (!attr) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, convsw::SMEM_BYTES));

@@ -365,6 +365,7 @@ static int build_plan(crnn_model* m, int N, int W, void* ws, cudaStream_t st) {
     CRNN_TRY(make_tmap_nhwc(&pl.tG_p31, pl.d_pre31, N, pl.H2, 8, 256, pl.mg3 ? 16 : 4));
     CRNN_TRY(make_tmap_nhwc(&pl.tG_p2, pl.d_pre2, N, pl.H1, 16, 128, pl.mg2 ? 8 : 2));
     CRNN_TRY(make_tmap_nhwc(&pl.tG_p2s, pl.d_pre2, N, pl.H1, 16, 128, 8));
+    CRNN_TRY(make_tmap_nhwc(&pl.tG_p31s, pl.d_pre31, N, pl.H2, 8, 256, 16));
     // weight-gradient (TN_CONV) views: 64-position boxes when two sub-boxes are contiguous rows of one image, else 32
     CRNN_TRY(make_tmap_nhwc(&pl.tW_a1, pl.a1, N, pl.H1, 16, 64, pl.wm2 ? 4 : 2));
     CRNN_TRY(make_tmap_nhwc(&pl.tW_p2, pl.d_pre2, N, pl.H1, 16, 128, pl.wm2 ? 4 : 2));

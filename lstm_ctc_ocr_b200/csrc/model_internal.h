@@ -64,7 +64,7 @@ struct Plan {
   float* bn_bwd_coef;                             // [3][512] scratch
   // K-major A maps of gradient buffers (data-gradient GEMMs)
   CUtensorMap tG_dl, tG_dz, tG_da5, tG_p4b, tG_p4a, tG_p32, tG_p31, tG_p2, tG_dzstate;
-  CUtensorMap tG_p2s;                             // d_pre2 through 128-position boxes regardless of H (conv2_dgrad_swap_kernel)
+  CUtensorMap tG_p2s, tG_p31s;                    // d_pre2 / d_pre31 through 128-position boxes regardless of H (conv_dgrad_swap_kernel)
   // MN-major (TN) maps: 2-D [rows, C] with 64x64 boxes, and the NHWC maps above reused for TN_CONV
   CUtensorMap tT_lstm_fw, tT_lstm_bw, tT_lstm_all, tT_dl, tT_a5, tT_dz, tT_dz_fw, tT_dz_bw, tT_a4b, tT_da5;
 };
@@ -96,7 +96,7 @@ struct crnn_model {
   CUtensorMap tBh_c2, tBh_c31, tBh_c32, tBh_c41, tBh_c42, tBh_c5, tBh_x;   // same weights, box = 128 rows: per-CTA half of a 256-row N tile
   bool use_2cta = true;      // cta_group::2 GEMM pairs for the Nc % 256 == 0 layers (CRNN_GEMM2=0 disables; debug A/B switch)
   bool conv1_tc = true;      // conv1 + pool1 on the tensor cores (conv1_tc.cuh, split-bf16 operands); CRNN_CONV1=simt -> kernels.cu
-  bool conv2_dgrad_swap = true;   // conv2 data gradient with swapped operands (conv_swap.cuh); CRNN_CONV2_DGRAD=old -> position-major N = 64
+  bool conv2_dgrad_swap = true;   // conv2 / conv3_1 data gradients with swapped operands (conv_swap.cuh); CRNN_CONV2_DGRAD=old -> position-major N = 64 / 128
   bool conv2_wgrad_swap = true;   // conv2 weight gradient with swapped operands + 4 taps per N tile (gemm_tn.cuh tap_pack_n); CRNN_CONV2_WGRAD=old -> 2 taps per M tile
   bool conv2_swap = true;    // conv2 with channels on the MMA M side and 256 positions on N (conv_swap.cuh); CRNN_CONV2=pos -> gemm.cuh
   int lstm_mc = 3;           // recurrence through lstm::lstm_mc_kernel (no per-step cluster barrier): 1 = global slice + multicast bulk copy
