@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- images/sec of the CRNN forward + CTC loss hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2shape|c1shape] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c2tf32|c2shape|c1shape] [--impl ours|reference]
 
 One "step" = conv stack -> BiLSTM -> logits -> CTC loss (+gradient, as warp-ctc's forward op computes it)
 -> mean + L2, over one synthetic batch.  Default workload = BASELINE.json configs[2] (1xB200 bf16 tcgen05 path,
@@ -26,6 +26,7 @@ WORKLOADS = {
     # name: (per-GPU batch, padded width, description)
     "c3": (1024, 256, "BASELINE configs[2]: bf16 tcgen05 conv+LSTM path, batch 1024, 32x256, fwd+CTC"),
     "c2": (256, 160, "BASELINE configs[1]: fp32-class CRNN fwd+CTC-loss (split-bf16 operands x3, f32 accumulate/elementwise), batch 256, 32x160"),
+    "c2tf32": (256, 160, "BASELINE configs[1]: fp32 CRNN fwd+CTC-loss on tcgen05 kind::tf32 operands (f32 accumulate/elementwise), batch 256, 32x160"),
     "c2shape": (256, 160, "BASELINE configs[1] shapes (batch 256, 32x160) on the bf16 path"),
     "c1shape": (32, 100, "BASELINE configs[0] shapes (batch 32, 32x100)"),
 }
@@ -210,8 +211,9 @@ def main():
     peaks = load_peaks()
 
     # ---- model with reference initialisers (random init; no checkpoints offline), identical on every rank
-    f32_path = args.workload == "c2"
-    model = engine.CrnnModel(weight_decay=1e-5, device=dev, compute_dtype="f32" if f32_path else "bf16")
+    f32_path = args.workload in ("c2", "c2tf32")
+    cdt = {"c2": "f32", "c2tf32": "tf32"}.get(args.workload, "bf16")     # engine.CrnnModel(compute_dtype=...)
+    model = engine.CrnnModel(weight_decay=1e-5, device=dev, compute_dtype=cdt)
     model.load_params(synthetic.init_params(3))
     if f32_path:
         args.no_train = True            # the f32-class path is forward + CTC only (BASELINE configs[1])
@@ -433,7 +435,8 @@ def main():
         line = {
             "metric": "text-line images/sec (fwd+CTC loss)", "value": round(value, 1), "unit": "images/s", "n_gpus": world,
             "steps": K, "warmup": Wm, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (bf16x3 split operands, f32 accumulate)" if f32_path else "bf16", "data": "synthetic",
+            "vs_baseline": None, "dtype": {"f32": "f32 (bf16x3 split operands, f32 accumulate)", "tf32": "tf32 (kind::tf32 operands, f32 accumulate)"}.get(cdt, "bf16"),
+            "data": "synthetic",
             "config": {"workload": desc, "batch_per_gpu": N, "global_batch": N * world, "width": W, "T": T,
                        "parallelism": (f"dp{world}: batch sharded over ranks; BatchNorm over the GLOBAL batch -- 2 exchanges of 8 KB per forward, "
                                        f"{'fused into the BN finalize kernel over NVLink peer memory' if (dp is not None and dp.peer) else 'NCCL all-reduce'}"
@@ -459,11 +462,15 @@ def main():
         if f32_path:
             # no per-stage events on this path: the whole step against the tensor peak of a 3-product contraction
             wt = N * GFLOP_PER_IMG(W) / ms_step
-            line["roofline"] = {"kernel": "whole step (gemm_kernel x3 products + f32 elementwise passes + per-step LSTM launches)", "bound": "tensor",
-                                "achieved": round(wt, 1), "peak": round(peaks["bf16_sustained"] / 3.0, 1), "unit": "TFLOP/s",
-                                "frac": round(wt / (peaks["bf16_sustained"] / 3.0), 3), "traffic": None,
-                                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 3 (each fp32-class product is three bf16 MMAs); "
-                                               "achieved counts the ALGORITHMIC flops once"}
+            div = 2.0 if cdt == "tf32" else 3.0
+            line["roofline"] = {"kernel": ("whole step (gemm_kernel kind::tf32 + f32 elementwise passes + per-step LSTM launches)" if cdt == "tf32" else
+                                           "whole step (gemm_kernel x3 products + f32 elementwise passes + per-step LSTM launches)"), "bound": "tensor",
+                                "achieved": round(wt, 1), "peak": round(peaks["bf16_sustained"] / div, 1), "unit": "TFLOP/s",
+                                "frac": round(wt / (peaks["bf16_sustained"] / div), 3), "traffic": None,
+                                "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (kind::tf32 issues at half the kind::f16 rate; no tf32 figure is measured)"
+                                                if cdt == "tf32" else
+                                                "MEASURED_PEAKS.json bf16_tflops_sustained / 3 (each fp32-class product is three bf16 MMAs); "
+                                                "achieved counts the ALGORITHMIC flops once")}
             line.pop("stages", None)
             line["gpu_launches"] = K * (1 + 2 * 6 + 4 + 2 + 2 * T + 4)
         if ms_fwd_sync is not None:
@@ -489,7 +496,7 @@ def main():
             # (the round-1 figure was taken on a model that had already run 13 Adam steps) against the fp64
             # oracle on the same seeded 32x256 samples, three seeds.
             try:
-                line["ctc_loss_delta"] = ctc_loss_delta(engine, synthetic, torch, dev, W, sn, compute_dtype="f32" if f32_path else "bf16")
+                line["ctc_loss_delta"] = ctc_loss_delta(engine, synthetic, torch, dev, W, sn, compute_dtype=cdt)
             except Exception as e:      # never lose the bench line over the side statistic
                 line["ctc_loss_delta"] = {"error": repr(e)[:300]}
             # BASELINE configs[3] / north-star: greedy-decode sequence equality with the oracle on 10k rendered lines, through the model
@@ -501,7 +508,7 @@ def main():
                     spec = importlib.util.spec_from_file_location("t10k", os.path.join(ROOT, "tests", "test_gpu_decode10k.py"))
                     t10k = importlib.util.module_from_spec(spec)
                     spec.loader.exec_module(t10k)
-                    st = t10k.run_decode10k("f32" if f32_path else "bf16", device=dev)
+                    st = t10k.run_decode10k(cdt, device=dev)
                     st.pop("per_width", None)
                     line["decode_equality"] = st
                 except Exception as e:

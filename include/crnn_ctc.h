@@ -94,7 +94,9 @@ typedef struct crnn_config {
   int   compute_dtype;  /* 1 = bf16 operands / f32 accumulate (tcgen05 kind::f16): the throughput path, forward + backward.
                          * 2 = f32-class: every operand split into bf16 hi + bf16 lo, three tcgen05 products per term, f32
                          *     accumulate and f32 elementwise math (the reference computes in fp32, LSTM_train.py:10);
-                         *     forward + CTC only (BASELINE configs[1]) */
+                         *     forward + CTC only (BASELINE configs[1])
+                         * 3 = tf32: the same forward-only orchestration on tcgen05 kind::tf32 operands (f32 tensors, rounded to
+                         *     nearest tf32 where produced; 10-bit mantissa, one pass over K at half the kind::f16 rate) */
 } crnn_config;
 
 int     crnn_model_create(const crnn_config* cfg, crnn_model** out);

@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include "backward_kernels.cuh"
+#include "conv1_wgrad_tc.cuh"
 #include "conv_swap.cuh"
 #include "gemm_launch.h"
 #include "kernels.cuh"
@@ -16,7 +17,7 @@
 
 extern "C" int crnn_model_set_training(crnn_model* m, int flag) {
   if (!m) return crnn_fail(CRNN_INVALID_VALUE, "set_training: null model");
-  if (flag && m->cfg.compute_dtype == 2) return crnn_fail(CRNN_UNSUPPORTED, "set_training: the f32-class path (compute_dtype 2) is forward + CTC only");
+  if (flag && m->cfg.compute_dtype >= 2) return crnn_fail(CRNN_UNSUPPORTED, "set_training: the f32-class paths (compute_dtype 2, 3) are forward + CTC only");
   if (flag && !m->wblock_bwd) {
     const size_t nB[9] = {512 * 4608, 256 * 4608, 256 * 2304, 128 * 2304, 64 * 1152, 1024 * 1024, 512 * 64, 512 * 2048, 512 * 1024};
     size_t tot = 1024;
@@ -235,13 +236,21 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   notify("conv4_2/weights", "conv5/weights");
   BMARK();
   {
+    // pass 1 of conv4_1's BatchNorm/ReLU backward (the two per-channel sums) rides in this epilogue: no separate read of the
+    // 268 MB gradient + 268 MB pre-BN activation
     gemm::Params p = conv_params(N, H2, 4, 512, 512, 256, nullptr, pl.d_pre4a, pl.mg4);
-    if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_CONV_STORE, 6>(pl.tG_p4b, m->tDh_c42, p, sms, st)));
-    else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_CONV_STORE, 4>(pl.tG_p4b, m->tD_c42, p, sms, st)));
+    p.mask = pl.a4a_pre; p.bnp = pl.bn; p.stats = sums41;
+    if (m->bn_red_fused) {
+      if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_CONV_STORE_BNRED, 6>(pl.tG_p4b, m->tDh_c42, p, sms, st)));
+      else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_CONV_STORE_BNRED, 4>(pl.tG_p4b, m->tD_c42, p, sms, st)));
+    } else {
+      if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_CONV_STORE, 6>(pl.tG_p4b, m->tDh_c42, p, sms, st)));
+      else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_CONV_STORE, 4>(pl.tG_p4b, m->tD_c42, p, sms, st)));
+    }
   }
   BMARK();
   // ------------------------------------------------------------------ conv4_1: ReLU + BN backward
-  CRNN_TRY(launch_bn_bwd_reduce(false, pl.d_pre4a, pl.a4a_pre, pl.bn, sums41, P4, 512, st));
+  if (!m->bn_red_fused) CRNN_TRY(launch_bn_bwd_reduce(false, pl.d_pre4a, pl.a4a_pre, pl.bn, sums41, P4, 512, st));
   if (m->dp_world > 1) CRNN_TRY(dp_allreduce_1024(m, sums41, gsum41, st));
   CRNN_TRY(launch_bn_bwd_apply(false, pl.d_pre4a, pl.a4a_pre, pl.d_pre4a, pl.bn, m->P("conv4_1/conv4_1/gamma"), gsum41, sums41, P4g, P4, 512,
                                pl.bn_bwd_coef, G("conv4_1/conv4_1/gamma"), G("conv4_1/conv4_1/beta"), st));
@@ -275,13 +284,20 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
   notify("conv3_2/weights", "conv4_1/weights");
   BMARK();
   {
+    // conv3_1's ReLU backward rides in this epilogue (zero where a3 == 0): saves one read + one write of the 268 MB gradient
     gemm::Params p = conv_params(N, H2, 8, 256, 256, 256, nullptr, pl.d_pre31, pl.mg3);
-    if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_CONV_STORE, 6>(pl.tG_p32, m->tDh_c32, p, sms, st)));
-    else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_CONV_STORE, 4>(pl.tG_p32, m->tD_c32, p, sms, st)));
+    p.mask = pl.a3;
+    if (m->relu_mask_fused) {
+      if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_CONV_STORE_MASK, 6>(pl.tG_p32, m->tDh_c32, p, sms, st)));
+      else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_CONV_STORE_MASK, 4>(pl.tG_p32, m->tD_c32, p, sms, st)));
+    } else {
+      if (m->use_2cta) CRNN_TRY((launch_gemm2<gemm::A_CONV3, gemm::EPI_CONV_STORE, 6>(pl.tG_p32, m->tDh_c32, p, sms, st)));
+      else CRNN_TRY((launch_gemm<256, gemm::A_CONV3, gemm::EPI_CONV_STORE, 4>(pl.tG_p32, m->tD_c32, p, sms, st)));
+    }
   }
   BMARK();
-  // ------------------------------------------------------------------ conv3_1: ReLU backward
-  CRNN_TRY(launch_relu_bwd(pl.d_pre31, pl.a3, (size_t)N * H2 * 8 * 256, st));
+  // ------------------------------------------------------------------ conv3_1: ReLU backward (unless fused above), bias gradient
+  if (!m->relu_mask_fused) CRNN_TRY(launch_relu_bwd(pl.d_pre31, pl.a3, (size_t)N * H2 * 8 * 256, st));
   CRNN_TRY(launch_colsum_bf16(pl.d_pre31, (long long)N * H2 * 8, 256, G("conv3_1/biases"), 0, 0, st));
   BMARK();
   {
@@ -330,8 +346,10 @@ extern "C" int crnn_backward(crnn_model* m, const float* data, const int* time_s
     CRNN_TRY((launch_gemm<64, gemm::A_CONV3, gemm::EPI_CONV_STORE, 8>(pl.tG_p2, m->tD_c2, p, sms, st)));
   }
   BMARK();
-  // ------------------------------------------------------------------ conv1 (K = 9, SIMT): pool1 + ReLU folded in
-  CRNN_TRY(launch_conv1_wgrad(pl.d_a1, pl.a1, pl.am1, data, G("conv1/weights"), G("conv1/biases"), N, W, st));
+  // ------------------------------------------------------------------ conv1 (Cin = 1): pool1 + ReLU backward folded in; tensor-core
+  // kernel with thread-built operands (conv1_wgrad_tc.cuh), CRNN_CONV1_WGRAD=simt -> the FMA kernel of backward_kernels.cu
+  if (m->conv1_wgrad_tc) CRNN_TRY(launch_conv1_wgrad_tc(pl.d_a1, pl.a1, pl.am1, data, G("conv1/weights"), G("conv1/biases"), N, W, sms, st));
+  else CRNN_TRY(launch_conv1_wgrad(pl.d_a1, pl.a1, pl.am1, data, G("conv1/weights"), G("conv1/biases"), N, W, st));
   notify("conv1/weights", "conv3_1/weights");
   BMARK();
 #undef BMARK

@@ -46,6 +46,9 @@ enum Epi {
   EPI_CONV_STORE = 9,   // conv: plain bf16 NHWC store (data-gradient convolutions)
   EPI_RELU_POOL22_T = 10,  // training variants of the pooled epilogues: also emit the arg-max window index (uint8)
   EPI_RELU_POOL12_T = 11,
+  EPI_CONV_STORE_MASK = 13,  // EPI_CONV_STORE with the ReLU backward of the PRODUCING layer folded in: zero where p.mask (its bf16 output, same NHWC layout) is 0
+  EPI_CONV_STORE_BNRED = 14, // EPI_CONV_STORE + pass 1 of the BatchNorm/ReLU backward of the PRODUCING layer: per-channel f64 sums of the
+                             // ReLU-masked gradient and of gradient * xhat (p.mask = its pre-BN bf16 output, p.bnp = scale|shift|mean|invstd)
   EPI_CONV_F32 = 12     // conv: raw f32 accumulators, NHWC store (f32-class path, forward_x3.cu: bias/BN/ReLU/pool + hi/lo split follow)
 };
 
@@ -72,6 +75,8 @@ struct Params {
   void* out;             // primary output
   int ldo;               // row stride of `out` in elements (plain modes)
   double* stats;         // [2][Nc] (EPI_STATS)
+  const __nv_bfloat16* mask;   // EPI_CONV_STORE_MASK: post-ReLU activation of the layer whose pre-activation gradient is being written
+  const float* bnp;      // EPI_CONV_STORE_BNRED: [4][Nc] scale, shift, mean, invstd of the producing layer's BatchNorm
   uint8_t* argmax;       // pooled-epilogue training variants: window index of the max, same shape as `out`
   // EPI_LSTM
   const __nv_bfloat16* xproj;   // [Nimg*H, 2048] gate pre-activations (x part + bias), permuted columns
@@ -133,7 +138,8 @@ __device__ __forceinline__ void run_epilogue(const Params& p, const uint32_t tba
   int n_img = 0, h = 0, w = 0;
   bool valid = true;
   if (EPI == EPI_RELU || EPI == EPI_RELU_POOL22 || EPI == EPI_RELU_POOL12 || EPI == EPI_STATS || EPI == EPI_CONV_STORE ||
-      EPI == EPI_RELU_POOL22_T || EPI == EPI_RELU_POOL12_T || EPI == EPI_CONV_F32) {
+      EPI == EPI_RELU_POOL22_T || EPI == EPI_RELU_POOL12_T || EPI == EPI_CONV_F32 || EPI == EPI_CONV_STORE_MASK ||
+      EPI == EPI_CONV_STORE_BNRED) {
     const int g = m_blk * 4 + q;
     n_img = g / p.sb_per_img;
     const int hb = g - n_img * p.sb_per_img;
@@ -278,6 +284,77 @@ __device__ __forceinline__ void run_epilogue(const Params& p, const uint32_t tba
                             ptx::pack_bf16x2(__uint_as_float(v[i + 12]), __uint_as_float(v[i + 13])),
                             ptx::pack_bf16x2(__uint_as_float(v[i + 14]), __uint_as_float(v[i + 15])));
       }
+    }
+  } else if (EPI == EPI_CONV_STORE_MASK) {
+    const size_t off = (((size_t)n_img * p.H + h) * p.Wd + w) * p.Nc + col0;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
+    const __nv_bfloat16* msk = p.mask + off;
+#pragma unroll 1
+    for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+      uint4 mk[4];
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mk[i] = __ldg(reinterpret_cast<const uint4*>(msk + c0) + i);     // issued before the TMEM wait
+      }
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(tbase + c0, v);
+      ptx::tmem_ld_wait();
+      if (valid) {
+        const uint32_t* mw = reinterpret_cast<const uint32_t*>(mk);
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          // the activation is post-ReLU (>= 0): "> 0" is "bf16 bits, sign aside, non-zero"; rounding then masking == masking then rounding
+          const uint32_t keep = ((mw[i] & 0x7FFFu) ? 0xFFFFu : 0u) | ((mw[i] & 0x7FFF0000u) ? 0xFFFF0000u : 0u);
+          pk[i] = ptx::pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])) & keep;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i += 8)
+          ptx::st_global_v8(out + c0 + 2 * i, pk[i], pk[i + 1], pk[i + 2], pk[i + 3], pk[i + 4], pk[i + 5], pk[i + 6], pk[i + 7]);
+      }
+    }
+  } else if (EPI == EPI_CONV_STORE_BNRED) {
+    // same sums as bn_bwd_reduce_kernel<false> (backward_kernels.cu), taken on the bf16-rounded gradient the apply pass will read
+    const size_t off = (((size_t)n_img * p.H + h) * p.Wd + w) * p.Nc + col0;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
+    const __nv_bfloat16* xp = p.mask + off;
+#pragma unroll 1
+    for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+      uint4 xq[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xq[i] = valid ? __ldg(reinterpret_cast<const uint4*>(xp + c0) + i) : make_uint4(0u, 0u, 0u, 0u);
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(tbase + c0, v);
+      ptx::tmem_ld_wait();
+      const uint32_t* xw = reinterpret_cast<const uint32_t*>(xq);
+      uint32_t pk[16];
+      float f[32], f2[32];
+      const float* bc = p.bnp + col0 + c0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(bc + i));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(bc + p.Nc + i));
+        const float4 mu = __ldg(reinterpret_cast<const float4*>(bc + 2 * p.Nc + i));
+        const float4 is = __ldg(reinterpret_cast<const float4*>(bc + 3 * p.Nc + i));
+        pk[i / 2] = ptx::pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+        pk[i / 2 + 1] = ptx::pack_bf16x2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+        const float x0 = ptx::bf16_lo(xw[i / 2]), x1 = ptx::bf16_hi(xw[i / 2]), x2 = ptx::bf16_lo(xw[i / 2 + 1]), x3 = ptx::bf16_hi(xw[i / 2 + 1]);
+        const float d0 = (valid && fmaf(x0, sc.x, sh.x) > 0.f) ? ptx::bf16_lo(pk[i / 2]) : 0.f;
+        const float d1 = (valid && fmaf(x1, sc.y, sh.y) > 0.f) ? ptx::bf16_hi(pk[i / 2]) : 0.f;
+        const float d2 = (valid && fmaf(x2, sc.z, sh.z) > 0.f) ? ptx::bf16_lo(pk[i / 2 + 1]) : 0.f;
+        const float d3 = (valid && fmaf(x3, sc.w, sh.w) > 0.f) ? ptx::bf16_hi(pk[i / 2 + 1]) : 0.f;
+        f[i] = d0; f[i + 1] = d1; f[i + 2] = d2; f[i + 3] = d3;
+        f2[i] = d0 * (x0 - mu.x) * is.x; f2[i + 1] = d1 * (x1 - mu.y) * is.y; f2[i + 2] = d2 * (x2 - mu.z) * is.z; f2[i + 3] = d3 * (x3 - mu.w) * is.w;
+      }
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 8)
+          ptx::st_global_v8(out + c0 + 2 * i, pk[i], pk[i + 1], pk[i + 2], pk[i + 3], pk[i + 4], pk[i + 5], pk[i + 6], pk[i + 7]);
+      }
+      const float s1 = warp_colsum32(f, lane);
+      const float s2 = warp_colsum32(f2, lane);
+      atomicAdd(p.stats + col0 + c0 + lane, (double)s1);
+      atomicAdd(p.stats + p.Nc + col0 + c0 + lane, (double)s2);
     }
   } else if (EPI == EPI_CONV_F32) {
     float* out = reinterpret_cast<float*>(p.out) + (((size_t)n_img * p.H + h) * p.Wd + w) * p.Nc + col0;
@@ -460,13 +537,16 @@ __device__ __forceinline__ void run_epilogue(const Params& p, const uint32_t tba
 
 }
 
-template <int BLOCK_N, int AMODE, int EPI, int STAGES>
+// KIND 0: bf16 operands (kind::f16), 64 elements per 128 B K-block.  KIND 1: f32 words read as tf32 (kind::tf32), 32 elements per
+// K-block (forward_x3.cu, compute_dtype 3); tensor maps are FLOAT32 with 32-element boxes, everything else is shared.
+template <int BLOCK_N, int AMODE, int EPI, int STAGES, int KIND = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
   static_assert(BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
   constexpr int B_STAGE_BYTES = BLOCK_N * 128;
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;        // power of two >= 32
-  constexpr uint32_t IDESC = ptx::make_idesc_bf16(BLOCK_M, BLOCK_N);
+  constexpr uint32_t IDESC = KIND ? ptx::make_idesc_tf32(BLOCK_M, BLOCK_N) : ptx::make_idesc_bf16(BLOCK_M, BLOCK_N);
+  constexpr int KELEMS = KIND ? 32 : BLOCK_K;        // operand elements per 128 B K-block
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -538,14 +618,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int rs = kb / p.kb_per_shift;
                 int kc = kb - rs * p.kb_per_shift;
                 if (p.kb_phys > 0 && kc >= p.kb_phys) kc -= p.kb_phys;
-                ptx::tma_load_2d(&tmA, &full_bar[stage], a_dst, kc * BLOCK_K, m_blk * BLOCK_M + rs * p.row_shift_mul);
+                ptx::tma_load_2d(&tmA, &full_bar[stage], a_dst, kc * KELEMS, m_blk * BLOCK_M + rs * p.row_shift_mul);
               } else {
                 const int r = tap / 3, sx = tap - 3 * r;
                 const int cbp = (p.cin_phys > 0 && cb >= p.cin_phys) ? cb - p.cin_phys : cb;
-                ptx::tma_load_4d(&tmA, &full_bar[stage], a_dst + lane * 4096, cbp * BLOCK_K, sx - 1, ch0 + r - 1, cn);
+                ptx::tma_load_4d(&tmA, &full_bar[stage], a_dst + lane * 4096, cbp * KELEMS, sx - 1, ch0 + r - 1, cn);
               }
             } else {
-              ptx::tma_load_2d(&tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, b_row);
+              ptx::tma_load_2d(&tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * KELEMS, b_row);
             }
           }
           if (++cb == p.cin_blocks) { cb = 0; ++tap; }
@@ -573,8 +653,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint64_t b_desc = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b + stage * B_STAGE_BYTES));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            ptx::mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0);
+            // advance 16 bf16 (8 tf32) = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            if (KIND) ptx::mma_tf32_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0);
+            else ptx::mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0);
           }
           ptx::tc_commit(&empty_bar[stage]);         // frees the smem slot once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }

@@ -4,9 +4,9 @@
 #include "gemm2.cuh"
 #include "gemm_tn.cuh"
 
-template <int BN, int AM, int EPI, int ST>
+template <int BN, int AM, int EPI, int ST, int KIND = 0>
 static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const gemm::Params& p, int num_sms, cudaStream_t st) {
-  auto kern = gemm::gemm_kernel<BN, AM, EPI, ST>;
+  auto kern = gemm::gemm_kernel<BN, AM, EPI, ST, KIND>;
   constexpr int smem = gemm::Smem<BN, ST>::BYTES;
   static bool attr = false;
   if (!attr) {

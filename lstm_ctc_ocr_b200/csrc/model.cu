@@ -103,6 +103,32 @@ int make_tmap_nhwc(CUtensorMap* m, const void* base, int N, int H, int Wd, int C
   if (r != CUDA_SUCCESS) return crnn_fail(CRNN_CUDA_ERROR, "cuTensorMapEncodeTiled(4d) failed: %d", (int)r);
   return CRNN_OK;
 }
+int make_tmap_2d_f32(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return crnn_fail(CRNN_CUDA_ERROR, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride * 4};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return crnn_fail(CRNN_CUDA_ERROR, "cuTensorMapEncodeTiled(2d f32) failed: %d", (int)r);
+  return CRNN_OK;
+}
+int make_tmap_nhwc_f32(CUtensorMap* m, const void* base, int N, int H, int Wd, int C, int bh) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return crnn_fail(CRNN_CUDA_ERROR, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wd, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)Wd * C * 4, (cuuint64_t)H * Wd * C * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)Wd, (cuuint32_t)bh, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return crnn_fail(CRNN_CUDA_ERROR, "cuTensorMapEncodeTiled(4d f32) failed: %d", (int)r);
+  return CRNN_OK;
+}
 
 static void add_tensor(crnn_model* m, const std::string& name, std::initializer_list<int64_t> shp) {
   TensorInfo t;
@@ -121,8 +147,8 @@ extern "C" int crnn_model_create(const crnn_config* cfg, crnn_model** out) {
   if (!cfg || !out) return crnn_fail(CRNN_INVALID_VALUE, "model_create: null");
   if (cfg->img_height != 32 || cfg->nclasses != 64 || cfg->num_hid != 512)
     return crnn_fail(CRNN_UNSUPPORTED, "model_create: only IMG_HEIGHT=32, NCLASSES=64, NUM_HID=512 (the reference's net)");
-  if (cfg->compute_dtype != 1 && cfg->compute_dtype != 2)
-    return crnn_fail(CRNN_UNSUPPORTED, "model_create: compute_dtype must be 1 (bf16 operands) or 2 (f32-class split-bf16 operands)");
+  if (cfg->compute_dtype < 1 || cfg->compute_dtype > 3)
+    return crnn_fail(CRNN_UNSUPPORTED, "model_create: compute_dtype must be 1 (bf16 operands), 2 (f32-class split-bf16 operands) or 3 (tf32 operands)");
   crnn_model* m = new crnn_model();
   m->cfg = *cfg;
   for (auto& c : kConvs) {
@@ -155,6 +181,9 @@ extern "C" int crnn_model_create(const crnn_config* cfg, crnn_model** out) {
   if (const char* e = getenv("CRNN_GEMM2")) m->use_2cta = std::string(e) != "0";
   if (const char* e = getenv("CRNN_BPTT")) m->bptt_ks = std::string(e) != "ring";        // debug A/B switch
   if (const char* e = getenv("CRNN_CONV1")) m->conv1_tc = std::string(e) != "simt";    // debug A/B switch
+  if (const char* e = getenv("CRNN_BN_FUSE")) m->bn_red_fused = std::string(e) != "0";            // debug A/B switch
+  if (const char* e = getenv("CRNN_RELU_FUSE")) m->relu_mask_fused = std::string(e) != "0";       // debug A/B switch
+  if (const char* e = getenv("CRNN_CONV1_WGRAD")) m->conv1_wgrad_tc = std::string(e) != "simt";  // debug A/B switch
   if (const char* e = getenv("CRNN_CONV2_DGRAD")) m->conv2_dgrad_swap = std::string(e) != "old";   // debug A/B switch
   if (const char* e = getenv("CRNN_CONV2_WGRAD")) m->conv2_wgrad_swap = std::string(e) != "old";   // debug A/B switch
   if (const char* e = getenv("CRNN_CONV2")) m->conv2_swap = std::string(e) != "pos";    // debug A/B switch: "pos" = position-major gemm.cuh kernel
@@ -321,8 +350,8 @@ size_t layout_plan(Plan& pl, int N, int W, uint8_t* base, bool train) {
 extern "C" int crnn_model_workspace_size(const crnn_model* m, int N, int W, int train, size_t* bytes) {
   if (!m || !bytes) return crnn_fail(CRNN_INVALID_VALUE, "workspace_size: null");
   if (N <= 0 || W < 8 || (W % 4) != 0) return crnn_fail(CRNN_INVALID_VALUE, "workspace_size: need N>0, W>=8, W%%4==0 (gen.py:58)");
-  if (m->cfg.compute_dtype == 2) {
-    if (train) return crnn_fail(CRNN_UNSUPPORTED, "workspace_size: the f32-class path (compute_dtype 2) is forward + CTC only");
+  if (m->cfg.compute_dtype >= 2) {
+    if (train) return crnn_fail(CRNN_UNSUPPORTED, "workspace_size: the f32-class paths (compute_dtype 2, 3) are forward + CTC only");
     *bytes = x3_workspace_size(N, W);
     return CRNN_OK;
   }
@@ -413,8 +442,8 @@ static int forward_impl(crnn_model* m, const float* data, const float* host_data
   CRNN_TRY(crnn_model_workspace_size(m, N, W, m->training ? 1 : 0, &need));
   if (workspace_bytes < need) return crnn_fail(CRNN_WORKSPACE_TOO_SMALL, "forward: workspace %zu < %zu", workspace_bytes, need);
   if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return crnn_fail(CRNN_INVALID_VALUE, "forward: workspace must be 1024-byte aligned");
-  if (m->cfg.compute_dtype == 2) {
-    // f32-class path (forward_x3.cu): copy-then-compute when fed from host memory
+  if (m->cfg.compute_dtype >= 2) {
+    // f32-class paths (forward_x3.cu): copy-then-compute when fed from host memory
     if (host_data != nullptr) {
       CUDA_TRY(cudaMemcpyAsync(const_cast<float*>(data), host_data, (size_t)N * W * 32 * sizeof(float), cudaMemcpyHostToDevice, st));
     }
@@ -713,7 +742,7 @@ extern "C" int crnn_total_loss(crnn_model* m, const float* costs, int N, float* 
 extern "C" int crnn_debug_tap(crnn_model* m, const char* name, float* dst, size_t dst_elems, void* workspace,
                               crnn_stream_t stream) {
   if (!m || !name || !dst) return crnn_fail(CRNN_INVALID_VALUE, "debug_tap: null");
-  if (m->cfg.compute_dtype == 2) return x3_debug_tap(m, name, dst, dst_elems, workspace, reinterpret_cast<cudaStream_t>(stream));
+  if (m->cfg.compute_dtype >= 2) return x3_debug_tap(m, name, dst, dst_elems, workspace, reinterpret_cast<cudaStream_t>(stream));
   Plan& pl = m->plan;
   if (pl.ws == nullptr || pl.ws != workspace) return crnn_fail(CRNN_INVALID_VALUE, "debug_tap: no forward ran on this workspace");
   const size_t n = pl.N, h1 = pl.H1, h2 = pl.H2;

@@ -10,6 +10,9 @@
 
 int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride, uint32_t box_rows);
 int make_tmap_nhwc(CUtensorMap* m, const void* base, int N, int H, int Wd, int C, int bh);
+// f32 tensors read as kind::tf32 operands: 32-element (128 B) boxes along the contiguous dimension
+int make_tmap_2d_f32(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride, uint32_t box_rows);
+int make_tmap_nhwc_f32(CUtensorMap* m, const void* base, int N, int H, int Wd, int C, int bh);
 size_t align_up(size_t v, size_t a = 1024);
 int make_tmap_2d_box(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride, uint32_t box_cols,
                      uint32_t box_rows);
@@ -96,6 +99,9 @@ struct crnn_model {
   CUtensorMap tBh_c2, tBh_c31, tBh_c32, tBh_c41, tBh_c42, tBh_c5, tBh_x;   // same weights, box = 128 rows: per-CTA half of a 256-row N tile
   bool use_2cta = true;      // cta_group::2 GEMM pairs for the Nc % 256 == 0 layers (CRNN_GEMM2=0 disables; debug A/B switch)
   bool conv1_tc = true;      // conv1 + pool1 on the tensor cores (conv1_tc.cuh, split-bf16 operands); CRNN_CONV1=simt -> kernels.cu
+  bool bn_red_fused = true;       // conv4_1's BN-backward sums inside conv4_2's data-gradient epilogue (EPI_CONV_STORE_BNRED); CRNN_BN_FUSE=0 -> separate pass
+  bool relu_mask_fused = true;    // conv3_1's ReLU backward inside conv3_2's data-gradient epilogue (EPI_CONV_STORE_MASK); CRNN_RELU_FUSE=0 -> separate pass
+  bool conv1_wgrad_tc = true;     // conv1 weight gradient on the tensor cores (conv1_wgrad_tc.cuh); CRNN_CONV1_WGRAD=simt -> backward_kernels.cu
   bool conv2_dgrad_swap = true;   // conv2 / conv3_1 data gradients with swapped operands (conv_swap.cuh); CRNN_CONV2_DGRAD=old -> position-major N = 64 / 128
   bool conv2_wgrad_swap = true;   // conv2 weight gradient with swapped operands + 4 taps per N tile (gemm_tn.cuh tap_pack_n); CRNN_CONV2_WGRAD=old -> 2 taps per M tile
   bool conv2_swap = true;    // conv2 with channels on the MMA M side and 256 positions on N (conv_swap.cuh); CRNN_CONV2=pos -> gemm.cuh

@@ -149,6 +149,24 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
       : "memory");
 }
 
+// kind::tf32: operands are 32-bit words read as tf32 (sign, 8-bit exponent, 10-bit mantissa; the low 13 bits are ignored),
+// K = 8 per instruction (32 B of the swizzle row), f32 accumulate.  Half the kind::f16 rate.
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// round-to-nearest f32 -> tf32 (the tensor core would otherwise truncate)
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (rows of 128 B, 8-row atoms of 1024 B):
 //   [0,14)  start address >> 4        [16,30) leading byte offset >> 4 (ignored for swizzled K-major; 1)
 //   [32,46) stride byte offset >> 4 (= 1024 B between 8-row groups)
@@ -168,6 +186,11 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
 //   [15] A major (0 = K)       [16] B major (0 = K)         [17,23) N >> 3      [24,29) M >> 4
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+// kind::tf32: same fields, A/B format code 2 (tf32)
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 

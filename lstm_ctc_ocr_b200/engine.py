@@ -30,8 +30,9 @@ class CrnnModel:
         self.lib = _lib.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         torch.cuda.set_device(self.device)
-        # "bf16": bf16 operands / f32 accumulate (throughput path); "f32": split-bf16 operands, f32-class (BASELINE configs[1])
-        self.compute_dtype = {"bf16": 1, "f32": 2, 1: 1, 2: 2}[compute_dtype]
+        # "bf16": bf16 operands / f32 accumulate (throughput path); "f32": split-bf16 operands, f32-class (BASELINE configs[1]);
+        # "tf32": kind::tf32 operands, same forward-only orchestration as "f32"
+        self.compute_dtype = {"bf16": 1, "f32": 2, "tf32": 3, 1: 1, 2: 2, 3: 3}[compute_dtype]
         cfg = CrnnConfig(32, NCLASSES, 512, bn_eps, weight_decay, self.compute_dtype)
         h = _lib.c_void_p()
         check(self.lib.crnn_model_create(cfg, h))
