@@ -319,6 +319,9 @@ def main():
     feeder = datagen.PrefetchFeeder(arg_fn, num_workers=nwork, depth=4, max_width=W, batch_size=N, keep=2,
                                     warm=[arg_fn(k) for k in range(4)])      # every producer draws its 4 cached batches at start-up
     try:
+        if not os.environ.get("CRNN_BENCH_NO_DEVICE_PREFETCH"):
+            sess.attach_feeder(feeder)        # the next ring slot's H2D copy overlaps the current step (one 33.6 MB copy per step either way)
+
         def feed_step(i):
             view, lab, ll, tsl = next(feeder)
             return run_on(view, np.asarray(lab, np.int32), np.asarray(ll, np.int32), np.asarray(tsl, np.int32))
@@ -327,7 +330,9 @@ def main():
         feed_path = sess.last_feed_path
         ms_feed, e2e_loss = timed(feed_step, Ke)
         h2d_b, d2h_b = int(sess.h2d_bytes), int(sess.d2h_bytes)
+        feed_path = sess.last_feed_path
     finally:
+        sess.attach_feeder(None)
         feeder.close()
     # (b) fresh pageable array every step
     fresh = [np.array(batches[i % nrot][5][0]) for i in range(Ke + 2)]

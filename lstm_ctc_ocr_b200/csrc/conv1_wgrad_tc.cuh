@@ -21,7 +21,7 @@
 // gradient) and its 8 entry stores then fall into 8 different bank groups across the quarter-warp.
 //
 // Roles (544 threads): warp 0 setup, warp 1 MMA issuer, warps 2..5 final epilogue (TMEM lane quadrants), warps 6..13 gradient
-// (A) builders, warps 14..16 patch (B) builders + input staging.  3-stage operand ring; a stage = 4 pooled rows x 16 pooled
+// (A) builders, warps 14..16 patch (B) builders + input staging.  4-stage operand ring; a stage = 4 pooled rows x 16 pooled
 // columns = 64 pooled positions = 256 K per set = 16 tcgen05.mma (K = 16).
 #pragma once
 #include <cuda.h>
@@ -33,7 +33,7 @@ namespace conv1wg {
 constexpr int NUM_THREADS = 544;
 constexpr int EPI_WARP0 = 2, A_WARP0 = 6, B_WARP0 = 14;
 constexpr int A_THREADS = 256, B_THREADS = 96;
-constexpr int NST = 3;
+constexpr int NST = 4;
 constexpr int CHUNKS = 16;                          // K chunks of 8 per set and stage
 constexpr int A_BYTES = CHUNKS * 128 * 16;          // 32 KB
 constexpr int B_BYTES = CHUNKS * 64 * 16;           // 16 KB
@@ -148,49 +148,57 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv1_wgrad_tc_kernel(const Pa
         float* rowp = s_in + b * IN_ROWS * IN_STRIDE + bt * IN_STRIDE;
         rowp[0] = 0.f; rowp[33] = 0.f; rowp[34] = 0.f; rowp[35] = 0.f;
       }
-    float4 pre;
+    // input rows are prefetched TWO tiles ahead in registers (a tile is ~1 us of work, about one HBM round trip: one tile ahead
+    // left the load latency exposed every iteration) and parked in the other s_in buffer one tile ahead
+    const int G = gridDim.x;
+    float4 pre[2];
     if ((int)blockIdx.x < num_tiles) {
-      fetch(blockIdx.x, pre);
-      stash(s_in, pre);
+      fetch(blockIdx.x, pre[0]);
+      stash(s_in, pre[0]);
     }
+    if ((int)blockIdx.x + G < num_tiles) fetch(blockIdx.x + G, pre[1]);
     int st = 0, it = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      float* stg = s_in + (it & 1) * (IN_ROWS * IN_STRIDE);
-      const int nxt = tile + gridDim.x;
-      if (nxt < num_tiles) fetch(nxt, pre);
-      asm volatile("bar.sync 3, %0;" ::"n"(B_THREADS) : "memory");     // this tile's input rows are staged (and the other buffer is free)
-      ptx::mbar_wait(&empty[st], ph ^ 1);
-      // rows 2*hol + r (+1) of the stage, columns 4*pw .. 4*pw+5 (index = image column + 1 -> the patch column origin)
-      float R[2][6];
+    for (int tile = blockIdx.x; tile < num_tiles;) {
 #pragma unroll
-      for (int dy = 0; dy < 2; ++dy) {
-        const float2* src = reinterpret_cast<const float2*>(stg + (2 * hol + r + dy) * IN_STRIDE + 4 * pw);
+      for (int u = 0; u < 2; ++u) {                          // u == it & 1: pre[u] held tile `it` (already parked), pre[u ^ 1] holds tile it+1
+        if (tile >= num_tiles) break;
+        float* stg = s_in + u * (IN_ROWS * IN_STRIDE);
+        if (tile + 2 * G < num_tiles) fetch(tile + 2 * G, pre[u]);
+        asm volatile("bar.sync 3, %0;" ::"n"(B_THREADS) : "memory");     // this tile's input rows are parked (and the other buffer is free)
+        ptx::mbar_wait(&empty[st], ph ^ 1);
+        // rows 2*hol + r (+1) of the stage, columns 4*pw .. 4*pw+5 (index = image column + 1 -> the patch column origin)
+        float R[2][6];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { const float2 t = src[c]; R[dy][2 * c] = t.x; R[dy][2 * c + 1] = t.y; }
+        for (int dy = 0; dy < 2; ++dy) {
+          const float2* src = reinterpret_cast<const float2*>(stg + (2 * hol + r + dy) * IN_STRIDE + 4 * pw);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { const float2 t = src[c]; R[dy][2 * c] = t.x; R[dy][2 * c + 1] = t.y; }
+        }
+        uint8_t* sb = smem_b + st * B_BYTES + chunk * 1024 + set * 32 * 16;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          // K order of the entry: [position 0: slots (0,0) (0,1) (1,0) (1,1) | position 1: the same], slot (dy,dx) reads R[dy][s + 2*pi + dx]
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int pi = 0; pi < 2; ++pi)
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+              const float x0 = R[dy][s + 2 * pi], x1 = R[dy][s + 2 * pi + 1];
+              const uint32_t h = ptx::pack_bf16x2(x0, x1);
+              hi[pi * 2 + dy] = h;
+              lo[pi * 2 + dy] = ptx::pack_bf16x2(x0 - ptx::bf16_lo(h), x1 - ptx::bf16_hi(h));
+            }
+          const int tap = r * 3 + s;
+          *reinterpret_cast<uint4*>(sb + tap * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(sb + (16 + tap) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&full[st]);
+        if (tile + G < num_tiles) stash(s_in + (u ^ 1) * (IN_ROWS * IN_STRIDE), pre[u ^ 1]);   // loaded a full tile ago
+        tile += G; ++it;
+        if (++st == NST) { st = 0; ph ^= 1; }
       }
-      uint8_t* sb = smem_b + st * B_BYTES + chunk * 1024 + set * 32 * 16;
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        // K order of the entry: [position 0: slots (0,0) (0,1) (1,0) (1,1) | position 1: the same], slot (dy,dx) reads R[dy][s + 2*pi + dx]
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int pi = 0; pi < 2; ++pi)
-#pragma unroll
-          for (int dy = 0; dy < 2; ++dy) {
-            const float x0 = R[dy][s + 2 * pi], x1 = R[dy][s + 2 * pi + 1];
-            const uint32_t h = ptx::pack_bf16x2(x0, x1);
-            hi[pi * 2 + dy] = h;
-            lo[pi * 2 + dy] = ptx::pack_bf16x2(x0 - ptx::bf16_lo(h), x1 - ptx::bf16_hi(h));
-          }
-        const int tap = r * 3 + s;
-        *reinterpret_cast<uint4*>(sb + tap * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(sb + (16 + tap) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      }
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&full[st]);
-      if (nxt < num_tiles) stash(s_in + ((it + 1) & 1) * (IN_ROWS * IN_STRIDE), pre);
-      if (++st == NST) { st = 0; ph ^= 1; }
     }
   } else if (warp_idx >= A_WARP0) {
     // ===================== gradient (A) builders =====================
@@ -214,38 +222,43 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv1_wgrad_tc_kernel(const Pa
         }
       }
     };
-    uint4 g[2], y[2];
-    uint2 ix[2];
-    if ((int)blockIdx.x < num_tiles) fetch(blockIdx.x, g, y, ix);
+    // three register slots, loads issued TWO tiles ahead (one tile is about one HBM round trip: see the patch builders)
+    const int G = gridDim.x;
+    uint4 g[3][2], y[3][2];
+    uint2 ix[3][2];
+    if ((int)blockIdx.x < num_tiles) fetch(blockIdx.x, g[0], y[0], ix[0]);
+    if ((int)blockIdx.x + G < num_tiles) fetch(blockIdx.x + G, g[1], y[1], ix[1]);
     int st = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      uint4 gc[2] = {g[0], g[1]}, yc[2] = {y[0], y[1]};
-      uint2 ic[2] = {ix[0], ix[1]};
-      const int nxt = tile + gridDim.x;
-      if (nxt < num_tiles) fetch(nxt, g, y, ix);             // in flight while this stage is built
-      ptx::mbar_wait(&empty[st], ph ^ 1);
-      uint8_t* sa = smem_a + st * A_BYTES + a_off;
-      const uint32_t* gw0 = reinterpret_cast<const uint32_t*>(&gc[0]);
-      const uint32_t* gw1 = reinterpret_cast<const uint32_t*>(&gc[1]);
-      const uint32_t* yw0 = reinterpret_cast<const uint32_t*>(&yc[0]);
-      const uint32_t* yw1 = reinterpret_cast<const uint32_t*>(&yc[1]);
+    for (int tile = blockIdx.x; tile < num_tiles;) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int sh = (j & 1) * 16;
-        // a1 is post-ReLU (>= 0): "a1 > 0" is "bf16 bits, sign aside, non-zero"
-        const uint32_t y0 = (yw0[j >> 1] >> sh) & 0x7FFFu, y1 = (yw1[j >> 1] >> sh) & 0x7FFFu;
-        const uint32_t g0 = y0 ? ((gw0[j >> 1] >> sh) & 0xFFFFu) : 0u, g1 = y1 ? ((gw1[j >> 1] >> sh) & 0xFFFFu) : 0u;
-        const uint32_t i0 = ((j < 4 ? ic[0].x : ic[0].y) >> ((j & 3) * 8)) & 3u;
-        const uint32_t i1 = ((j < 4 ? ic[1].x : ic[1].y) >> ((j & 3) * 8)) & 3u;
-        uint4 e;
-        quad_words(g0, i0, e.x, e.y);
-        quad_words(g1, i1, e.z, e.w);
-        *reinterpret_cast<uint4*>(sa + j * 128) = e;
+      for (int u = 0; u < 3; ++u) {
+        if (tile >= num_tiles) break;
+        if (tile + 2 * G < num_tiles) fetch(tile + 2 * G, g[(u + 2) % 3], y[(u + 2) % 3], ix[(u + 2) % 3]);
+        ptx::mbar_wait(&empty[st], ph ^ 1);
+        uint8_t* sa = smem_a + st * A_BYTES + a_off;
+        const uint32_t* gw0 = reinterpret_cast<const uint32_t*>(&g[u][0]);
+        const uint32_t* gw1 = reinterpret_cast<const uint32_t*>(&g[u][1]);
+        const uint32_t* yw0 = reinterpret_cast<const uint32_t*>(&y[u][0]);
+        const uint32_t* yw1 = reinterpret_cast<const uint32_t*>(&y[u][1]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int sh = (j & 1) * 16;
+          // a1 is post-ReLU (>= 0): "a1 > 0" is "bf16 bits, sign aside, non-zero"
+          const uint32_t y0 = (yw0[j >> 1] >> sh) & 0x7FFFu, y1 = (yw1[j >> 1] >> sh) & 0x7FFFu;
+          const uint32_t g0 = y0 ? ((gw0[j >> 1] >> sh) & 0xFFFFu) : 0u, g1 = y1 ? ((gw1[j >> 1] >> sh) & 0xFFFFu) : 0u;
+          const uint32_t i0 = ((j < 4 ? ix[u][0].x : ix[u][0].y) >> ((j & 3) * 8)) & 3u;
+          const uint32_t i1 = ((j < 4 ? ix[u][1].x : ix[u][1].y) >> ((j & 3) * 8)) & 3u;
+          uint4 e;
+          quad_words(g0, i0, e.x, e.y);
+          quad_words(g1, i1, e.z, e.w);
+          *reinterpret_cast<uint4*>(sa + j * 128) = e;
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&full[st]);
+        tile += G;
+        if (++st == NST) { st = 0; ph ^= 1; }
       }
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&full[st]);
-      if (++st == NST) { st = 0; ph ^= 1; }
     }
   } else if (warp_idx >= EPI_WARP0) {
     // ===================== final epilogue: lane = (set, row of the set), columns set*32 .. = [taps hi | ones | taps lo] =====================

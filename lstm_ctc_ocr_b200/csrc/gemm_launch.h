@@ -3,6 +3,8 @@
 #include "gemm.cuh"
 #include "gemm2.cuh"
 #include "gemm_tn.cuh"
+#include <cstdlib>
+#include <string>
 
 template <int BN, int AM, int EPI, int ST, int KIND = 0>
 static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const gemm::Params& p, int num_sms, cudaStream_t st) {
@@ -38,6 +40,30 @@ static int launch_gemm2(const CUtensorMap& a, const CUtensorMap& b_half, const g
   return CRNN_OK;
 }
 
+// Split-K factor of a weight-gradient GEMM.  Work items (output tile x K chunk) all cost the same and the persistent CTAs take them
+// round-robin, so the launch lasts  ceil(items / workers) rounds x (K blocks per chunk + epilogue).  The first-generation rule
+// ("about 3 items per worker") left a mostly idle last round -- conv4_1: 18 tiles x 13 chunks = 234 items on 74 CTA pairs = 4 rounds
+// at 79 % occupancy; 18 x 4 = 72 items is ONE round at 97 %.  Pick the factor that minimises the modelled time (ties: fewer chunks =
+// fewer f32 reduction atomics).  CRNN_KSPLIT=old restores the old rule.
+static inline int pick_k_splits(int tiles, int k_blocks_total, int workers) {
+  static const bool old_rule = [] { const char* e = getenv("CRNN_KSPLIT"); return e && std::string(e) == "old"; }();
+  if (old_rule) {
+    int s = (3 * workers + tiles - 1) / tiles;
+    if (s > k_blocks_total) s = k_blocks_total;
+    return s < 1 ? 1 : s;
+  }
+  const int kEpi = 6;                            // epilogue + pipeline refill of one item, in K-block units
+  int best = 1;
+  long long best_cost = -1;
+  const int kmax = k_blocks_total < 4 * workers ? k_blocks_total : 4 * workers;
+  for (int k = 1; k <= kmax; ++k) {
+    const long long rounds = ((long long)tiles * k + workers - 1) / workers;
+    const long long cost = rounds * ((k_blocks_total + k - 1) / k + kEpi);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = k; }
+  }
+  return best;
+}
+
 template <int BN, int AM, int ST>
 static int launch_gemm_tn(const CUtensorMap& a, const CUtensorMap& b, gemm_tn::Params p, int num_sms, cudaStream_t st) {
   auto kern = gemm_tn::gemm_tn_kernel<BN, AM, ST>;
@@ -48,12 +74,7 @@ static int launch_gemm_tn(const CUtensorMap& a, const CUtensorMap& b, gemm_tn::P
     attr = true;
   }
   const int tiles = p.num_taps * p.num_m_tiles * p.num_n_tiles;
-  if (p.k_splits <= 0) {
-    int s = (3 * num_sms + tiles - 1) / tiles;
-    if (s > p.k_blocks_total) s = p.k_blocks_total;
-    if (s < 1) s = 1;
-    p.k_splits = s;
-  }
+  if (p.k_splits <= 0) p.k_splits = pick_k_splits(tiles, p.k_blocks_total, num_sms);
   const int items = tiles * p.k_splits;
   const int grid = items < num_sms ? items : num_sms;
   kern<<<grid, gemm_tn::NUM_THREADS, smem, st>>>(a, b, p);
@@ -73,12 +94,7 @@ static int launch_gemm_tn2(const CUtensorMap& a, const CUtensorMap& b, gemm_tn::
   }
   const int tiles = p.num_taps * p.num_m_tiles * p.num_n_tiles;
   const int max_clusters = num_sms / 2;
-  if (p.k_splits <= 0) {
-    int s = (3 * max_clusters + tiles - 1) / tiles;
-    if (s > p.k_blocks_total) s = p.k_blocks_total;
-    if (s < 1) s = 1;
-    p.k_splits = s;
-  }
+  if (p.k_splits <= 0) p.k_splits = pick_k_splits(tiles, p.k_blocks_total, max_clusters);
   const int items = tiles * p.k_splits;
   const int clusters = items < max_clusters ? items : max_clusters;
   kern<<<2 * clusters, gemm_tn::NUM_THREADS, smem, st>>>(a, b, p);

@@ -161,6 +161,8 @@ class SolverWrapper(object):
         self._lr, self._global_step = lr, global_step
         train_op = TrainOp(self.net, lr, global_step, clip=10.0)
         first_iter = self._prepare(sess, restore, lr, global_step)
+        if hasattr(sess, "attach_feeder"):
+            sess.attach_feeder(train_gen)                  # PrefetchFeeder: the next batch's H2D copy overlaps the current step (no-op for plain generators)
         timer, history, val_cache = Timer(), [], {}
         loss_min = 0.015                                   # best-loss snapshot threshold (train.py:109)
         is_chief = parallel.rank() == 0

@@ -305,6 +305,8 @@ class PrefetchFeeder(object):
         self._pending = {}
         self._next_submit = 0
         self._next_yield = 0
+        self._peeked = None
+        self.delivered = 0                     # batches handed to the consumer so far (the consumer holds batch delivered - 1)
         if self.num_workers > 0:
             import multiprocessing as mp
             # `warm`: kwargs of the batches every producer should pre-generate (synthetic `cache` streams)
@@ -323,7 +325,22 @@ class PrefetchFeeder(object):
     def __iter__(self):
         return self
 
+    def peek(self):
+        """The batch the NEXT ``next()`` will deliver, without delivering it -- lets ``Session.attach_feeder`` start its host->device
+        copy while the step on the current batch is still running.  Needs ``keep >= 2``: the peeked batch counts as handed out."""
+        if self._peeked is None:
+            self._peeked = self._take()
+        return self._peeked
+
     def __next__(self):
+        if self._peeked is not None:
+            b, self._peeked = self._peeked, None
+        else:
+            b = self._take()
+        self.delivered += 1
+        return b
+
+    def _take(self):
         k = self._next_yield
         self._next_yield += 1                  # batch k is being handed out: slot k+depth (== batch k-keep's) may be refilled
         if self._pool is not None:

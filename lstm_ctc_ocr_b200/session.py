@@ -105,6 +105,15 @@ class Session(object):
         self.last_feed_path = None    # "page-locked in place" (chunked crnn_forward_host) | "staged" (copy into pinned staging first)
         import os
         self.h2d_chunks = int(os.environ.get("CRNN_H2D_CHUNKS", "4"))   # image ranges of the overlapped host->device feed (1 = copy, then compute)
+        # device prefetch (attach_feeder): the NEXT batch of a PrefetchFeeder is copied host->device on a side stream while the
+        # current step computes -- what tf.data's prefetch_to_device does for a TF input pipeline
+        self._feeder = None
+        self._ahead = None                      # (feeder sequence number, host ptr, nbytes, device tensor, copy-done event, buffer index)
+        self._ahead_bufs = [None, None]
+        self._ahead_free = [None, None]         # per buffer: event recorded on the compute stream after the last step that read it
+        self._ahead_idx = 0
+        self._ahead_stream = None
+        self.ahead_hits = 0
 
     def __enter__(self):
         return self
@@ -114,8 +123,62 @@ class Session(object):
 
     def close(self):
         torch.cuda.synchronize(self.device)
+        self._feeder = None
+        self._ahead = None
+        self._ahead_bufs = [None, None]
         self._pinned.close()
         self._engines.clear()
+
+    # ---- device prefetch ------------------------------------------------------------------
+    def attach_feeder(self, feeder):
+        """``feeder``: a PrefetchFeeder (anything with ``peek()`` and ``delivered``) whose batches are fed to ``run`` in order.
+        From then on every ``run`` starts the host->device copy of the feeder's NEXT batch on a side stream before it waits for
+        its own results, and the next ``run`` finds its input already resident (the copy is still one H2D per step, issued
+        from the page-locked ring slot; it just overlaps the previous step instead of preceding its own).  ``None`` detaches."""
+        self._feeder = feeder if (feeder is not None and hasattr(feeder, "peek") and hasattr(feeder, "delivered")) else None
+        self._ahead = None
+
+    def _stage_ahead(self):
+        f = self._feeder
+        if f is None or self._ahead is not None:
+            return
+        try:
+            nxt = f.peek()
+        except StopIteration:
+            return
+        data = nxt[0]
+        if not (isinstance(data, np.ndarray) and data.dtype == np.float32 and data.flags.c_contiguous and data.ndim == 3
+                and self._pinned.is_page_locked(data)):
+            return
+        i = self._ahead_idx
+        buf = self._ahead_bufs[i]
+        if buf is None or tuple(buf.shape) != tuple(data.shape):
+            buf = self._ahead_bufs[i] = torch.empty(data.shape, dtype=torch.float32, device=self.device)
+            self._ahead_free[i] = None
+        if self._ahead_stream is None:
+            self._ahead_stream = torch.cuda.Stream(device=self.device)
+        st = self._ahead_stream
+        if self._ahead_free[i] is not None:
+            st.wait_event(self._ahead_free[i])   # the step that last read this device buffer has finished with it
+        with torch.cuda.stream(st):
+            buf.copy_(torch.from_numpy(data), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(st)
+        self._ahead = (f.delivered, data.ctypes.data, data.nbytes, buf, ev, i)   # f.delivered == sequence number of the peeked batch
+        self._ahead_idx = i ^ 1
+
+    def _take_ahead(self, data):
+        """Device copy of `data` if it is the batch staged ahead (same feeder sequence number, same ring slot), else None."""
+        a, f = self._ahead, self._feeder
+        if a is None or f is None:
+            return None
+        self._ahead = None
+        seq, ptr, nbytes, buf, ev, i = a
+        if seq != f.delivered - 1 or ptr != data.ctypes.data or nbytes != data.nbytes or tuple(buf.shape) != tuple(data.shape):
+            return None
+        torch.cuda.current_stream(self.device).wait_event(ev)
+        self._pinned.pending.append(ev)        # the ring slot must not be recycled before this DMA is done (it is, long before)
+        return buf, i
 
     # ---- variables ------------------------------------------------------------------------
     def engine_for(self, net):
@@ -192,7 +255,14 @@ class Session(object):
         d_tsl = self._pinned.stage("tsl", tsl, dev)
         self.h2d_bytes = data.nbytes + tsl.nbytes
         data = np.ascontiguousarray(data)
-        if self.h2d_chunks > 1 and self._pinned.is_page_locked(data):
+        ahead = self._take_ahead(data)
+        used_ahead = None
+        if ahead is not None:
+            d_data, used_ahead = ahead
+            logits = eng.forward(d_data, d_tsl)
+            self.last_feed_path = "page-locked in place, copied during the previous step (device prefetch)"
+            self.ahead_hits += 1
+        elif self.h2d_chunks > 1 and self._pinned.is_page_locked(data):
             # large re-fed batch buffer (page-locked in place): chunked H2D overlapped with the conv front end
             logits, d_data = eng.forward_host(data, d_tsl, chunks=self.h2d_chunks)
             self.last_feed_path = "page-locked in place"
@@ -210,6 +280,9 @@ class Session(object):
             costs, grad = engine.ctc_loss(logits, d_lab, d_ll, d_tsl, want_grad=True, grad_scale=1.0 / N,
                                           max_label_len=int(llen.max()) if llen.size else 0)
             loss = eng.total_loss(costs)
+        has_train = any(k == "train_op" for k in kinds)
+        if not has_train:
+            self._stage_ahead()                # everything of this step is enqueued: start the next batch's copy before waiting for results
         out = []
         self.d2h_bytes = 0
         for f in flist:
@@ -234,6 +307,7 @@ class Session(object):
                     v = engine.dense_decoded(o, ol).cpu().numpy()
             elif k == "train_op":
                 v = f.step_fn(eng, logits, grad, d_data, d_tsl)
+                self._stage_ahead()
             elif k.startswith("layer:"):
                 name = k.split(":", 1)[1]
                 tapname = {"pool1": "conv1", "pool2": "conv3_2", "pool3": "conv4_2", "reshaped_layer": "conv5"}.get(name, name)
@@ -245,5 +319,10 @@ class Session(object):
             elif isinstance(v, (np.floating, float)):
                 self.d2h_bytes += 4
             out.append(v)
+        if used_ahead is not None:
+            ev = self._ahead_free[used_ahead]
+            if ev is None:
+                ev = self._ahead_free[used_ahead] = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
         self._pinned.wait_pending()
         return out[0] if single else out

@@ -331,3 +331,25 @@ def test_prefetch_feeder_delivers_the_stream_in_order():
     finally:
         if hasattr(it, "close"):
             it.close()
+
+
+def test_prefetch_feeder_peek_does_not_reorder_or_skip():
+    """peek() (what Session.attach_feeder uses to start the next batch's host->device copy early) hands back the batch the next
+    next() delivers; `delivered` counts what the consumer holds."""
+    from lstm_ctc_ocr_b200.lib.lstm.utils import gen
+    arg_fn = lambda k: dict(k=k, batch_size=4, render=False, seed=5, rank=0, world=1, bucket=gen.BUCKETS[k % 3])
+    ref = [gen.make_batch(**arg_fn(k)) for k in range(6)]
+    f = gen.PrefetchFeeder(arg_fn, num_workers=0, depth=2, max_width=256, batch_size=4, pinned=False, keep=2)
+    try:
+        assert f.delivered == 0
+        for k in range(6):
+            if k % 2 == 0:
+                pv = f.peek()
+                assert f.peek() is pv and f.delivered == k
+            view, lab, ll, tsl = next(f)
+            assert f.delivered == k + 1
+            assert np.array_equal(np.asarray(view), np.stack(ref[k][0])) and list(lab) == list(ref[k][1])
+            if k % 2 == 0:
+                assert view is pv[0]
+    finally:
+        f.close()

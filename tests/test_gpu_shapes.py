@@ -291,3 +291,47 @@ def test_session_feeds_from_the_page_locked_feeder_and_beam_decodes():
                     assert same >= 62, same
     finally:
         f.close()
+
+
+def test_session_device_prefetch_overlaps_the_next_batch_and_changes_nothing():
+    """Session.attach_feeder: the NEXT ring slot is copied host->device on a side stream while the current step runs; every step
+    after the first finds its input resident, and losses / decodes equal those of a session fed without the prefetch."""
+    from lstm_ctc_ocr_b200 import synthetic
+    from lstm_ctc_ocr_b200.lib.lstm.utils import gen
+    from lstm_ctc_ocr_b200.lib.networks.factory import get_network
+    from lstm_ctc_ocr_b200.session import Session
+    net = get_network("LSTM_train")
+    loss, dense_decoded = net.build_loss()
+    arg_fn = lambda k: dict(k=k, batch_size=64, render=False, seed=21, rank=0, world=1, bucket=gen.BUCKETS[k % 3])
+    results = {}
+    for mode in ("plain", "prefetch"):
+        f = gen.PrefetchFeeder(arg_fn, num_workers=2, depth=3, max_width=256, batch_size=64, keep=2)
+        try:
+            with Session(device=DEV) as sess:
+                sess.assign(net, synthetic.init_params(3, logits_scale=10.0))
+                if mode == "prefetch":
+                    sess.attach_feeder(f)
+                out = []
+                for k in range(7):
+                    view, lab, ll, tsl = next(f)
+                    feed = {net.data: view, net.labels: np.array(lab), net.time_step_len: np.array(tsl), net.labels_len: np.array(ll),
+                            net.keep_prob: 1.0}
+                    l, dec = sess.run([loss, dense_decoded], feed_dict=feed)
+                    out.append((float(l), dec.copy(), sess.last_feed_path))
+                    if mode == "prefetch" and k == 3:
+                        # a batch fed out of order (not the feeder's) must not pick up the staged copy
+                        other = np.ascontiguousarray(view[::-1])
+                        feed_o = dict(feed)
+                        feed_o[net.data] = other
+                        l_o = sess.run(loss, feed_dict=feed_o)
+                        assert sess.last_feed_path == "staged" and np.isfinite(l_o)
+                results[mode] = (out, sess.ahead_hits)
+        finally:
+            f.close()
+    plain, pre = results["plain"][0], results["prefetch"][0]
+    assert results["plain"][1] == 0
+    assert results["prefetch"][1] >= 5, results["prefetch"][1]           # steps 1..3 and 5..6 (step 4's copy was dropped by the out-of-order run)
+    assert all("device prefetch" in p[2] for p in pre[1:4])
+    for a, b in zip(plain, pre):
+        assert abs(a[0] - b[0]) <= 1e-3 * abs(a[0])                         # BN-statistic atomics may differ in the last bits
+        assert a[1].shape == b[1].shape and (a[1] == b[1]).mean() > 0.99
