@@ -317,7 +317,9 @@ def test_prefetch_feeder_delivers_the_stream_in_order():
             for k in range(7):
                 view, lab, ll, tsl = next(f)
                 assert isinstance(view, np.ndarray) and view.shape == (6, gen.BUCKETS[k % 3], 32) and view.flags.c_contiguous
-                assert np.array_equal(view, np.stack(ref[k][0])) and (lab, ll, tsl) == tuple(ref[k][1:])
+                assert np.array_equal(view, np.stack(ref[k][0]))
+                for got, want in zip((lab, ll, tsl), ref[k][1:]):             # int32 arrays of the data layer's lists
+                    assert isinstance(got, np.ndarray) and got.dtype == np.int32 and got.tolist() == list(want)
                 held.append((k, view))
                 for kk, v in held[-3:]:                                         # the last `depth` views are still valid
                     assert np.array_equal(v, np.stack(ref[kk][0]))
