@@ -331,6 +331,12 @@ def main():
         ms_feed, e2e_loss = timed(feed_step, Ke)
         h2d_b, d2h_b = int(sess.h2d_bytes), int(sess.d2h_bytes)
         feed_path = sess.last_feed_path
+        prefetch_hits = int(sess.ahead_hits)
+        # the same feeder WITHOUT the device prefetch: every step's H2D copy (4 chunks, overlapped with conv1..conv3_2) inside its own step
+        sess.attach_feeder(None)
+        for i in range(4):
+            feed_step(i)
+        ms_feed_instep, _ = timed(feed_step, Ke)
     finally:
         sess.attach_feeder(None)
         feeder.close()
@@ -455,8 +461,13 @@ def main():
                     "d2h_bytes_per_step": d2h_b, "steps": Ke, "api": "Session.run(loss, feed_dict=host numpy)",
                     "feed": f"PrefetchFeeder: a fresh batch every step, written by {nwork} producer processes into page-locked "
                             f"shared-memory ring slots, DMA'd in place ({feed_path})",
+                    "pipelining": ("Session.attach_feeder: the H2D copy of step i+1's ring slot (and its integer feeds) is issued on a side stream once step i's "
+                                   f"kernels are enqueued, step i+1 waits for it on the GPU; every timed step issues one {h2d_b / 1e6:.1f} MB copy and consumes one "
+                                   f"(prefetch hits so far: {prefetch_hits}); the loss is read back synchronously every step"),
                     "loss": float(e2e_loss),
                     "variants": {
+                        "feeder_copy_inside_own_step": {"value": round(world * N / (ms_feed_instep / Ke / 1e3), 1),
+                                                        "what": "same feeder without the device prefetch: the chunked H2D copy overlaps only its own step's conv front end (the r2 mid-round e2e)"},
                         "fresh_pageable_array_every_step": {"value": round(world * N / (ms_fresh / Ke / 1e3), 1), "path": fresh_path,
                                                             "what": "np.array(...) built per step as reference train.py:119-125 does; staged through pinned memory"},
                         "refed_host_buffers": {"value": round(world * N / (ms_refed / Ke / 1e3), 1),
