@@ -342,9 +342,19 @@ def main():
         feeder.close()
     # (b) fresh pageable array every step
     fresh = [np.array(batches[i % nrot][5][0]) for i in range(Ke + 2)]
-    run_on(fresh[0], *batches[0][5][1:]); run_on(fresh[1], *batches[1 % nrot][5][1:])
-    ms_fresh, _ = timed(lambda i: run_on(fresh[i + 2], *batches[(i + 2) % nrot][5][1:]), Ke)
-    fresh_path = sess.last_feed_path
+    try:
+        run_on(fresh[0], *batches[0][5][1:]); run_on(fresh[1], *batches[1 % nrot][5][1:])
+        ms_fresh, l_fresh = timed(lambda i: run_on(fresh[i + 2], *batches[(i + 2) % nrot][5][1:]), Ke)
+        fresh_path = sess.last_feed_path + (" (host-thread pool -> page-locked staging, pipelined with the DMA: crnn_forward_pageable)"
+                                            if sess.h2d_chunks > 1 and sess.pageable_pool else "")
+        # same inputs through the resident-input forward: the side statistic must not be the only check of this path
+        ref_l = float(model.total_loss(engine.ctc_loss(model.forward(batches[(Ke + 1) % nrot][0], batches[(Ke + 1) % nrot][3]), batches[(Ke + 1) % nrot][1],
+                                                       batches[(Ke + 1) % nrot][2], batches[(Ke + 1) % nrot][3],
+                                                       max_label_len=batches[(Ke + 1) % nrot][4])[0]).item())
+        if not abs(float(l_fresh) - ref_l) <= 2e-3 * abs(ref_l):
+            fresh_path += f" LOSS MISMATCH {float(l_fresh)} vs {ref_l}"
+    except Exception as e:                    # never lose the bench line over a variant
+        ms_fresh, fresh_path = float("inf"), "failed: " + repr(e)[:200]
     del fresh
     # (c) the same host buffers re-fed
     for i in range(max(3, 3 * nrot)):

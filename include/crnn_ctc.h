@@ -132,6 +132,20 @@ int     crnn_forward_host(crnn_model* m, const float* host_data, float* data_sta
                           int N, int W, float* logits_out, void* workspace, size_t workspace_bytes, int chunks,
                           crnn_stream_t stream, crnn_stream_t copy_stream);
 
+/* Same forward, fed from ORDINARY (pageable) host memory -- the reference's solver builds a fresh np.array(...) batch every
+ * iteration (lib/lstm/train.py:119-125).  Every image range is first moved into the caller's page-locked `pinned_staging`
+ * [N,W,32] by `host_threads` host threads (a persistent pool inside the library), then DMA'd and processed as in
+ * crnn_forward_host; the host moves range c+1 while the GPU copies / computes range c.  The caller must not touch
+ * `pinned_staging` until the copies issued on `copy_stream` have completed. */
+int     crnn_forward_pageable(crnn_model* m, const float* pageable_data, float* pinned_staging, float* data_staging,
+                              const int* time_step_len, int N, int W, float* logits_out, void* workspace,
+                              size_t workspace_bytes, int chunks, int host_threads, crnn_stream_t stream,
+                              crnn_stream_t copy_stream);
+
+/* The host-side copy crnn_forward_pageable uses, on its own: `bytes` from `src` to `dst` (plain host pointers, non-overlapping) split
+ * over `threads` threads of the library's persistent pool (the caller's thread included).  No CUDA call is made. */
+int     crnn_host_copy(void* dst, const void* src, size_t bytes, int threads);
+
 /* loss = mean_n(costs) + weight_decay * 0.5 * sum(w^2) over conv kernels + logits matrix
  * (lib/networks/network.py:655,660-662).  loss_out: 1 f32 on device. */
 int     crnn_total_loss(crnn_model* m, const float* costs, int N, float* loss_out,

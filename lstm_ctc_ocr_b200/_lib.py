@@ -38,6 +38,9 @@ SIGNATURES = {
     "crnn_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "crnn_forward_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_int,
                                   c_void_p, c_void_p]),
+    "crnn_forward_pageable": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_int,
+                                      c_int, c_void_p, c_void_p]),
+    "crnn_host_copy": (c_int, [c_void_p, c_void_p, c_size_t, c_int]),
     "crnn_total_loss": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "crnn_debug_tap": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "crnn_profile_begin": (c_int, [c_void_p, c_int]),

@@ -6,6 +6,9 @@
 #include <vector>
 
 #include <cstdlib>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 
 #include "gemm_launch.h"
 #include "lstm.cuh"
@@ -429,12 +432,79 @@ int ensure_plan(crnn_model* m, int N, int W, void* ws, cudaStream_t st) {
   return CRNN_OK;
 }
 
+// ---- host-side copy pool (crnn_forward_pageable): a pageable numpy batch has to be moved into page-locked staging before it can
+// be DMA'd; one thread moves 33.6 MB at 4-10 GB/s (3-8 ms, longer than the whole GPU step).  A few persistent workers split every
+// copy; the caller copies one share itself and waits for the rest.
+namespace {
+class CopyPool {
+ public:
+  static CopyPool& get() { static CopyPool* p = new CopyPool(); return *p; }   // leaked on purpose: workers may outlive static destructors
+  void copy(void* dst, const void* src, size_t bytes, int threads) {
+    if (threads > kMax + 1) threads = kMax + 1;
+    if (threads < 2 || bytes < (1u << 20)) { memcpy(dst, src, bytes); return; }
+    std::unique_lock<std::mutex> call_lock(call_mu_);                // one copy at a time
+    ensure(threads - 1);
+    const size_t share = ((bytes / threads) + 4095) & ~size_t(4095);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      dst_ = static_cast<uint8_t*>(dst); src_ = static_cast<const uint8_t*>(src); bytes_ = bytes; share_ = share;
+      active_ = threads - 1; pending_ = threads - 1; ++gen_;
+    }
+    cv_.notify_all();
+    const size_t own = (size_t)(threads - 1) * share;               // the caller takes the last share
+    if (own < bytes) memcpy(static_cast<uint8_t*>(dst) + own, static_cast<const uint8_t*>(src) + own, bytes - own);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [&] { return pending_ == 0; });
+  }
+
+ private:
+  static constexpr int kMax = 15;
+  void ensure(int n) {
+    while ((int)workers_.size() < n) {
+      const int id = (int)workers_.size();
+      workers_.emplace_back([this, id] { run(id); });
+      workers_.back().detach();
+    }
+  }
+  void run(int id) {
+    uint64_t seen = 0;
+    for (;;) {
+      uint8_t* d; const uint8_t* s; size_t n, share;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (id >= active_) continue;
+        d = dst_; s = src_; n = bytes_; share = share_;
+      }
+      const size_t b = (size_t)id * share;
+      if (b < n) memcpy(d + b, s + b, (b + share <= n) ? share : n - b);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  std::mutex mu_, call_mu_;
+  std::condition_variable cv_, done_;
+  std::vector<std::thread> workers_;
+  uint8_t* dst_ = nullptr; const uint8_t* src_ = nullptr;
+  size_t bytes_ = 0, share_ = 0;
+  int active_ = 0, pending_ = 0;
+  uint64_t gen_ = 0;
+};
+}  // namespace
+
 // Forward pass.  `host_data` != nullptr (crnn_forward_host): the batch is still in page-locked HOST memory; it is cut into
 // `chunks` image ranges whose H2D copies run on `copy_st` while the batch-independent front end (conv1 .. conv3_2 + pools) of
 // the previous range runs on `st` -- the copy (33.6 MB at batch 1024 x 32x256, ~0.65 ms over PCIe 5) hides behind ~0.9 ms of
 // compute instead of preceding it.  From conv4_1 on (batch-statistics BatchNorm) the batch is processed whole.
+// `pageable_src` != nullptr (crnn_forward_pageable): the batch is in ordinary host memory; every range is first moved into the
+// page-locked `host_data` staging by the copy pool, its DMA is issued, its front end is launched -- and the host moves the next
+// range while the GPU works on this one.
 static int forward_impl(crnn_model* m, const float* data, const float* host_data, const int* time_step_len, int N, int W,
-                        float* logits_out, void* workspace, size_t workspace_bytes, int chunks, cudaStream_t st, cudaStream_t copy_st) {
+                        float* logits_out, void* workspace, size_t workspace_bytes, int chunks, cudaStream_t st, cudaStream_t copy_st,
+                        const float* pageable_src = nullptr, int host_threads = 1) {
   if (!m || !data || !time_step_len || !logits_out || !workspace) return crnn_fail(CRNN_INVALID_VALUE, "forward: null pointer");
   if (!m->params) return crnn_fail(CRNN_NOT_BOUND, "forward: call crnn_model_bind first");
   if (N <= 0 || W < 8 || (W % 4) != 0) return crnn_fail(CRNN_INVALID_VALUE, "forward: need N>0, W>=8, W%%4==0");
@@ -445,6 +515,7 @@ static int forward_impl(crnn_model* m, const float* data, const float* host_data
   if (m->cfg.compute_dtype >= 2) {
     // f32-class paths (forward_x3.cu): copy-then-compute when fed from host memory
     if (host_data != nullptr) {
+      if (pageable_src != nullptr) CopyPool::get().copy(const_cast<float*>(host_data), pageable_src, (size_t)N * W * 32 * sizeof(float), host_threads);
       CUDA_TRY(cudaMemcpyAsync(const_cast<float*>(data), host_data, (size_t)N * W * 32 * sizeof(float), cudaMemcpyHostToDevice, st));
     }
     return x3_forward(m, data, time_step_len, N, W, logits_out, workspace, workspace_bytes, st);
@@ -475,7 +546,7 @@ static int forward_impl(crnn_model* m, const float* data, const float* host_data
     // the staging tensor may still be read by work queued earlier on `st` (previous forward / backward)
     CUDA_TRY(cudaEventRecord(m->chunk_events[kMaxChunks], st));
     CUDA_TRY(cudaStreamWaitEvent(copy_st, m->chunk_events[kMaxChunks], 0));
-    for (int c = 0; c * nc < N; ++c) {
+    for (int c = 0; pageable_src == nullptr && c * nc < N; ++c) {
       const int n0 = c * nc, n1 = (n0 + nc < N) ? n0 + nc : N;
       const size_t off = (size_t)n0 * W * 32;
       CUDA_TRY(cudaMemcpyAsync(const_cast<float*>(data) + off, host_data + off, (size_t)(n1 - n0) * W * 32 * sizeof(float),
@@ -486,6 +557,13 @@ static int forward_impl(crnn_model* m, const float* data, const float* host_data
   for (int c = 0; c * nc < N; ++c) {
     const int n0 = c * nc, n1 = (n0 + nc < N) ? n0 + nc : N, cn = n1 - n0;
     const bool mark = (n1 == N) && chunks == 1;      // per-stage events only make sense for an unchunked front end
+    if (pageable_src != nullptr) {
+      // pageable source: move this range into the page-locked staging now (the GPU is busy with the previous range), then issue its DMA
+      const size_t off = (size_t)n0 * W * 32, bytes = (size_t)cn * W * 32 * sizeof(float);
+      CopyPool::get().copy(const_cast<float*>(host_data) + off, pageable_src + off, bytes, host_threads);
+      CUDA_TRY(cudaMemcpyAsync(const_cast<float*>(data) + off, host_data + off, bytes, cudaMemcpyHostToDevice, copy_st));
+      CUDA_TRY(cudaEventRecord(m->chunk_events[c], copy_st));
+    }
     if (host_data != nullptr) CUDA_TRY(cudaStreamWaitEvent(st, m->chunk_events[c], 0));
     // conv1 + pool1 (SIMT: K = 9)
     {
@@ -696,6 +774,21 @@ extern "C" int crnn_forward_host(crnn_model* m, const float* host_data, float* d
   if (!host_data || !data_staging) return crnn_fail(CRNN_INVALID_VALUE, "forward_host: null pointer");
   return forward_impl(m, data_staging, host_data, time_step_len, N, W, logits_out, workspace, workspace_bytes, chunks,
                       reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<cudaStream_t>(copy_stream));
+}
+
+extern "C" int crnn_host_copy(void* dst, const void* src, size_t bytes, int threads) {
+  if ((!dst || !src) && bytes) return crnn_fail(CRNN_INVALID_VALUE, "host_copy: null pointer");
+  CopyPool::get().copy(dst, src, bytes, threads < 1 ? 1 : threads);
+  return CRNN_OK;
+}
+
+extern "C" int crnn_forward_pageable(crnn_model* m, const float* pageable_data, float* pinned_staging, float* data_staging,
+                                     const int* time_step_len, int N, int W, float* logits_out, void* workspace, size_t workspace_bytes,
+                                     int chunks, int host_threads, crnn_stream_t stream, crnn_stream_t copy_stream) {
+  if (!pageable_data || !pinned_staging || !data_staging) return crnn_fail(CRNN_INVALID_VALUE, "forward_pageable: null pointer");
+  return forward_impl(m, data_staging, pinned_staging, time_step_len, N, W, logits_out, workspace, workspace_bytes, chunks,
+                      reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<cudaStream_t>(copy_stream), pageable_data,
+                      host_threads < 1 ? 1 : host_threads);
 }
 
 // ------------------------------------------------------------------------------------------------ profiling

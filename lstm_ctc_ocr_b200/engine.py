@@ -164,6 +164,27 @@ class CrnnModel:
             self._copy_stream.synchronize()
         return out, self._stage
 
+    def forward_pageable(self, host_data, pinned, time_step_len, chunks=4, host_threads=8, out=None):
+        """host_data: C-contiguous f32 numpy array [N,W,32] in ORDINARY memory (the reference's np.array(...) per step); `pinned`: a
+        page-locked f32 torch tensor with at least N*W*32 elements.  Range by range the library's host threads move the batch into
+        `pinned`, DMA it and run the conv front end (crnn_forward_pageable).  Returns (logits, device data, copy stream)."""
+        N, W, Hh = host_data.shape
+        if Hh != 32:
+            raise CrnnError("data must be [N, W, 32] (cfg.NUM_FEATURES = 32)")
+        assert host_data.dtype == np.float32 and host_data.flags.c_contiguous and pinned.is_pinned() and pinned.numel() >= host_data.size
+        T = W // 4 - 1
+        if out is None:
+            out = torch.empty((T, N, NCLASSES), dtype=torch.float32, device=self.device)
+        if getattr(self, "_stage", None) is None or self._stage.shape != (N, W, 32):
+            self._stage = torch.empty((N, W, 32), dtype=torch.float32, device=self.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        ws, nbytes = self._workspace(N, W)
+        check(self.lib.crnn_forward_pageable(self.handle, host_data.ctypes.data, pinned.data_ptr(), self._stage.data_ptr(),
+                                             time_step_len.data_ptr(), N, W, out.data_ptr(), ws, nbytes, int(chunks), int(host_threads),
+                                             _stream(), self._copy_stream.cuda_stream))
+        return out, self._stage, self._copy_stream
+
     def tap(self, name, N, W):
         """Intermediate of the last forward as f32 NHWC (tests only)."""
         H1, H2 = W // 2, W // 4

@@ -90,6 +90,20 @@ class _Pinned(object):
         ev.record()
         return {k: d[offs[k]:offs[k] + a.size].view(a.shape) for k, a in arrays.items()}
 
+    def staging_for(self, name, numel):
+        """Page-locked f32 staging buffer `name` with room for `numel` elements, safe to overwrite (the previous DMA out of it has
+        completed), and the event the caller must record after issuing the next DMA out of it."""
+        t = self.bufs.get(name)
+        if t is None or t.numel() < numel or t.dtype != torch.float32:
+            t = self.bufs[name] = torch.empty(max(numel, 1), dtype=torch.float32).pin_memory()
+            self.events.pop(name, None)
+        ev = self.events.get(name)
+        if ev is not None:
+            ev.synchronize()
+        else:
+            ev = self.events[name] = torch.cuda.Event()
+        return t, ev
+
     def stage(self, name, arr, device):
         arr = np.ascontiguousarray(arr)
         tdt = _NP2T[arr.dtype]
@@ -128,6 +142,8 @@ class Session(object):
         self.last_feed_path = None    # "page-locked in place" (chunked crnn_forward_host) | "staged" (copy into pinned staging first)
         import os
         self.h2d_chunks = int(os.environ.get("CRNN_H2D_CHUNKS", "4"))   # image ranges of the overlapped host->device feed (1 = copy, then compute)
+        self.pageable_pool = not os.environ.get("CRNN_NO_PAGEABLE_POOL")   # large pageable batches through crnn_forward_pageable (else: torch copy into staging, then copy-then-compute)
+        self.host_copy_threads = int(os.environ.get("CRNN_HOST_COPY_THREADS", str(min(8, os.cpu_count() or 1))))   # pageable -> pinned staging copies
         # device prefetch (attach_feeder): the NEXT batch of a PrefetchFeeder is copied host->device on a side stream while the
         # current step computes -- what tf.data's prefetch_to_device does for a TF input pipeline
         self._feeder = None
@@ -306,10 +322,19 @@ class Session(object):
             logits = eng.forward(d_data, d_tsl)
             self.last_feed_path = "page-locked in place, copied during the previous step (device prefetch)"
             self.ahead_hits += 1
-        elif self.h2d_chunks > 1 and self._pinned.is_page_locked(data):
-            # large re-fed batch buffer (page-locked in place): chunked H2D overlapped with the conv front end
+        elif self.h2d_chunks > 1 and (self._pinned.is_page_locked(data) or
+                                      (data.nbytes >= self._pinned.REGISTER_MIN_BYTES and data.flags.owndata and self._pinned._registered(data))):
+            # page-locked batch buffer (a feeder's ring slot, or a large array fed a second time and registered in place now):
+            # chunked H2D overlapped with the conv front end
             logits, d_data = eng.forward_host(data, d_tsl, chunks=self.h2d_chunks)
             self.last_feed_path = "page-locked in place"
+        elif self.pageable_pool and self.h2d_chunks > 1 and data.nbytes >= self._pinned.REGISTER_MIN_BYTES:
+            # large batch in ordinary memory (the reference's np.array(...) per step): the library's host threads move it into
+            # page-locked staging range by range while the GPU copies / computes the previous range (crnn_forward_pageable)
+            pin, ev = self._pinned.staging_for("data", data.size)
+            logits, d_data, cst = eng.forward_pageable(data, pin, d_tsl, chunks=self.h2d_chunks, host_threads=self.host_copy_threads)
+            ev.record(cst)
+            self.last_feed_path = "staged"
         else:
             d_data = self._pinned.stage("data", data, dev)
             logits = eng.forward(d_data, d_tsl)

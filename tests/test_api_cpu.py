@@ -355,3 +355,27 @@ def test_prefetch_feeder_peek_does_not_reorder_or_skip():
                 assert view is pv[0]
     finally:
         f.close()
+
+
+def test_host_copy_pool_moves_every_byte_for_any_size_and_thread_count():
+    """crnn_host_copy: the persistent thread pool behind crnn_forward_pageable (pageable numpy batch -> page-locked staging).  No GPU
+    needed.  Sizes around the share / page boundaries, thread counts beyond the pool size, many back-to-back calls (a lost wake-up
+    would hang here under the test timeout, not on the GPU box)."""
+    from lstm_ctc_ocr_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    src = rng.integers(0, 255, size=(40 << 20) + 77, dtype=np.uint8)
+    dst = np.zeros_like(src)
+    sizes = [0, 1, 4095, 4096, (1 << 20) - 1, 1 << 20, (1 << 20) + 1, 3 * (1 << 20) + 4097, (33 << 20) + 5, src.size]
+    for rep in range(3):
+        for n in sizes:
+            for threads in (1, 2, 3, 8, 16, 64):
+                dst[:n + 16] = 0 if n + 16 <= dst.size else 0
+                assert lib.crnn_host_copy(dst.ctypes.data, src.ctypes.data, n, threads) == 0
+                assert np.array_equal(dst[:n], src[:n]) and (n + 16 > dst.size or not dst[n:n + 16].any()), (n, threads)
+    for i in range(400):                                                        # back-to-back small-large alternation
+        n = int(rng.integers(1 << 20, 6 << 20))
+        t = int(rng.integers(2, 12))
+        dst[:n] = 0
+        assert lib.crnn_host_copy(dst.ctypes.data, src.ctypes.data, n, t) == 0
+        assert dst[n - 1] == src[n - 1] and dst[0] == src[0] and dst[n // 2] == src[n // 2]

@@ -335,3 +335,27 @@ def test_session_device_prefetch_overlaps_the_next_batch_and_changes_nothing():
     for a, b in zip(plain, pre):
         assert abs(a[0] - b[0]) <= 1e-3 * abs(a[0])                         # BN-statistic atomics may differ in the last bits
         assert a[1].shape == b[1].shape and (a[1] == b[1]).mean() > 0.99
+
+
+def test_pageable_batches_go_through_the_host_copy_pool_and_change_nothing():
+    """crnn_forward_pageable (what Session.run does with the reference's np.array(...)-per-step feeds, lib/lstm/train.py:119-125): the
+    library's host threads move the batch into page-locked staging range by range; logits equal those of the resident-input forward
+    bit for bit except for the order of the BN-statistic atomics, for 1 and for 4 ranges, at a size that does and one that does not
+    split on tile boundaries."""
+    from lstm_ctc_ocr_b200 import engine, synthetic
+    m = engine.CrnnModel(device=DEV)
+    m.load_params(synthetic.init_params(3, logits_scale=10.0))
+    for N, W in ((64, 256), (6, 100)):
+        data, _, _, tsl = synthetic.synth_batch(N, W, seed=9)
+        d_tsl = torch.tensor(tsl, device=DEV)
+        ref = m.forward(torch.tensor(data, device=DEV), d_tsl).clone()
+        pin = torch.empty(data.size, dtype=torch.float32).pin_memory()
+        for chunks, threads in ((1, 1), (4, 3), (4, 8)):
+            pin.fill_(-7.0)
+            src = np.array(data)                                            # fresh pageable copy, as the reference's solver builds
+            out, d_data, cst = m.forward_pageable(src, pin, d_tsl, chunks=chunks, host_threads=threads)
+            torch.cuda.synchronize()
+            assert np.array_equal(pin[:data.size].numpy().reshape(data.shape), data)
+            assert torch.equal(d_data.cpu(), torch.from_numpy(data))
+            err = float((out - ref).abs().max() / ref.abs().max())
+            assert err < 1e-3, (N, W, chunks, threads, err)
