@@ -5,14 +5,21 @@ THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``,
 reference`` legs may import it.  The product path (``lstm_ctc_ocr_b200``) never
 imports anything under ``oracle/``.
 
-PARITY UNPINNED: the reference ships no tests or golden vectors, and its
-arithmetic lives in TensorFlow 1.0.1 and baidu warp-ctc, neither of which is
-importable here (no wheels for Python 3.12, no network).  This file restates
-the *published* semantics of those ops at the reference's own call sites; it is
-cross-checked against independent implementations (torch ``F.ctc_loss``,
-``torch.nn.LSTM`` with permuted gates, brute-force CTC path enumeration,
-finite differences) in ``tests/test_oracle.py``, not against a run of the
-reference itself.
+PARITY UNPINNED against the reference itself: it ships no tests or golden
+vectors, and its arithmetic lives in TensorFlow 1.0.1 and baidu warp-ctc,
+neither of which is importable here (no wheels for Python 3.12, no network).
+This file restates the *published* semantics of those ops at the reference's
+own call sites.  What it IS pinned to (``tests/test_oracle.py``):
+  * the known answers those two third-party projects hold in their own unit
+    tests for the loss / decode call sites of network.py:653-657
+    (``tests/golden/third_party_kats.py``: tf.nn.ctc_loss testBasic == warp-ctc
+    options_test -- costs to the 6 published digits, all 60 gradient entries to
+    1e-6; ctc_greedy_decoder; ctc_beam_search_decoder's beam_width-2 vector,
+    which only TF's candidate ordering / eviction rule reproduces);
+  * independent implementations for everything else (torch ``F.ctc_loss``,
+    ``torch.nn.LSTM`` with permuted gates, ``F.batch_norm``, brute-force CTC
+    path enumeration, fp64 finite differences through the whole graph).
+The conv / BN / LSTM / Adam restatements have no externally held vector.
 
 Reference call sites restated (paths relative to /root/reference):
   * topology / hyper-parameters ......... lib/networks/LSTM_train.py:22-38

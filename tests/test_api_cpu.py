@@ -254,6 +254,21 @@ def test_beam_search_matches_oracle_restatement(kind, seed):
     assert _beam(x, il, beam_width=3)[0] == O.beam_search_decode(x, il, beam_width=3)
 
 
+def test_beam_search_reproduces_tensorflows_own_known_answer():
+    """crnn_ctc_beam_search on the vector TensorFlow's ctc_decoder_ops_test.py::testCTCDecoderBeamSearch pins
+    (tests/golden/third_party_kats.py): top path [1, 0] at beam_width 2 (6 classes, blank 5, unnormalised log p + 2), the
+    most probable labelling [0, 1, 0] at every other width.  The product decoder against a number held by the project it
+    replaces (network.py:656), not against the oracle."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("third_party_kats", os.path.join(ROOT, "tests", "golden", "third_party_kats.py"))
+    K = importlib.util.module_from_spec(spec); spec.loader.exec_module(K)
+    x, il = K.beam_case()
+    x = x.astype(np.float32)
+    assert _beam(x, il, beam_width=K.BEAM_WIDTH, merge_repeated=True, strip=-1)[0] == [K.BEAM_TOP_PATHS[0]]
+    for bw in (1, 3, 100):
+        assert _beam(x, il, beam_width=bw, merge_repeated=True, strip=-1)[0] == [K.BEAM_TOP_PATHS[1]]
+
+
 def test_beam_search_rejects_bad_lengths():
     from lstm_ctc_ocr_b200 import engine
     from lstm_ctc_ocr_b200._lib import CrnnError

@@ -220,3 +220,58 @@ def test_finite_difference_full_graph():
         fd = (vals[0] - vals[1]) / (2 * eps)
         an = float(out["grads"][name][idx])
         assert abs(fd - an) <= 1e-6 * max(1.0, abs(an)), (name, fd, an)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Known answers held by the third-party projects behind network.py:653-657 (TensorFlow's and warp-ctc's own unit tests):
+# the one place the oracle is pinned to numbers it did not produce itself.  tests/golden/third_party_kats.py has provenance.
+# ---------------------------------------------------------------------------------------------------------------------------
+def _kats():
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "third_party_kats.py")
+    spec = importlib.util.spec_from_file_location("third_party_kats", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("blank,C", [(5, 6), (0, 6), (0, 64)])
+def test_third_party_known_answers_ctc_loss_and_gradient(blank, C):
+    """tf.nn.ctc_loss testBasic == warp-ctc options_test: costs to the 6 published digits, gradient w.r.t. the unnormalised
+    activations to 1e-6, in TF's class numbering (blank 5), in warp-ctc's default numbering (blank 0, network.py:653) and
+    embedded in the 64-class layout the product kernels take."""
+    K = _kats()
+    x, flat, ll, il, cost, grad = K.ctc_case(num_classes=C, blank=blank)
+    costs, g = O.ctc_loss_np(x, flat, ll, il, blank=blank)
+    assert np.allclose(costs, cost, rtol=0, atol=6e-6), costs          # published with 6 significant digits
+    assert np.abs(g - grad).max() < 2e-6
+    # the differentiable restatement used for whole-graph autograd agrees too
+    xt = torch.tensor(x, requires_grad=True)
+    ct = O.ctc_loss_torch(xt, flat, ll, il, blank=blank)
+    ct.sum().backward()
+    assert np.allclose(ct.detach().numpy(), cost, rtol=0, atol=6e-6)
+    assert np.abs(xt.grad.numpy() - grad).max() < 2e-6
+
+
+def test_third_party_known_answers_greedy_decoder():
+    """tf.nn.ctc_greedy_decoder testCTCGreedyDecoder (merge_repeated=True, frames past seq_len ignored), with TF's blank in its
+    own place (class 3 of 4) and moved to class 63 of 64 (network.py:656 numbering)."""
+    K = _kats()
+    for C, blank in ((4, 3), (64, 63)):
+        x, il, want = K.greedy_case(num_classes=C, blank=blank)
+        assert O.greedy_decode(x, il, tf_blank=blank, strip=-1) == want
+    # the solver's zero stripping (training.py:32) on top of it
+    x, il, want = K.greedy_case()
+    assert O.greedy_decode(x, il, tf_blank=3, strip=0) == [[1], [1, 1]]
+
+
+def test_third_party_known_answers_beam_search_decoder():
+    """tf.nn.ctc_beam_search_decoder testCTCDecoderBeamSearch: at beam_width 2 TF's top path is [1, 0] -- NOT the most
+    probable labelling [0, 1, 0], which every other width returns -- so the vector pins the candidate ordering and the
+    eviction rule of the restatement, not just its probabilities."""
+    K = _kats()
+    x, il = K.beam_case()
+    assert O.beam_search_decode(x, il, beam_width=K.BEAM_WIDTH, merge_repeated=True, strip=-1) == [K.BEAM_TOP_PATHS[0]]
+    for bw in (1, 3, 100):
+        assert O.beam_search_decode(x, il, beam_width=bw, merge_repeated=True, strip=-1) == [K.BEAM_TOP_PATHS[1]]
