@@ -195,6 +195,18 @@ def conv_single(x, w_hwio, b, bn=None, relu=True, padding="SAME"):
     return y, stats
 
 
+def lstm_cell(xt, c, h, w, b):
+    """One step of tf.contrib.rnn.LSTMCell (no peepholes, no projection; identical to BasicLSTMCell): w [(in+H), 4H] with rows
+    [x; h], gate columns i,j,f,o, forget_bias 1.0.  Pinned to TensorFlow's own known answer (rnn_cell_test.py::testBasicLSTMCell)
+    in tests/test_oracle.py::test_third_party_known_answer_lstm_cell."""
+    H = w.shape[1] // 4
+    z = torch.cat([xt, h], dim=1) @ w + b                          # [x,h] concat order
+    i, j, f, o = z.split(H, dim=1)                                # TF gate order i,j,f,o
+    c_new = torch.sigmoid(f + 1.0) * c + torch.sigmoid(i) * torch.tanh(j)   # forget_bias=1.0
+    h_new = torch.sigmoid(o) * torch.tanh(c_new)
+    return c_new, h_new
+
+
 def lstm_direction(x, seq_len, w, b, reverse):
     """One tf.contrib.rnn.LSTMCell(256) under dynamic_rnn(sequence_length)
     (network.py:104-107).  x [N,T,512]; returns [N,T,256] with zeros past len."""
@@ -212,10 +224,7 @@ def lstm_direction(x, seq_len, w, b, reverse):
         else:
             t_idx = torch.full_like(lens, s)
         xt = x[ar, t_idx]                                         # [N,512]
-        z = torch.cat([xt, h], dim=1) @ w + b                      # [x,h] concat order
-        i, j, f, o = z.split(H, dim=1)                            # TF gate order i,j,f,o
-        c_new = torch.sigmoid(f + 1.0) * c + torch.sigmoid(i) * torch.tanh(j)   # forget_bias=1.0
-        h_new = torch.sigmoid(o) * torch.tanh(c_new)
+        c_new, h_new = lstm_cell(xt, c, h, w, b)
         m = active[:, None].to(x.dtype)
         c = m * c_new + (1 - m) * c                               # state carried past len
         h = m * h_new + (1 - m) * h

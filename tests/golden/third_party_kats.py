@@ -13,6 +13,9 @@ Provenance [upstream-memory -- transcribed, not fetched: there is no network]:
   * BEAM: same file, testCTCDecoderBeamSearch (6 classes, blank = class 5, beam_width = 2, merge_repeated: the top path the
     test pins is [1, 0] although [0, 1, 0] carries more probability mass and wins at any beam width != 2 -- a vector that
     only an implementation with TF's candidate ordering and eviction rule reproduces).
+  * LSTM_CELL: tensorflow/python/kernel_tests/rnn_cell_test.py::RNNCellTest.testBasicLSTMCell (two stacked 2-unit cells, every
+    weight 0.5, zero biases, forget_bias 1.0, input [1, 1], every state entry 0.1; state_is_tuple=False packs [c, h] per layer).
+    Uniform weights cannot tell gate ORDER apart; they pin the cell equations and the forget bias.
 
 Self-check of the transcription: `tests/test_oracle.py::test_third_party_known_answers_*` recomputes the two losses from the
 matrices with an fp64 alpha recursion and gets 3.342113 and 5.422622 -- six matching digits on values nobody could guess --
@@ -115,3 +118,11 @@ def beam_case():
     x = np.zeros((8, 1, 6), np.float64)
     x[:6, 0] = np.log(BEAM_PROBS) + 2.0
     return x, np.asarray([BEAM_SEQ_LEN], np.int32)
+
+
+# ---- rnn_cell_test.py::testBasicLSTMCell ----------------------------------------------------------------------------------
+LSTM_X = np.asarray([[1.0, 1.0]])
+LSTM_STATE0 = 0.1                                   # every entry of [c1, h1, c2, h2]
+LSTM_WEIGHT = 0.5                                   # constant_initializer(0.5) for both [4, 8] matrices; biases 0
+LSTM_OUT = np.asarray([[0.24024698, 0.24024698]])
+LSTM_STATE = np.asarray([[0.68967271, 0.68967271, 0.44848421, 0.44848421, 0.39897051, 0.39897051, 0.24024698, 0.24024698]])

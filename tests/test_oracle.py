@@ -275,3 +275,16 @@ def test_third_party_known_answers_beam_search_decoder():
     assert O.beam_search_decode(x, il, beam_width=K.BEAM_WIDTH, merge_repeated=True, strip=-1) == [K.BEAM_TOP_PATHS[0]]
     for bw in (1, 3, 100):
         assert O.beam_search_decode(x, il, beam_width=bw, merge_repeated=True, strip=-1) == [K.BEAM_TOP_PATHS[1]]
+
+
+def test_third_party_known_answer_lstm_cell():
+    """TensorFlow's rnn_cell_test.py::testBasicLSTMCell: c' = sigmoid(f + 1) c + sigmoid(i) tanh(j), h' = sigmoid(o) tanh(c')
+    with [x, h] @ W -- the cell lstm_direction steps (network.py:104-107), to the published f32 digits."""
+    K = _kats()
+    w = torch.full((4, 8), K.LSTM_WEIGHT, dtype=torch.float64)
+    b = torch.zeros(8, dtype=torch.float64)
+    s0 = torch.full((1, 2), K.LSTM_STATE0, dtype=torch.float64)
+    c1, h1 = O.lstm_cell(torch.tensor(K.LSTM_X), s0, s0, w, b)
+    c2, h2 = O.lstm_cell(h1, s0, s0, w, b)
+    assert np.allclose(h2.numpy(), K.LSTM_OUT, rtol=0, atol=2e-7)
+    assert np.allclose(torch.cat([c1, h1, c2, h2], 1).numpy(), K.LSTM_STATE, rtol=0, atol=2e-7)
