@@ -81,8 +81,9 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def cpu_reference(N, W, steps, warmup, seed=3):
-    """The reference's CPU path: the op-for-op fp32 restatement (oracle port) on all host cores."""
+def cpu_reference(N, W, steps, warmup, seed=3, run_budget_s=None, n_max=None):
+    """The reference's CPU path: the op-for-op fp32 restatement (oracle port) on all host cores.  `run_budget_s`: grow the
+    per-step sample from N towards `n_max` (powers of two) as far as warmup+steps steps fit in that many seconds."""
     import torch
     from oracle import crnn_oracle as O
     p32 = O.to_torch(O.init_params(seed, dtype=np.float32), torch.float32)
@@ -91,15 +92,25 @@ def cpu_reference(N, W, steps, warmup, seed=3):
     # 128-core host, so try a ladder of thread counts once and keep the best (reported as `cores`)
     ncpu = os.cpu_count() or 1
     best = (None, 1e30)
+    q = max(1, N // 4)
     for nt in sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)}):
         torch.set_num_threads(nt)
-        O.fwd_ctc_fp32(p32, data[:max(1, N // 4)], lab[:int(ll[:max(1, N // 4)].sum())], ll[:max(1, N // 4)], tsl[:max(1, N // 4)])
+        O.fwd_ctc_fp32(p32, data[:q], lab[:int(ll[:q].sum())], ll[:q], tsl[:q])
         t0 = time.perf_counter()
-        O.fwd_ctc_fp32(p32, data[:max(1, N // 4)], lab[:int(ll[:max(1, N // 4)].sum())], ll[:max(1, N // 4)], tsl[:max(1, N // 4)])
+        O.fwd_ctc_fp32(p32, data[:q], lab[:int(ll[:q].sum())], ll[:q], tsl[:q])
         dt = time.perf_counter() - t0
         if dt < best[1]:
             best = (nt, dt)
     torch.set_num_threads(best[0])
+    if run_budget_s is not None and n_max is not None and n_max > N:
+        per_step = run_budget_s / float(warmup + steps)
+        rate = q / best[1]                                  # images/s seen on the ladder's quarter sample
+        n = N
+        while n * 2 <= n_max and (n * 2) / rate <= per_step:
+            n *= 2
+        if n != N:
+            N = n
+            data, lab, ll, tsl = O.synth_batch(N, W, seed=seed)
     times = []
     loss = None
     for i in range(warmup + steps):
@@ -109,7 +120,7 @@ def cpu_reference(N, W, steps, warmup, seed=3):
         if i >= warmup:
             times.append(dt)
     t = float(np.median(times))
-    return dict(value=N / t, ms_per_step=t * 1e3, loss=loss, cores=torch.get_num_threads())
+    return dict(value=N / t, ms_per_step=t * 1e3, loss=loss, cores=torch.get_num_threads(), sample_n=N)
 
 
 def ctc_loss_delta(engine, synthetic, torch, dev, W, n_lines, seeds=(3, 4, 5), compute_dtype="bf16"):
@@ -142,19 +153,26 @@ def ctc_loss_delta(engine, synthetic, torch, dev, W, n_lines, seeds=(3, 4, 5), c
 
 
 def run_reference_arm(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path (TF1 / warp-ctc cannot be installed: the oracle's
+    fp32 torch-CPU port), on the main arm's metric and workload.  Each step is a bounded sample of that workload: as many lines
+    of 32xW (a power of two between 32 and the workload's batch) as let warmup+steps steps finish in about 90 s on this host."""
     N_full, W, desc = WORKLOADS[args.workload]
     if rank != 0:
         return
-    sample_n = min(N_full, 32)        # bounded sample of the same workload: 32 lines of 32xW per step
-    r = cpu_reference(sample_n, W, args.steps, max(args.warmup, 1))
+    steps, warmup = max(args.steps, 1), max(args.warmup, 1)
+    r = cpu_reference(min(N_full, 32), W, steps, warmup, run_budget_s=90.0, n_max=N_full)
+    sample_n = r["sample_n"]
+    sample = (f"{sample_n} lines of 32x{W} per step (the workload's batch is {N_full}; CPU throughput per line is flat in the batch "
+              f"size), median of {steps} steps after {warmup} warm-up, {r['cores']} torch threads of {os.cpu_count()} host CPUs")
     line = {
         "impl": "reference", "metric": "text-line images/sec (fwd+CTC loss)", "value": r["value"], "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "batch_per_step": sample_n, "width": W,
-                   "note": "TF1/warp-ctc not installable (py3.12, no network): op-for-op fp32 restatement on torch-CPU"},
-        "cpu_baseline": {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port",
-                         "sample": f"{sample_n} lines of 32x{W} per step, median of {args.steps} steps"},
+        "config": {"workload": desc, "batch_per_gpu": N_full, "global_batch": N_full * max(args.gpus, 1), "width": W, "T": W // 4 - 1,
+                   "reference_sample_per_step": sample_n,
+                   "note": "TF1/warp-ctc not installable (py3.12, no network): op-for-op fp32 restatement on torch-CPU, rank 0 only"},
+        "cpu_baseline": {"value": r["value"], "unit": "images/s", "cores": r["cores"], "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count()},
         "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
