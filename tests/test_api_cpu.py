@@ -394,3 +394,38 @@ def test_host_copy_pool_moves_every_byte_for_any_size_and_thread_count():
         dst[:n] = 0
         assert lib.crnn_host_copy(dst.ctypes.data, src.ctypes.data, n, t) == 0
         assert dst[n - 1] == src[n - 1] and dst[0] == src[0] and dst[n // 2] == src[n // 2]
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# bench.py contract pieces that run without a GPU
+# ---------------------------------------------------------------------------------------------------------------------------
+def test_bench_reference_arm_prints_the_contract_line_and_ours_refuses_without_a_gpu():
+    """`bench.py --impl reference` (the CPU port of the reference path, rank 0 only) prints ONE JSON line with the main arm's
+    metric / unit / workload keys, `impl`, `cpu_baseline` and a zero-copy `e2e`; a non-zero rank prints nothing and exits 0;
+    the product arm exits non-zero on a box without CUDA instead of measuring a fallback."""
+    import json
+    import subprocess
+    import sys
+    import torch
+    bench = os.path.join(ROOT, "bench.py")
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    p = subprocess.run([sys.executable, bench, "--impl", "reference", "--workload", "c1shape", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "text-line images/sec (fwd+CTC loss)" and d["unit"] == "images/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["config"]["batch_per_gpu"] == 32 and d["config"]["width"] == 100 and d["config"]["T"] == 24
+    assert d["config"]["reference_sample_per_step"] == 32
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["cores"] >= 1 and "sample" in cb
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # under torchrun only rank 0 works
+    p = subprocess.run([sys.executable, bench, "--impl", "reference", "--workload", "c1shape", "--steps", "1", "--warmup", "1", "--gpus", "2"],
+                       capture_output=True, text=True, env=dict(env, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2"), timeout=600)
+    assert p.returncode == 0 and not [l for l in p.stdout.splitlines() if l.startswith("{")]
+    if not torch.cuda.is_available():
+        p = subprocess.run([sys.executable, bench, "--steps", "1", "--warmup", "1"], capture_output=True, text=True, env=env, timeout=600)
+        assert p.returncode != 0 and "no CPU fallback" in (p.stderr + p.stdout)
