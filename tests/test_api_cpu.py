@@ -94,6 +94,25 @@ def test_config_merge_and_set(tmp_path):
     C.cfg.EXP_DIR = "default"
 
 
+def test_shipped_run_configuration_holds_the_reference_hyper_parameters():
+    """lstm_ctc_ocr_b200/lstm/lstm.yml (what train.sh / test.sh pass to --cfg) merges cleanly and carries the values the reference
+    trains with (its lstm/lstm.yml: Adam, lr 1e-4, gamma 1.0 every 2000, wd 1e-5, display 100, snapshot 2000)."""
+    import copy
+    from lstm_ctc_ocr_b200.lib.lstm import config as C
+    saved = copy.deepcopy(dict(C.cfg))
+    try:
+        C.cfg_from_file(os.path.join(ROOT, "lstm_ctc_ocr_b200", "lstm", "lstm.yml"))
+        t = C.cfg.TRAIN
+        assert (t.SOLVER, t.LEARNING_RATE, t.MOMENTUM, t.GAMMA, t.STEPSIZE, t.WEIGHT_DECAY) == ("Adam", 1e-4, 0.9, 1.0, 2000, 1e-5)
+        assert (t.DISPLAY, t.SNAPSHOT_ITERS, t.SYNC_BN, t.BATCH_SIZE) == (100, 2000, True, 64)
+        assert (C.cfg.EXP_DIR, C.cfg.LOG_DIR, C.cfg.NET_NAME, C.cfg.GPU_ID, C.cfg.DECODER) == ("lstm_ctc", "lstm_ctc", "LSTM", 0, "greedy")
+    finally:
+        for k, v in saved.items():
+            C.cfg[k] = C.AttrDict(v) if isinstance(v, dict) else v
+    for script in ("train.sh", "test.sh"):
+        assert os.access(os.path.join(ROOT, script), os.X_OK)
+
+
 def test_feed_validation():
     from lstm_ctc_ocr_b200.session import Session
     v = Session.validate_feed
