@@ -16,8 +16,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
-#include <deque>
 #include <limits>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -41,48 +41,115 @@ struct Prob {
   void reset() { total = blank = label = kLogZero; }
 };
 
+// One prefix of the tree.  Children are created on demand (only a child that enters the beam needs storage: an inactive child
+// carries no state), `kids` is a per-entry table label -> arena index that appears with the first child.
 struct Entry {
   Entry* parent = nullptr;
   int label = -1;
-  int first_child = -1;       // index into the arena of the first of (C-1) consecutive children, -1 = not populated
+  int kids = -1;              // offset of this entry's (C-1)-slot child table in the table pool, -1 = no child yet
+  int64_t leaf_seq = -1;      // insertion number while the entry is in the leaf list, -1 = not in it
+  int evicted_kid_frame = -1; // last frame in which one of this entry's children was evicted from the list
   Prob oldp, newp;
   bool active() const { return newp.total != kLogZero; }
 };
 
-// Beam-width bounded list of the current leaves; the "bottom" is the entry with the smallest newp.total.
+// The beam: entries in insertion order (what the next frame's stable sort and the final arg-max walk), plus a min-heap on
+// (total, insertion number) so that the bottom -- the FIRST of the smallest totals in insertion order, the entry a full list
+// evicts -- costs O(log width) instead of a scan per candidate.  Totals of listed entries do not change while candidates are
+// being inserted (re-scoring happens before), so the heap keys stay valid for the whole frame.
 struct Leaves {
-  std::vector<Entry*> v;
-  Entry* bottom() const {
-    Entry* b = v[0];
-    for (Entry* e : v) if (e->newp.total < b->newp.total) b = e;
-    return b;
+  struct Item { double total; int64_t seq; Entry* e; };
+  static bool above(const Item& a, const Item& b) { return a.total > b.total || (a.total == b.total && a.seq > b.seq); }   // min-heap order
+  std::vector<Item> heap;
+  std::vector<std::pair<Entry*, int64_t>> order;
+  int64_t next_seq = 0;
+  size_t size() const { return heap.size(); }
+  double bottom_total() const { return heap.front().total; }
+  void push(Entry* e) {
+    e->leaf_seq = next_seq;
+    order.emplace_back(e, next_seq);
+    heap.push_back(Item{e->newp.total, next_seq, e});
+    std::push_heap(heap.begin(), heap.end(), above);
+    ++next_seq;
   }
-  void remove(Entry* e) { v.erase(std::find(v.begin(), v.end(), e)); }
+  // evicts the bottom and lists `e` in its place: one sift-down instead of a pop and a push
+  Entry* replace_bottom(Entry* e) {
+    Entry* ev = heap.front().e;
+    ev->leaf_seq = -1;
+    e->leaf_seq = next_seq;
+    order.emplace_back(e, next_seq);
+    const Item it{e->newp.total, next_seq++, e};
+    const size_t n = heap.size();
+    size_t i = 0;
+    for (;;) {
+      size_t l = 2 * i + 1, r = l + 1, m = l;
+      if (l >= n) break;
+      if (r < n && above(heap[l], heap[r])) m = r;       // the smaller child
+      if (!above(it, heap[m])) break;
+      heap[i] = heap[m];
+      i = m;
+    }
+    heap[i] = it;
+    return ev;
+  }
+  // listed entries in insertion order; clears the list
+  void drain(std::vector<Entry*>& out) {
+    out.clear();
+    for (auto& pr : order) if (pr.first->leaf_seq == pr.second) { out.push_back(pr.first); pr.first->leaf_seq = -1; }
+    order.clear(); heap.clear(); next_seq = 0;
+  }
 };
 
-void decode_one(const float* logits, int stride_t, int len, int C, int beam_width, int merge_repeated, int strip, int* out,
+// Per-thread working memory, reused from utterance to utterance: entries live in fixed chunks (stable addresses, no
+// allocation per entry), child tables in one growing pool.
+struct Scratch {
+  static constexpr int kChunkBits = 10;
+  std::vector<std::unique_ptr<Entry[]>> chunks;
+  int used = 0;
+  std::vector<int> kid_pool;                     // child tables, (C-1) slots each: entry index or -1
+  Leaves leaves;
+  std::vector<Entry*> branches;
+  std::vector<double> lp, lp_desc;
+  std::vector<int> by_lp;
+  Entry* at(int i) { return &chunks[i >> kChunkBits][i & ((1 << kChunkBits) - 1)]; }
+  int alloc() {
+    if ((size_t)(used >> kChunkBits) == chunks.size()) chunks.emplace_back(new Entry[1 << kChunkBits]);
+    Entry* e = at(used);
+    *e = Entry();
+    return used++;
+  }
+  void reset(int C) {
+    used = 0; kid_pool.clear();
+    leaves.order.clear(); leaves.heap.clear(); leaves.next_seq = 0;
+    lp.assign(C, 0.0); lp_desc.assign(C - 1, 0.0); by_lp.assign(C - 1, 0);
+  }
+};
+
+void decode_one(Scratch& S, const float* logits, int stride_t, int len, int C, int beam_width, int merge_repeated, int strip, int* out,
                 int max_out, int* out_len, float* log_prob) {
   const int blank = C - 1, nlab = C - 1;
-  std::deque<Entry> arena;                       // stable addresses
-  arena.emplace_back();
-  Entry* root = &arena[0];
+  S.reset(C);
+  std::vector<int>& kid_pool = S.kid_pool;
+  Entry* root = S.at(S.alloc());
   root->newp.total = 0.0; root->newp.blank = 0.0; root->newp.label = kLogZero;
-  Leaves leaves;
-  leaves.v.push_back(root);
-  std::vector<Entry*> branches;
-  std::vector<double> lp(C);
+  Leaves& leaves = S.leaves;
+  leaves.push(root);
+  std::vector<Entry*>& branches = S.branches;
+  std::vector<double>&lp = S.lp, &lp_desc = S.lp_desc;
+  std::vector<int>& by_lp = S.by_lp;
+  constexpr int kFewClasses = 16;
   for (int t = 0; t < len; ++t) {
     const float* row = logits + (size_t)t * stride_t;
-    double mx = row[0];
-    for (int c = 1; c < C; ++c) mx = std::max<double>(mx, row[c]);
+    double mx = kLogZero;
+    for (int c = 0; c < C; ++c) if (row[c] == row[c]) mx = std::max<double>(mx, row[c]);      // a NaN logit counts as -inf
     double se = 0.0;
-    for (int c = 0; c < C; ++c) se += std::exp((double)row[c] - mx);
+    for (int c = 0; c < C; ++c) if (row[c] == row[c]) se += std::exp((double)row[c] - mx);
     const double norm = mx + std::log(se);
-    for (int c = 0; c < C; ++c) lp[c] = (double)row[c] - norm;
+    for (int c = 0; c < C; ++c) lp[c] = (row[c] == row[c]) ? (double)row[c] - norm : kLogZero;
+    if (!(norm == norm)) for (int c = 0; c < C; ++c) lp[c] = kLogZero;                      // an all -inf / NaN row: nothing survives it
 
-    branches = leaves.v;
+    leaves.drain(branches);
     std::stable_sort(branches.begin(), branches.end(), [](const Entry* a, const Entry* b) { return a->newp.total > b->newp.total; });
-    leaves.v.clear();
     for (Entry* b : branches) b->oldp = b->newp;
     for (Entry* b : branches) {
       if (b->parent != nullptr) {
@@ -94,44 +161,87 @@ void decode_one(const float* logits, int stride_t, int len, int C, int beam_widt
       }
       b->newp.blank = b->oldp.total + lp[blank];
       b->newp.total = log_add(b->newp.blank, b->newp.label);
-      leaves.v.push_back(b);
+      leaves.push(b);
     }
-    auto is_candidate = [&](double total) {
-      return total > kLogZero && ((int)leaves.v.size() < beam_width || total > leaves.bottom()->newp.total);
-    };
+    // classes in descending order of lp: once the list is full, only a class with lp[c] > bottom - total(b) can enter it from
+    // branch b, and with peaked frames that is one or two classes instead of C-1
+    for (int c = 0; c < nlab; ++c) by_lp[c] = c;
+    std::sort(by_lp.begin(), by_lp.end(), [&](int a, int b) { return lp[a] > lp[b]; });
+    for (int c = 0; c < nlab; ++c) lp_desc[c] = lp[by_lp[c]];
+
+    const size_t width = (size_t)beam_width;
     for (Entry* b : branches) {
-      if (!is_candidate(b->oldp.total)) continue;
-      if (b->first_child < 0) {
-        b->first_child = (int)arena.size();
-        for (int c = 0; c < nlab; ++c) {
-          arena.emplace_back();
-          arena.back().parent = b;
-          arena.back().label = c;
+      const double btotal = b->oldp.total;
+      const bool full = leaves.size() >= width;
+      if (!(btotal > kLogZero && (!full || btotal > leaves.bottom_total()))) continue;
+      int few[kFewClasses];
+      int k = -1, pos = 0;                 // k >= 0: pruned visit of few[0..k), pos = index of the class being visited
+      // TF's per-class step, unchanged: an active child was re-scored above; otherwise the child (label c appended to b) is a
+      // candidate with lp[c] + P(b, not ending in c) and enters the list if it beats the bottom, evicting it when the list is full.
+      // A rejected child that exists is wiped -- which matters when it is a branch of THIS frame that an earlier insertion
+      // evicted: wiping its oldp is what stops the branch loop from expanding it later in the frame.
+      auto try_class = [&](int c) {
+        Entry* ch = (b->kids >= 0 && kid_pool[b->kids + c] >= 0) ? S.at(kid_pool[b->kids + c]) : nullptr;
+        if (ch != nullptr && ch->active()) return;
+        const double total = lp[c] + ((c == b->label) ? b->oldp.blank : btotal);
+        if (!(total > kLogZero && (leaves.size() < width || total > leaves.bottom_total()))) {
+          if (ch != nullptr) { ch->oldp.reset(); ch->newp.reset(); }
+          return;
         }
-      }
-      for (int c = 0; c < nlab; ++c) {
-        Entry* ch = &arena[b->first_child + c];
-        if (ch->active()) continue;
-        const double prev = (c == b->label) ? b->oldp.blank : b->oldp.total;
-        ch->newp.blank = kLogZero;
-        ch->newp.label = lp[c] + prev;
-        ch->newp.total = ch->newp.label;
-        if (is_candidate(ch->newp.total)) {
-          if ((int)leaves.v.size() == beam_width) {
-            Entry* bt = leaves.bottom();
-            bt->newp.reset();
-            leaves.remove(bt);
+        if (ch == nullptr) {
+          if (b->kids < 0) {
+            b->kids = (int)kid_pool.size();
+            kid_pool.resize(kid_pool.size() + nlab, -1);
           }
-          leaves.v.push_back(ch);
-        } else {
-          ch->oldp.reset();
-          ch->newp.reset();
+          const int idx = S.alloc();
+          kid_pool[b->kids + c] = idx;
+          ch = S.at(idx);
+          ch->parent = b;
+          ch->label = c;
         }
+        ch->newp.blank = kLogZero;
+        ch->newp.label = total;
+        ch->newp.total = total;
+        if (leaves.size() == width) {
+          Entry* ev = leaves.replace_bottom(ch);
+          ev->newp.reset();
+          if (ev->parent != nullptr) ev->parent->evicted_kid_frame = t;
+          if (k >= 0 && ev->parent == b && ev->label > c) {
+            // pruned visit: the full visit would still reach this child of b; if its class is not among the ones left to visit it
+            // can only be rejected there (it is outside the superset), i.e. wiped
+            bool later = false;
+            for (int i = pos + 1; i < k; ++i) later |= (few[i] == ev->label);
+            if (!later) ev->oldp.reset();
+          }
+        } else {
+          leaves.push(ch);
+        }
+      };
+      if (full && b->evicted_kid_frame != t) {
+        // superset of the classes that can still enter: the bottom only rises while this branch is expanded, and the repeated
+        // label uses oldp.blank <= oldp.total; the slack keeps the subtraction's rounding on the safe side (exact test in try_class).
+        // Not used when a child of b was evicted earlier in this frame: the full visit has to reach (and wipe or re-admit) it.
+        const double bt = leaves.bottom_total();
+        const double thr = (bt - btotal) - 1e-9 * (1.0 + std::fabs(bt) + std::fabs(btotal));
+        // lp_desc is descending: the count of elements >= thr
+        const int cnt = (int)(std::upper_bound(lp_desc.begin(), lp_desc.end(), thr, [](double v, double e) { return v > e; }) - lp_desc.begin());
+        if (cnt <= kFewClasses) k = cnt;
+      }
+      if (k < 0) {
+        for (int c = 0; c < nlab; ++c) try_class(c);
+      } else {
+        for (int i = 0; i < k; ++i) {                   // insertion sort into ascending class order: TF visits classes by index
+          int v = by_lp[i], j = i;
+          while (j > 0 && few[j - 1] > v) { few[j] = few[j - 1]; --j; }
+          few[j] = v;
+        }
+        for (pos = 0; pos < k; ++pos) try_class(few[pos]);
       }
     }
   }
-  Entry* best = leaves.v[0];
-  for (Entry* e : leaves.v) if (e->newp.total > best->newp.total) best = e;
+  leaves.drain(branches);
+  Entry* best = branches[0];
+  for (Entry* e : branches) if (e->newp.total > best->newp.total) best = e;
   std::vector<int> seq;
   for (Entry* e = best; e->parent != nullptr; e = e->parent) seq.push_back(e->label);
   int n = 0, prev = -1;
@@ -158,8 +268,9 @@ extern "C" int crnn_ctc_beam_search(const float* logits_host, const int* input_l
   int nt = num_threads > 0 ? num_threads : (int)std::thread::hardware_concurrency();
   nt = std::max(1, std::min(nt, N));
   auto work = [&](int tid) {
+    Scratch S;
     for (int n = tid; n < N; n += nt)
-      decode_one(logits_host + (size_t)n * C, N * C, input_len_host[n], C, beam_width, merge_repeated, strip,
+      decode_one(S, logits_host + (size_t)n * C, N * C, input_len_host[n], C, beam_width, merge_repeated, strip,
                  out_host + (size_t)n * T, T, out_len_host + n, neg_log_prob_host ? neg_log_prob_host + n : nullptr);
   };
   if (nt == 1) { work(0); return CRNN_OK; }

@@ -418,7 +418,13 @@ def beam_search_decode(logits, input_len, beam_width=100, merge_repeated=True, s
         leaves = [root]
         for t in range(int(input_len[n])):
             row = x[t, n]
-            lp = row - (row.max() + np.log(np.exp(row - row.max()).sum()))
+            # log-softmax in double with a SEQUENTIAL sum (not numpy's pairwise one): on frames with exactly tied scores the
+            # decode depends on the last bit of the normaliser, and this is the arithmetic the product decoder states too
+            mx = float(row.max())
+            se = 0.0
+            for v in row:
+                se += math.exp(float(v) - mx)
+            lp = row - (mx + math.log(se))
             branches = sorted(leaves, key=lambda b: -b.new[0])
             leaves = []
             for b in branches:
@@ -433,30 +439,46 @@ def beam_search_decode(logits, input_len, beam_width=100, merge_repeated=True, s
                 b.new[0] = lse(b.new[1], b.new[2])
                 leaves.append(b)
             bottom = lambda: min(leaves, key=lambda e: e.new[0])
+
+            state = {"bot": bottom().new[0]}              # total of the bottom, refreshed whenever the list changes
+
+            def is_candidate(total):
+                return total > -np.inf and (len(leaves) < beam_width or total > state["bot"])
+            # CTCBeamSearchDecoder::Step's "grow new leaves" loop visits EVERY child of a candidate branch in class order, and
+            # the visit order is observable: a branch that an insertion evicted earlier in this frame is still expanded when the
+            # loop reaches it (its `old` survives the eviction) unless its parent's visit came first and rejected -- i.e. wiped
+            # -- it.  Restated without the C-1 visits per branch: a child object exists only once it has entered the beam
+            # (`children` is a dict), a child that never did has nothing to wipe, so the visit covers the classes that can still
+            # enter (total above the bottom as of the start of the visit: the bottom only rises) plus every existing child.
             for b in branches:
-                def is_candidate(total):
-                    return total > -np.inf and (len(leaves) < beam_width or total > bottom().new[0])
                 if not is_candidate(b.old[0]):
                     continue
                 if b.children is None:
-                    b.children = [_Beam(b, c) for c in range(C - 1)]
+                    b.children = {}
                 base = np.full(C - 1, b.old[0])
                 if 0 <= b.label < C - 1:
                     base[b.label] = b.old[1]
                 cand = base + lp[:C - 1]
-                thr = -np.inf if len(leaves) < beam_width else bottom().new[0]
-                for c in np.nonzero(cand > thr)[0] if len(leaves) >= beam_width else range(C - 1):
-                    ch = b.children[int(c)]
-                    if ch.active():
+                if len(leaves) < beam_width:
+                    visit = range(C - 1)
+                else:
+                    visit = sorted(set(np.nonzero(cand > state["bot"])[0].tolist()) | set(b.children))
+                for c in visit:
+                    ch = b.children.get(c)
+                    if ch is not None and ch.active():
                         continue
-                    ch.new = [cand[c], -np.inf, cand[c]]
-                    if is_candidate(ch.new[0]):
+                    total = float(cand[c])
+                    if is_candidate(total):
+                        if ch is None:
+                            ch = b.children[c] = _Beam(b, c)
+                        ch.new = [total, -np.inf, total]
                         if len(leaves) == beam_width:
                             bt = bottom()
                             bt.new = [-np.inf, -np.inf, -np.inf]
                             leaves.remove(bt)
                         leaves.append(ch)
-                    else:
+                        state["bot"] = bottom().new[0]
+                    elif ch is not None:
                         ch.old = [-np.inf, -np.inf, -np.inf]
                         ch.new = [-np.inf, -np.inf, -np.inf]
         best = max(leaves, key=lambda e: e.new[0])

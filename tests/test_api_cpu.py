@@ -273,6 +273,33 @@ def test_beam_search_matches_oracle_restatement(kind, seed):
     assert _beam(x, il, beam_width=3)[0] == O.beam_search_decode(x, il, beam_width=3)
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_beam_search_ties_and_narrow_beams_match_oracle(seed):
+    """The decoder keeps the beam in a heap, visits only the classes that can still enter a full list and creates children on
+    demand; TF's results depend on visiting ORDER (which of several equal totals is the bottom, a branch evicted mid-frame
+    still being expanded unless its parent's visit wipes it), so the restatement is compared on the inputs where order shows:
+    quantised logits (exact ties), all-equal frames, few classes, beam widths 1..7 that evict constantly, both merge modes."""
+    from oracle import crnn_oracle as O
+    rng = np.random.default_rng(100 + seed)
+    C = int(rng.choice([3, 6, 17]))
+    T, N = int(rng.integers(4, 15)), 8
+    kind = seed % 3
+    if kind == 0:
+        x = np.round(rng.standard_normal((T, N, C)) * 2) / 2
+    elif kind == 1:
+        x = rng.integers(0, 2, size=(T, N, C)).astype(np.float64) * float(rng.choice([1, 5]))
+        x[T // 2] = 0.0                                           # an all-equal frame
+    else:
+        x = rng.standard_normal((T, N, C)) * float(rng.choice([0.3, 3.0]))
+    x = x.astype(np.float32)
+    il = rng.integers(0, T + 1, size=N).astype(np.int32)
+    il[0] = T
+    for bw in (1, 2, 3, 5, 7, 100):
+        for merge in (True, False):
+            ref = O.beam_search_decode(x, il, beam_width=bw, merge_repeated=merge, strip=-1)
+            assert _beam(x, il, beam_width=bw, merge_repeated=merge, strip=-1)[0] == ref, (C, T, bw, merge)
+
+
 def test_beam_search_reproduces_tensorflows_own_known_answer():
     """crnn_ctc_beam_search on the vector TensorFlow's ctc_decoder_ops_test.py::testCTCDecoderBeamSearch pins
     (tests/golden/third_party_kats.py): top path [1, 0] at beam_width 2 (6 classes, blank 5, unnormalised log p + 2), the
