@@ -280,7 +280,14 @@ def ctc_loss_np(logits, flat_labels, label_len, input_len, blank=CTC_BLANK, want
     """Explicit alpha/beta restatement in float64 numpy.
 
     logits [T,N,C] unnormalised.  Returns (costs [N], grad [T,N,C]) where
-    grad = d costs[n] / d logits[:,n,:] (what warp-ctc stores as its 2nd output)."""
+    grad = d costs[n] / d logits[:,n,:] (what warp-ctc stores as its 2nd output).
+
+    Defined deviation in the deep tail [upstream-memory]: warp-ctc forms the softmax PROBABILITIES in float first and takes
+    their log inside the recursion, so a class more than ~87-103 below its frame's maximum underflows to probability 0 and
+    a labelling that needs it costs +inf (its tests/test_cpu.cpp::inf_test sets a label's activations to -1e30 and expects
+    exactly that, with a NaN-free gradient).  This restatement -- and the product kernels -- stay in log space (log-softmax
+    = x - logsumexp), where the same labelling gets its finite -log p (2e30 in that test's setting).  Identical wherever no
+    needed probability underflows float, i.e. for any logits a trained model of this path produces."""
     x = np.asarray(logits, dtype=np.float64)
     T, N, C = x.shape
     flat_labels = np.asarray(flat_labels).astype(np.int64)
