@@ -14,6 +14,7 @@
 // the label sequence of the best entry, with consecutive equal labels collapsed when merge_repeated is set (TF applies that to
 // the decoded sequence, so "a, blank, a" also comes out as one "a").
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <limits>
@@ -267,15 +268,29 @@ extern "C" int crnn_ctc_beam_search(const float* logits_host, const int* input_l
     if (input_len_host[n] < 0 || input_len_host[n] > T) return crnn_fail(CRNN_INVALID_VALUE, "beam_search: input_len[%d] outside [0, T]", n);
   int nt = num_threads > 0 ? num_threads : (int)std::thread::hardware_concurrency();
   nt = std::max(1, std::min(nt, N));
-  auto work = [&](int tid) {
-    Scratch S;
-    for (int n = tid; n < N; n += nt)
-      decode_one(S, logits_host + (size_t)n * C, N * C, input_len_host[n], C, beam_width, merge_repeated, strip,
-                 out_host + (size_t)n * T, T, out_len_host + n, neg_log_prob_host ? neg_log_prob_host + n : nullptr);
+  // utterances are handed out one at a time (ragged lengths: a static split leaves threads idle); nothing may throw across the ABI
+  std::atomic<int> next{0};
+  std::atomic<bool> failed{false};
+  auto work = [&]() {
+    try {
+      Scratch S;
+      for (int n = next.fetch_add(1); n < N && !failed.load(std::memory_order_relaxed); n = next.fetch_add(1))
+        decode_one(S, logits_host + (size_t)n * C, N * C, input_len_host[n], C, beam_width, merge_repeated, strip,
+                   out_host + (size_t)n * T, T, out_len_host + n, neg_log_prob_host ? neg_log_prob_host + n : nullptr);
+    } catch (...) {
+      failed.store(true);
+    }
   };
-  if (nt == 1) { work(0); return CRNN_OK; }
-  std::vector<std::thread> th;
-  for (int i = 0; i < nt; ++i) th.emplace_back(work, i);
-  for (auto& t : th) t.join();
+  if (nt == 1) {
+    work();
+  } else {
+    std::vector<std::thread> th;
+    try {
+      for (int i = 0; i < nt - 1; ++i) th.emplace_back(work);
+    } catch (...) {}                                   // fewer helper threads than asked for: the caller's thread still drains the queue
+    work();
+    for (auto& t : th) t.join();
+  }
+  if (failed.load()) return crnn_fail(CRNN_INVALID_VALUE, "beam_search: out of host memory");
   return CRNN_OK;
 }
