@@ -17,6 +17,11 @@ Provenance [upstream-memory -- transcribed, not fetched: there is no network]:
     weight 0.5, zero biases, forget_bias 1.0, input [1, 1], every state entry 0.1; state_is_tuple=False packs [c, h] per layer).
     Uniform weights cannot tell gate ORDER apart; they pin the cell equations and the forget bias.
 
+  * CONV / POOL / CLIP: tensorflow/python/kernel_tests/conv_ops_test.py::testConv2D1x1Filter and ::testConv2D2x2Filter (NHWC input
+    [1,2,3,3] = 1..18, HWIO filters 1..9 / 1..36, stride 1, VALID -- the layout conventions of the checkpoint's conv kernels and
+    conv5's 2x2 VALID case, network.py:160-182), pooling_ops_test.py::_testMaxPoolValidPadding ([1,3,3,3] = 1..27, 2x2 / stride 2
+    VALID), clip_ops_test.py::testClipByGlobalNormClipped / NotClipped (lib/lstm/train.py:82).
+
 Self-check of the transcription: `tests/test_oracle.py::test_third_party_known_answers_*` recomputes the two losses from the
 matrices with an fp64 alpha recursion and gets 3.342113 and 5.422622 -- six matching digits on values nobody could guess --
 and all 60 gradient entries to 1e-6; a mis-remembered digit anywhere in a matrix would break both."""
@@ -126,3 +131,20 @@ LSTM_STATE0 = 0.1                                   # every entry of [c1, h1, c2
 LSTM_WEIGHT = 0.5                                   # constant_initializer(0.5) for both [4, 8] matrices; biases 0
 LSTM_OUT = np.asarray([[0.24024698, 0.24024698]])
 LSTM_STATE = np.asarray([[0.68967271, 0.68967271, 0.44848421, 0.44848421, 0.39897051, 0.39897051, 0.24024698, 0.24024698]])
+
+
+# ---- conv_ops_test.py::testConv2D1x1Filter / testConv2D2x2Filter, pooling_ops_test.py::_testMaxPoolValidPadding --------------
+CONV_INPUT_NHWC = np.arange(1, 19, dtype=np.float64).reshape(1, 2, 3, 3)
+CONV_1X1_FILTER_HWIO = np.arange(1, 10, dtype=np.float64).reshape(1, 1, 3, 3)
+CONV_1X1_EXPECTED = [30.0, 36.0, 42.0, 66.0, 81.0, 96.0, 102.0, 126.0, 150.0, 138.0, 171.0, 204.0, 174.0, 216.0, 258.0, 210.0, 261.0, 312.0]
+CONV_2X2_FILTER_HWIO = np.arange(1, 37, dtype=np.float64).reshape(2, 2, 3, 3)
+CONV_2X2_EXPECTED = [2271.0, 2367.0, 2463.0, 2901.0, 3033.0, 3165.0]         # VALID, stride 1 -> [1,1,2,3]
+POOL_INPUT_NHWC = np.arange(1, 28, dtype=np.float64).reshape(1, 3, 3, 3)
+POOL_2X2_S2_VALID_EXPECTED = [13.0, 14.0, 15.0]
+
+# ---- clip_ops_test.py::testClipByGlobalNormClipped / testClipByGlobalNormNotClipped ----------------------------------------------
+CLIP_X0 = np.asarray([[-2.0, 0.0, 0.0], [4.0, 0.0, 0.0]])
+CLIP_X1 = np.asarray([1.0, -2.0])
+CLIP_GLOBAL_NORM = 5.0
+CLIP_AT_4 = (np.asarray([[-1.6, 0.0, 0.0], [3.2, 0.0, 0.0]]), np.asarray([0.8, -1.6]))       # clip_norm 4.0
+CLIP_AT_6 = (CLIP_X0, CLIP_X1)                                                               # clip_norm 6.0: unchanged

@@ -288,3 +288,21 @@ def test_third_party_known_answer_lstm_cell():
     c2, h2 = O.lstm_cell(h1, s0, s0, w, b)
     assert np.allclose(h2.numpy(), K.LSTM_OUT, rtol=0, atol=2e-7)
     assert np.allclose(torch.cat([c1, h1, c2, h2], 1).numpy(), K.LSTM_STATE, rtol=0, atol=2e-7)
+
+
+def test_third_party_known_answers_conv_pool_layouts_and_global_norm_clip():
+    """TensorFlow's conv2d (NHWC x HWIO, VALID: conv5's kind and the checkpoint's kernel layout), max_pool and
+    clip_by_global_norm known answers against the oracle's conv_single / pooling call / clip_by_global_norm."""
+    K = _kats()
+    x = torch.tensor(K.CONV_INPUT_NHWC).permute(0, 3, 1, 2)                      # the oracle computes in NCHW
+    zero = torch.zeros(3, dtype=torch.float64)
+    for w, want in ((K.CONV_1X1_FILTER_HWIO, K.CONV_1X1_EXPECTED), (K.CONV_2X2_FILTER_HWIO, K.CONV_2X2_EXPECTED)):
+        y, _ = O.conv_single(x, torch.tensor(w), zero, bn=None, relu=False, padding="VALID")
+        assert y.permute(0, 2, 3, 1).reshape(-1).tolist() == want
+    xp = torch.tensor(K.POOL_INPUT_NHWC).permute(0, 3, 1, 2)
+    assert F.max_pool2d(xp, (2, 2), (2, 2)).permute(0, 2, 3, 1).reshape(-1).tolist() == K.POOL_2X2_S2_VALID_EXPECTED
+    g = {"x0": torch.tensor(K.CLIP_X0), "x1": torch.tensor(K.CLIP_X1)}
+    for clip, want in ((4.0, K.CLIP_AT_4), (6.0, K.CLIP_AT_6)):
+        out, gn = O.clip_by_global_norm(g, clip=clip)
+        assert gn == K.CLIP_GLOBAL_NORM
+        assert np.allclose(out["x0"].numpy(), want[0], rtol=0, atol=1e-15) and np.allclose(out["x1"].numpy(), want[1], rtol=0, atol=1e-15)
