@@ -19,7 +19,11 @@ own call sites.  What it IS pinned to (``tests/test_oracle.py``):
   * independent implementations for everything else (torch ``F.ctc_loss``,
     ``torch.nn.LSTM`` with permuted gates, ``F.batch_norm``, brute-force CTC
     path enumeration, fp64 finite differences through the whole graph).
-The conv / BN / LSTM / Adam restatements have no externally held vector.
+  * TensorFlow's small known answers for the LSTM cell step (rnn_cell_test
+    testBasicLSTMCell), conv2d NHWC x HWIO / max_pool (conv_ops_test,
+    pooling_ops_test) and clip_by_global_norm (clip_ops_test): equations and
+    layouts, not the network's sizes.
+BatchNorm and Adam have no externally held vector.
 
 Reference call sites restated (paths relative to /root/reference):
   * topology / hyper-parameters ......... lib/networks/LSTM_train.py:22-38
