@@ -475,3 +475,28 @@ def test_bench_reference_arm_prints_the_contract_line_and_ours_refuses_without_a
     if not torch.cuda.is_available():
         p = subprocess.run([sys.executable, bench, "--steps", "1", "--warmup", "1"], capture_output=True, text=True, env=env, timeout=600)
         assert p.returncode != 0 and "no CPU fallback" in (p.stderr + p.stdout)
+
+
+def build_c_abi_smoke(tmp_path):
+    """gcc -std=c99 tests/c_abi/abi_smoke.c against include/crnn_ctc.h and the in-tree libcrnnctc.so; returns the binary's path."""
+    import subprocess
+    from lstm_ctc_ocr_b200 import _lib
+    _lib.load()                                                     # builds the library if it is stale
+    libdir = os.path.join(ROOT, "lstm_ctc_ocr_b200")
+    exe = str(tmp_path / "abi_smoke")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c_abi", "abi_smoke.c"), "-o", exe, "-L" + libdir, "-lcrnnctc", "-lm", "-Wl,-rpath," + libdir]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-3000:]
+    return exe
+
+
+def test_c_abi_is_usable_from_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: a C99 translation unit that includes only include/crnn_ctc.h compiles warning-free,
+    links against libcrnnctc.so and drives the GPU-free entry points (status strings, host beam search on TensorFlow's known
+    answer, host copy pool); crnn_model_create fails with a status + message where there is no CUDA device."""
+    import subprocess
+    import torch
+    exe = build_c_abi_smoke(tmp_path)
+    p = subprocess.run([exe] + (["--gpu"] if torch.cuda.is_available() else []), capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "FAIL" not in p.stdout and p.stdout.count("ok ") >= 8, p.stdout + p.stderr

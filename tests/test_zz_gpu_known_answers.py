@@ -56,3 +56,20 @@ def test_greedy_kernel_reproduces_the_tensorflow_known_answer():
                                      tf_blank=63, strip=0)
     out = out.cpu().numpy(); out_len = out_len.cpu().numpy()
     assert [out[n, :out_len[n]].tolist() for n in range(2)] == [[1], [1, 1]]
+
+
+def test_c_abi_from_plain_c_creates_the_model_on_the_gpu(tmp_path):
+    """tests/c_abi/abi_smoke.c (C99, includes only include/crnn_ctc.h) run with --gpu: besides the GPU-free checks of the CPU
+    suite it creates the model through the C ABI -- no Python, no torch in that process -- and reads back 24 trainable tensors
+    / 7 158 592 parameters."""
+    import subprocess
+    from lstm_ctc_ocr_b200 import _lib
+    _lib.load()
+    libdir = os.path.join(ROOT, "lstm_ctc_ocr_b200")
+    exe = str(tmp_path / "abi_smoke")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c_abi", "abi_smoke.c"), "-o", exe, "-L" + libdir, "-lcrnnctc", "-lm", "-Wl,-rpath," + libdir]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-3000:]
+    p = subprocess.run([exe, "--gpu"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "FAIL" not in p.stdout, p.stdout + p.stderr
