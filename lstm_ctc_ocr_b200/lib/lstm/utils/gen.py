@@ -84,18 +84,66 @@ def _font(size=42):
     return _FONT_CACHE[key]
 
 
+_GLYPHS = {}          # font cache key -> {"adv": {ch: int}, "mask": {ch: (core mask, (ox, oy))}, "fast": True | False}
+
+
+def _glyphs(font):
+    """Per-font cache of what ImageDraw.text recomputes for every character it draws: the advance and the anti-aliased glyph
+    mask + offset (FreeType rasterisation is ~85 % of a rendered line).  The cached path draws with the same primitive
+    ImageDraw.text ends in (`draw_bitmap(xy + offset, mask, ink)`), and is switched on only after it reproduced ImageDraw.text
+    byte for byte on a probe line in this process -- otherwise (another Pillow, no getmask2) the plain path stays."""
+    g = _GLYPHS.get(id(font))
+    if g is None:
+        g = _GLYPHS[id(font)] = {"adv": {}, "mask": {}, "fast": False, "font": font}
+        try:
+            from PIL import Image, ImageDraw
+            probe = "Wg0jQy8"
+            a = Image.new("L", (260, 60), color=200); da = ImageDraw.Draw(a)
+            b = Image.new("L", (260, 60), color=200); db = ImageDraw.Draw(b)
+            x = 3
+            for i, ch in enumerate(probe):
+                da.text((x, i), ch, font=font, fill=10 * i)
+                _draw_glyph(db, g, font, ch, x, i, 10 * i)
+                x += 33
+            g["fast"] = a.tobytes() == b.tobytes()
+        except Exception:
+            g["fast"] = False
+    return g
+
+
+def _draw_glyph(d, g, font, ch, x, y, fill):
+    m = g["mask"].get(ch)
+    if m is None:
+        m = g["mask"][ch] = font.getmask2(ch, d.fontmode, anchor="la", start=(0.0, 0.0))
+    mask, off = m
+    d.draw.draw_bitmap((x + off[0], y + off[1]), mask, d.draw.draw_ink(fill))
+
+
 def render_line(chars, height=60, width=None, rng=random):
     """Gray uint8 HxW image of the text (stand-in for ImageCaptcha.generate_image + gray conversion, gen.py:31-37,79)."""
     from PIL import Image, ImageDraw
     font = _font(42)
-    adv = [int(font.getlength(c)) for c in chars]
+    g = _glyphs(font)
+    advc = g["adv"]
+    adv = []
+    for c in chars:
+        a = advc.get(c)
+        if a is None:
+            a = advc[c] = int(font.getlength(c))
+        adv.append(a)
     if width is None:                      # wide enough for the text: batches then mix widths (exercises the padding contract)
         width = sum(adv) + 28
     img = Image.new("L", (width, height), color=rng.randint(180, 255))
     d = ImageDraw.Draw(img)
     x = rng.randint(2, 12)
+    fast = g["fast"]
     for ch, a in zip(chars, adv):
-        d.text((x, rng.randint(0, 10)), ch, font=font, fill=rng.randint(0, 90))
+        y = rng.randint(0, 10)
+        fill = rng.randint(0, 90)
+        if fast:
+            _draw_glyph(d, g, font, ch, x, y, fill)
+        else:
+            d.text((x, y), ch, font=font, fill=fill)
         x += a + rng.randint(-2, 3)
     return np.asarray(img, dtype=np.uint8)
 
@@ -120,12 +168,11 @@ def groupBatch(imgs, labels, pad_to=None):
         if max_w > pad_to:
             raise ValueError(f"line of width {max_w} does not fit the bucket width {pad_to}")
         max_w = int(pad_to)
-    batch = []
-    for im in resized:
-        pad = np.zeros((nh, max_w), np.float32)
-        pad[:, :im.shape[1]] = im / 255.0
-        batch.append(np.ascontiguousarray(pad.swapaxes(0, 1)).reshape(-1, cfg.NUM_FEATURES))
-    return batch, label_vec, label_len, time_steps
+    # one zero-filled [N, W, 32] block, every line written transposed into its rows; the list holds its N contiguous [W, 32] views
+    block = np.zeros((len(resized), max_w, nh), np.float32)
+    for i, im in enumerate(resized):
+        np.divide(im.T, np.float32(255.0), out=block[i, :im.shape[1], :])
+    return list(block), label_vec, label_len, time_steps
 
 
 def batch_seed(k, seed=None, rank=0, world=1):
