@@ -500,3 +500,38 @@ def test_c_abi_is_usable_from_plain_c(tmp_path):
     exe = build_c_abi_smoke(tmp_path)
     p = subprocess.run([exe] + (["--gpu"] if torch.cuda.is_available() else []), capture_output=True, text=True, timeout=300)
     assert p.returncode == 0 and "FAIL" not in p.stdout and p.stdout.count("ok ") >= 8, p.stdout + p.stderr
+
+
+def test_ctypes_binding_matches_the_header_prototypes():
+    """Every prototype of include/crnn_ctc.h against the argtypes / restype table of lstm_ctc_ocr_b200/_lib.py: same set of names,
+    same number of parameters, and per parameter the same class (pointer / int / float / size_t / int64) -- a drifted binding would
+    otherwise only show up as garbage arguments on the GPU box."""
+    import ctypes
+    from lstm_ctc_ocr_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "crnn_ctc.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"typedef\s+\w[\w\s\*]*\(\s*\*\s*\w+\s*\)\s*\([^;]*\)\s*;", "", src)         # callback typedefs are not entry points
+    protos = dict((m.group(2), (m.group(1).strip(), m.group(3))) for m in
+                  re.finditer(r"(?m)^\s*((?:const\s+)?[\w]+\s*\**)\s*(crnn_[a-z0-9_]+)\s*\(([^;{]*)\)\s*;", src))
+    assert set(protos) == set(_lib.SIGNATURES), sorted(set(protos) ^ set(_lib.SIGNATURES))
+
+    def kind_of_c(decl):
+        decl = decl.strip()
+        if "*" in decl or "[" in decl or re.search(r"\b(crnn_stream_t|crnn_\w+_fn)\b", decl):
+            return "ptr"
+        base = re.sub(r"\bconst\b", "", decl).split()
+        t = base[0] if base else decl
+        return {"int": "int", "float": "float", "size_t": "size_t", "int64_t": "int64"}.get(t, t)
+
+    def kind_of_ctypes(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or isinstance(t, type(ctypes.POINTER(ctypes.c_int))) and issubclass(t, ctypes._Pointer):
+            return "ptr"
+        return {ctypes.c_int: "int", ctypes.c_float: "float", ctypes.c_size_t: "size_t", ctypes.c_int64: "int64"}[t]
+
+    for name, (ret, params) in protos.items():
+        res, args = _lib.SIGNATURES[name]
+        plist = [p for p in (q.strip() for q in params.split(",")) if p and p != "void"]
+        assert len(plist) == len(args), (name, plist, args)
+        for i, (p, a) in enumerate(zip(plist, args)):
+            assert kind_of_c(p) == kind_of_ctypes(a), (name, i, p, a)
+        assert kind_of_c(ret + " x") == kind_of_ctypes(res), (name, ret, res)
