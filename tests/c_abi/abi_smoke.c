@@ -4,6 +4,7 @@
  * testCTCDecoderBeamSearch vector (tests/golden/third_party_kats.py), the host copy pool, and the loud failure of
  * crnn_model_create on a box without a CUDA device.  Prints one "ok ..." line per check; exit code 0 only if all hold. */
 #include <math.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -19,6 +20,10 @@ static int failures = 0;
 
 int main(int argc, char** argv) {
   const int expect_gpu = (argc > 1 && strcmp(argv[1], "--gpu") == 0);
+  /* struct layout as this C compiler sees it; the Python test compares it with the ctypes mirror (lstm_ctc_ocr_b200/_lib.py) */
+  printf("layout crnn_config %u %u %u %u %u %u %u\n", (unsigned)sizeof(crnn_config), (unsigned)offsetof(crnn_config, img_height),
+         (unsigned)offsetof(crnn_config, nclasses), (unsigned)offsetof(crnn_config, num_hid), (unsigned)offsetof(crnn_config, bn_eps),
+         (unsigned)offsetof(crnn_config, weight_decay), (unsigned)offsetof(crnn_config, compute_dtype));
   CHECK(crnn_version() > 0, "crnn_version");
   CHECK(strlen(crnn_status_string(CRNN_OK)) > 0 && strcmp(crnn_status_string(CRNN_OK), crnn_status_string(CRNN_INVALID_VALUE)) != 0,
         "crnn_status_string");

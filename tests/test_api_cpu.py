@@ -500,6 +500,11 @@ def test_c_abi_is_usable_from_plain_c(tmp_path):
     exe = build_c_abi_smoke(tmp_path)
     p = subprocess.run([exe] + (["--gpu"] if torch.cuda.is_available() else []), capture_output=True, text=True, timeout=300)
     assert p.returncode == 0 and "FAIL" not in p.stdout and p.stdout.count("ok ") >= 8, p.stdout + p.stderr
+    # crnn_config as the C compiler lays it out == the ctypes mirror the Python side passes to crnn_model_create
+    from lstm_ctc_ocr_b200._lib import CrnnConfig
+    import ctypes
+    layout = [int(v) for v in next(l for l in p.stdout.splitlines() if l.startswith("layout crnn_config")).split()[2:]]
+    assert layout == [ctypes.sizeof(CrnnConfig)] + [getattr(CrnnConfig, f).offset for f, _ in CrnnConfig._fields_], layout
 
 
 def test_ctypes_binding_matches_the_header_prototypes():
