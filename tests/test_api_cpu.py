@@ -72,6 +72,68 @@ def test_factory_contract():
         te.build_loss()                      # LSTM_test has no 'labels' layer (reference: get_output raises)
 
 
+def test_reference_style_setup_chain_declares_the_compiled_network_and_anything_else_fails_loudly():
+    """A `setup()` written in the reference's layer DSL (the chain of lib/networks/LSTM_train.py:22-38: feed / conv_single /
+    max_pool / reshape_squeeze_layer / bi_lstm with the reference's argument order, defaults and names) runs unchanged on this
+    Network and yields the same layer table as the shipped classes; a chain that differs from the topology compiled into
+    libcrnnctc.so -- another width, a missing pool, a dropout, an off-path layer -- raises instead of computing something else."""
+    from lstm_ctc_ocr_b200.lib.lstm.config import cfg
+    from lstm_ctc_ocr_b200.lib.networks.LSTM_train import LSTM_train
+    from lstm_ctc_ocr_b200.lib.networks.network import UnsupportedGraph
+    from lstm_ctc_ocr_b200.lib.networks.factory import get_network
+
+    def chain(net, conv2_out=128, with_pool3=True, pad5="VALID"):
+        c = (net.feed("data")
+             .conv_single(3, 3, 64, 1, 1, name="conv1", c_i=cfg.NCHANNELS)
+             .max_pool(2, 2, 2, 2, padding="VALID", name="pool1")
+             .conv_single(3, 3, conv2_out, 1, 1, name="conv2")
+             .max_pool(2, 2, 2, 2, padding="VALID", name="pool2")
+             .conv_single(3, 3, 256, 1, 1, name="conv3_1")
+             .conv_single(3, 3, 256, 1, 1, name="conv3_2")
+             .max_pool(1, 2, 1, 2, padding="VALID", name="pool2")
+             .conv_single(3, 3, 512, 1, 1, name="conv4_1", bn=True)
+             .conv_single(3, 3, 512, 1, 1, name="conv4_2", bn=True))
+        if with_pool3:
+            c = c.max_pool(1, 2, 1, 2, padding="VALID", name="pool3")
+        c.conv_single(2, 2, 512, 1, 1, padding=pad5, name="conv5", relu=False).reshape_squeeze_layer(d=512, name="reshaped_layer")
+        net.feed("reshaped_layer", "time_step_len").bi_lstm(cfg.TRAIN.NUM_HID, cfg.TRAIN.NUM_LAYERS, name="logits")
+
+    class Mine(LSTM_train):
+        variant = {}
+
+        def setup(self):
+            chain(self, **self.variant)
+
+    net = Mine()
+    ref = get_network("LSTM_train")
+    assert sorted(net.layers) == sorted(ref.layers) and [op for op, _ in net._declared] == [op for op, _ in ref._declared]
+    assert net._declared == ref._declared
+    loss, dense = net.build_loss()
+    assert loss.kind == "loss" and dense.kind == "dense_decoded" and net.get_output("logits").kind == "logits"
+    for variant in (dict(conv2_out=96), dict(with_pool3=False), dict(pad5="SAME")):
+        Mine.variant = variant
+        with pytest.raises(UnsupportedGraph):
+            Mine()
+    Mine.variant = {}
+
+    class Short(LSTM_train):
+        def setup(self):
+            self.feed("data").conv_single(3, 3, 64, 1, 1, name="conv1", c_i=cfg.NCHANNELS)
+    with pytest.raises(UnsupportedGraph):
+        Short().build_loss()                                         # a chain that stops early cannot be run
+    n = get_network("LSTM_test")
+    with pytest.raises(UnsupportedGraph):
+        n.feed("conv5").dropout(0.5, name="dropout_layer")           # LSTM_train.py:35 is commented out in the reference
+    with pytest.raises(UnsupportedGraph):
+        n.feed("conv5").fc(10, name="fc")                            # off-path layer of the reference's DSL
+    with pytest.raises(AttributeError):
+        n.not_a_layer
+    with pytest.raises(RuntimeError):
+        n2 = get_network("LSTM_test"); n2.inputs = []; n2.max_pool(2, 2, 2, 2, name="p")   # no input fed (network.py:24-25)
+    with pytest.raises(AssertionError):
+        get_network("LSTM_test").feed("data").conv_single(3, 3, 64, 1, 1, name="conv1", c_i=1, padding="FULL")
+
+
 def test_config_merge_and_set(tmp_path):
     from lstm_ctc_ocr_b200.lib.lstm import config as C
     assert C.cfg.NCLASSES == 64 and C.cfg.TRAIN.NUM_HID == 512 and C.cfg.POOL_SCALE == 4
