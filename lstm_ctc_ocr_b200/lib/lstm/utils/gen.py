@@ -148,6 +148,13 @@ def render_line(chars, height=60, width=None, rng=random):
     return np.asarray(img, dtype=np.uint8)
 
 
+def generateImg(rng=random):
+    """(gray uint8 image, its characters): the reference's per-sample entry (gen.py:29-35; it returns the captcha's RGB array and
+    converts to gray in the generator, gen.py:79 -- here the line is rendered gray directly)."""
+    theChars = gen_rand(rng)
+    return render_line(theChars, rng=rng), theChars
+
+
 def groupBatch(imgs, labels, pad_to=None):
     """Resize to height 32 keeping aspect, time_step = nw//4 - 1, right-pad with 0 to a multiple of 4 (or to ``pad_to``), /255,
     transpose to [W, 32] (gen.py:41-67)."""
