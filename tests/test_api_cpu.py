@@ -602,3 +602,20 @@ def test_ctypes_binding_matches_the_header_prototypes():
         for i, (p, a) in enumerate(zip(plist, args)):
             assert kind_of_c(p) == kind_of_ctypes(a), (name, i, p, a)
         assert kind_of_c(ret + " x") == kind_of_ctypes(res), (name, ret, res)
+
+
+def test_warpctc_tensorflow_import_name_resolves_to_the_drop_in():
+    """`import warpctc_tensorflow` (the reference's binding import, network.py:6) finds the shim at the repository root; `ctc`
+    takes the reference's keyword names (network.py:653-654) and refuses to run without a GPU instead of falling back."""
+    import inspect
+    import torch
+    import warpctc_tensorflow
+    from lstm_ctc_ocr_b200 import warpctc
+    from lstm_ctc_ocr_b200._lib import CrnnError
+    assert warpctc_tensorflow.ctc is warpctc.ctc
+    params = list(inspect.signature(warpctc_tensorflow.ctc).parameters)
+    assert params == ["activations", "flat_labels", "label_lengths", "input_lengths", "blank_label"]
+    assert inspect.signature(warpctc_tensorflow.ctc).parameters["blank_label"].default == 0
+    if not torch.cuda.is_available():
+        with pytest.raises(CrnnError):
+            warpctc_tensorflow.ctc(activations=np.zeros((3, 1, 64), np.float32), flat_labels=[1], label_lengths=[1], input_lengths=[3])
